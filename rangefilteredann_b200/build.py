@@ -1,0 +1,72 @@
+"""Builds the two native artefacts of the package, in-tree:
+
+  libwsann_cuda.so                 nvcc, sm_100a only  (csrc/wsann.cu: kernels + C ABI)
+  window_ann.cpython-*.so          g++ + pybind11      (csrc/host/python_bindings.cpp)
+
+Both land next to this file so they travel with the repo snapshot.  nvcc cross-compiles
+without a GPU.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import sysconfig
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libwsann_cuda.so")
+EXT = os.path.join(HERE, "window_ann" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+
+def _newer(target: str, sources: list[str]) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _sources(*dirs: str) -> list[str]:
+    out = []
+    for d in dirs:
+        for root, _, files in os.walk(d):
+            out += [os.path.join(root, f) for f in files if f.endswith((".cu", ".cuh", ".h", ".hpp", ".cpp"))]
+    return out
+
+
+def build_cuda(force: bool = False, verbose: bool = False) -> str:
+    srcs = _sources(CSRC, os.path.join(os.path.dirname(HERE), "include"))
+    if not force and _newer(LIB, srcs):
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, os.path.join(CSRC, "wsann.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+def build_bindings(force: bool = False) -> str:
+    import pybind11
+    srcs = _sources(os.path.join(CSRC, "host"), os.path.join(os.path.dirname(HERE), "include")) + [LIB]
+    if not force and _newer(EXT, srcs):
+        return EXT
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden",
+           "-I" + pybind11.get_include(), "-I" + sysconfig.get_paths()["include"],
+           os.path.join(CSRC, "host", "python_bindings.cpp"), "-o", EXT,
+           "-L" + HERE, "-lwsann_cuda", "-Wl,-rpath,$ORIGIN"]
+    subprocess.run(cmd, check=True)
+    return EXT
+
+
+def build_all(force: bool = False, verbose: bool = False) -> None:
+    build_cuda(force, verbose)
+    build_bindings(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print("built", LIB, EXT)

@@ -1,0 +1,165 @@
+// python_bindings.cpp — the `window_ann` pybind11 module of this engine.
+//
+// Mirrors the part of the reference module that experiments/wrapper.py and
+// experiments/run_our_method.py use (python_bindings/python_bindings.cpp:111-157,204-213):
+// the same class names, constructor keyword arguments, batch_search argument order and
+// return type (tuple of uint32 ids [nq,k] and float32 distances [nq,k]).  Only the float
+// variants exist — they are the only ones wrapper.py can reach.
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "window_index.hpp"
+
+namespace py = pybind11;
+using namespace pybind11::literals;
+using wsann::BuildParams;
+using wsann::QueryParams;
+
+using FArray = py::array_t<float, py::array::c_style | py::array::forcecast>;
+using Result = std::pair<py::array_t<unsigned int>, py::array_t<float>>;
+
+static wsann::BuildParams DEFAULT_BUILD_PARAMS(64, 500, 1.175, "index_cache");  // python_bindings.cpp:88
+
+struct Points {
+  const float* data;
+  size_t n, dim;
+};
+
+// prefiltering.h:78-98 / tree_utils.h:44-60 error behaviour
+static Points check_points(const FArray& points, const FArray& filter_values) {
+  if (points.ndim() != 2) throw std::runtime_error("points numpy array must be 2-dimensional");
+  if (filter_values.ndim() != 1) throw std::runtime_error("filter data numpy array must be 1-dimensional");
+  if (filter_values.shape(0) != points.shape(0))
+    throw std::runtime_error("filter data numpy array must have the same number of elements as the points array");
+  return Points{points.data(), (size_t)points.shape(0), (size_t)points.shape(1)};
+}
+
+struct Batch {
+  const float* queries;
+  const float* filters;
+  uint64_t nq;
+};
+
+static Batch check_batch(const FArray& queries, const FArray& filters, uint64_t num_queries, size_t dim) {
+  if (queries.ndim() != 2 || (size_t)queries.shape(1) != dim)
+    throw std::runtime_error("queries must be a 2-dimensional array with the index's dimension");
+  if ((uint64_t)queries.shape(0) < num_queries) throw std::runtime_error("fewer query rows than num_queries");
+  if (filters.ndim() != 2 || filters.shape(1) != 2) throw std::runtime_error("filters must be a sequence of (lo, hi) pairs");
+  if ((uint64_t)filters.shape(0) < num_queries) throw std::runtime_error("fewer filters than num_queries");
+  return Batch{queries.data(), filters.data(), num_queries};
+}
+
+template <class F>
+static Result run(uint64_t nq, long k, F&& f) {
+  if (k < 1) throw std::runtime_error("k must be >= 1");
+  py::array_t<unsigned int> ids({(py::ssize_t)nq, (py::ssize_t)k});
+  py::array_t<float> dists({(py::ssize_t)nq, (py::ssize_t)k});
+  unsigned int* ip = ids.mutable_data();
+  float* dp = dists.mutable_data();
+  {
+    py::gil_scoped_release release;
+    f(ip, dp);
+  }
+  return std::make_pair(ids, dists);
+}
+
+template <int METRIC>
+static void add_variant(py::module_& m, const std::string& sfx) {
+  struct Prefilter : wsann::PrefilterIndex { using wsann::PrefilterIndex::PrefilterIndex; };
+  struct Postfilter : wsann::PostfilterVamanaIndex { using wsann::PostfilterVamanaIndex::PostfilterVamanaIndex; };
+  struct Tree : wsann::VamanaRangeFilterTreeIndex { using wsann::VamanaRangeFilterTreeIndex::VamanaRangeFilterTreeIndex; };
+  struct Super : wsann::SuperOptimizedPostfilterTree { using wsann::SuperOptimizedPostfilterTree::SuperOptimizedPostfilterTree; };
+
+  py::class_<Prefilter>(m, ("PrefilterIndex" + sfx).c_str())
+      .def(py::init([](FArray points, FArray filter_values, BuildParams bp) {
+             Points p = check_points(points, filter_values);
+             return new Prefilter(p.data, filter_values.data(), p.n, p.dim, METRIC, bp);
+           }),
+           "points"_a, "filter_values"_a, "build_params"_a = DEFAULT_BUILD_PARAMS)
+      .def("batch_search",
+           [](Prefilter& self, FArray queries, FArray filters, uint64_t num_queries, QueryParams qp) {
+             Batch b = check_batch(queries, filters, num_queries, self.dim());
+             return run(b.nq, qp.k, [&](unsigned int* ids, float* dists) { self.batch_search(b.queries, b.filters, b.nq, qp, ids, dists); });
+           },
+           "queries"_a, "filters"_a, "num_queries"_a, "query_params"_a);
+
+  py::class_<Postfilter>(m, ("PostfilterVamanaIndex" + sfx).c_str())
+      .def(py::init([](FArray points, FArray filters, BuildParams bp) {
+             Points p = check_points(points, filters);
+             return new Postfilter(p.data, filters.data(), p.n, p.dim, METRIC, bp);
+           }),
+           "points"_a, "filters"_a, "build_params"_a = DEFAULT_BUILD_PARAMS)
+      .def("batch_search",
+           [](Postfilter& self, FArray queries, FArray filters, uint64_t num_queries, QueryParams qp) {
+             Batch b = check_batch(queries, filters, num_queries, self.dim());
+             return run(b.nq, qp.k, [&](unsigned int* ids, float* dists) { self.batch_search(b.queries, b.filters, b.nq, qp, ids, dists); });
+           },
+           "queries"_a, "filters"_a, "num_queries"_a, "query_params"_a);
+
+  py::class_<Tree>(m, ("VamanaRangeFilterTreeIndex" + sfx).c_str())
+      .def(py::init([](FArray points, FArray filter_values, int32_t cutoff, size_t split_factor, BuildParams bp) {
+             Points p = check_points(points, filter_values);
+             return new Tree(p.data, filter_values.data(), p.n, p.dim, METRIC, cutoff, split_factor, bp);
+           }),
+           "points"_a, "filter_values"_a, "cutoff"_a = 1000, "split_factor"_a = 2,
+           "build_params"_a = DEFAULT_BUILD_PARAMS)
+      .def("batch_search",
+           [](Tree& self, FArray queries, FArray filters, uint64_t num_queries, const std::string& query_method,
+              QueryParams qp) {
+             Batch b = check_batch(queries, filters, num_queries, self.dim());
+             return run(b.nq, qp.k, [&](unsigned int* ids, float* dists) {
+               self.batch_search(b.queries, b.filters, b.nq, query_method, qp, ids, dists);
+             });
+           },
+           "queries"_a, "filters"_a, "num_queries"_a, "query_method"_a, "query_params"_a)
+      .def("_arena_handle", [](Tree& self) { return (uintptr_t)self.arena().get(); })
+      .def("_bucket_offsets", [](Tree& self) { return self.bucket_offsets(); });
+
+  py::class_<Super>(m, ("SuperOptimizedPostfilterTreeIndex" + sfx).c_str())
+      .def(py::init([](FArray points, FArray filter_values, int32_t cutoff, float split_factor, float shift_factor,
+                       BuildParams bp) {
+             Points p = check_points(points, filter_values);
+             return new Super(p.data, filter_values.data(), p.n, p.dim, METRIC, cutoff, split_factor, shift_factor, bp);
+           }),
+           "points"_a, "filter_values"_a, "cutoff"_a = 1000, "split_factor"_a = 2, "shift_factor"_a = 0.5,
+           "build_params"_a = DEFAULT_BUILD_PARAMS)
+      .def("batch_search",
+           [](Super& self, FArray queries, FArray filters, uint64_t num_queries, QueryParams qp) {
+             Batch b = check_batch(queries, filters, num_queries, self.dim());
+             return run(b.nq, qp.k, [&](unsigned int* ids, float* dists) { self.batch_search(b.queries, b.filters, b.nq, qp, ids, dists); });
+           },
+           "queries"_a, "filters"_a, "num_queries"_a, "query_params"_a)
+      .def("_arena_handle", [](Super& self) { return (uintptr_t)self.arena().get(); });
+
+}
+
+PYBIND11_MODULE(window_ann, m) {
+  m.doc() = "WindowANN Python bindings — B200-native window-search engine (drop-in for the reference module)";
+  m.attr("__version__") = "b200-dev";
+  m.attr("__engine__") = "wsann_cuda";
+
+  py::module_ default_values = m.def_submodule("defaults");  // python_bindings.cpp:170-175
+  default_values.attr("METRIC") = "Euclidian";
+  default_values.attr("ALPHA") = 1.2;
+  default_values.attr("GRAPH_DEGREE") = 64;
+  default_values.attr("BEAMWIDTH") = 128;
+
+  py::class_<QueryParams>(m, "QueryParams")
+      .def(py::init<long, long, double, long, long, long, long, std::optional<float>, bool>(), "k"_a, "beam_width"_a,
+           "cut"_a, "limit"_a, "degree_limit"_a, "final_beam_multiply"_a, "postfiltering_max_beam"_a,
+           "min_query_to_bucket_ratio"_a, "verbose"_a);
+
+  py::class_<BuildParams>(m, "BuildParams")
+      .def(py::init<long, long, double, std::string>(), "max_degree"_a, "limit"_a, "alpha"_a, "cache_path"_a);
+
+  add_variant<WS_METRIC_L2>(m, "FloatEuclidian");
+  add_variant<WS_METRIC_MIPS>(m, "FloatMips");
+
+  m.def("device_count", []() {
+    int c = 0;
+    ws_device_count(&c);
+    return c;
+  });
+  m.def("abi_version", []() { return ws_abi_version(); });
+}

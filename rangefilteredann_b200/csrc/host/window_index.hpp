@@ -1,0 +1,357 @@
+// window_index.hpp — host-side index classes of the drop-in boundary's upper face.
+//
+// Same class names, constructor arguments and batch_search signatures as the reference's
+// header-only classes; all query work is delegated to libwsann_cuda.so through the C ABI
+// (include/wsann.h).  What stays on the host is what the reference also does once at
+// construction: validate inputs, argsort the labels, lay the points out label-sorted,
+// derive the tree geometry and find each node's cached Vamana graph.
+//
+//   PrefilterIndex                      src/prefiltering.h:28-205
+//   PostfilterVamanaIndex               src/postfilter_vamana.h:29-255
+//   RangeFilterTreeIndex (Vamana nodes) src/range_filter_tree.h:30-550
+//   SuperOptimizedPostfilterTree        src/super_optimized_postfilter_tree.h:29-271
+//   sort_python_and_convert             src/tree_utils.h:39-98
+//   Graph file format                   ParlayANN/algorithms/utils/graph.h:126-196
+//   QueryParams / BuildParams           ParlayANN/algorithms/utils/types.h:77-140
+//
+// Graph CONSTRUCTION is not on this path: graphs are loaded from the
+// reference builder's cache files (postfilter_vamana.h:54-61,126-132).  A missing file is
+// an error, never a silently different graph.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <memory>
+#include <numeric>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/wsann.h"
+
+namespace wsann {
+
+struct BuildParams {  // types.h:77-112 (only the fields this path reads)
+  long L = 0;
+  long R = 0;
+  double alpha = 0;
+  std::string cache_path;
+  BuildParams() {}
+  BuildParams(long R, long L, double a, std::string cache_path)
+      : L(L), R(R), alpha(a), cache_path(std::move(cache_path)) {}
+};
+
+struct QueryParams {  // types.h:115-140
+  long k = 0;
+  long beamSize = 0;
+  double cut = 1.35;
+  long limit = 0;
+  long degree_limit = 0;
+  long final_beam_multiply = 8;
+  long postfiltering_max_beam = 10000;
+  std::optional<float> min_query_to_bucket_ratio = std::nullopt;
+  bool verbose = false;
+  QueryParams() {}
+  QueryParams(long k, long Q, double cut, long limit, long dg, long final_beam_multiply,
+              long postfiltering_max_beam, std::optional<float> min_query_to_bucket_ratio, bool verbose)
+      : k(k), beamSize(Q), cut(cut), limit(limit), degree_limit(dg),
+        final_beam_multiply(final_beam_multiply), postfiltering_max_beam(postfiltering_max_beam),
+        min_query_to_bucket_ratio(min_query_to_bucket_ratio), verbose(verbose) {}
+
+  ws_query_params to_c() const {
+    ws_query_params c;
+    std::memset(&c, 0, sizeof(c));
+    c.k = k; c.beam_size = beamSize; c.cut = cut; c.limit = limit; c.degree_limit = degree_limit;
+    c.final_beam_multiply = final_beam_multiply; c.postfiltering_max_beam = postfiltering_max_beam;
+    c.has_min_query_to_bucket_ratio = min_query_to_bucket_ratio.has_value() ? 1 : 0;
+    c.min_query_to_bucket_ratio = min_query_to_bucket_ratio.value_or(0.f);
+    c.verbose = verbose ? 1 : 0;
+    return c;
+  }
+};
+
+inline void check(int status, const char* what) {
+  if (status != WS_OK)
+    throw std::runtime_error(std::string(what) + ": " + ws_last_error() + " (status " + std::to_string(status) + ")");
+}
+
+inline int default_device() {
+  if (const char* e = std::getenv("WSANN_DEVICE")) return std::atoi(e);
+  return 0;
+}
+
+// ---- reference graph cache -----------------------------------------------------------------
+struct GraphFile {
+  int32_t n = 0, max_degree = 0;
+  std::vector<int32_t> degrees, edges;
+};
+
+// graph.h:126-172 layout: int32 n, int32 maxDeg, int32 degree[n], int32 edges[sum degree]
+inline GraphFile read_graph_file(const std::string& path) {
+  std::ifstream in(path, std::ios::binary);
+  if (!in) throw std::runtime_error("cannot open graph file " + path);
+  GraphFile g;
+  in.read(reinterpret_cast<char*>(&g.n), 4);
+  in.read(reinterpret_cast<char*>(&g.max_degree), 4);
+  if (!in || g.n <= 0 || g.max_degree <= 0) throw std::runtime_error("bad graph header in " + path);
+  g.degrees.resize(g.n);
+  in.read(reinterpret_cast<char*>(g.degrees.data()), 4ll * g.n);
+  if (!in) throw std::runtime_error("truncated degree table in " + path);
+  int64_t total = 0;
+  for (int32_t d : g.degrees) {
+    if (d < 0 || d > g.max_degree) throw std::runtime_error("bad degree in " + path);
+    total += d;
+  }
+  g.edges.resize(total);
+  in.read(reinterpret_cast<char*>(g.edges.data()), 4ll * total);
+  if (!in) throw std::runtime_error("truncated edge list in " + path);
+  return g;
+}
+
+// postfilter_vamana.h:126-132 (std::to_string of long / double / float)
+inline std::string graph_filename(const BuildParams& bp, float min_label, float max_label, size_t n) {
+  return bp.cache_path + "vamana_" + std::to_string(bp.L) + "_" + std::to_string(bp.R) + "_" +
+         std::to_string(bp.alpha) + "_" + std::to_string(min_label) + "_" + std::to_string(max_label) + "_" +
+         std::to_string(n) + ".bin";
+}
+
+// ---- the HBM arena + its graphs --------------------------------------------------------------
+class Arena {
+ public:
+  Arena() = default;
+  Arena(const Arena&) = delete;
+  Arena& operator=(const Arena&) = delete;
+  ~Arena() { if (idx_) ws_index_destroy(idx_); }
+
+  // tree_utils.h:39-98: argsort labels, physically permute, decode[sorted] = original.
+  // Equal labels are ordered by original id (the reference's unstable parlay sort leaves
+  // that order implementation-defined).
+  void init_sorted(const float* points, const float* labels, size_t n, size_t dim, int metric, int device) {
+    n_ = n; dim_ = dim;
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return labels[a] < labels[b]; });
+    std::vector<float> sorted(n * dim);
+    labels_.resize(n);
+    for (size_t i = 0; i < n; i++) {
+      std::memcpy(&sorted[i * dim], points + (size_t)order[i] * dim, dim * sizeof(float));
+      labels_[i] = labels[order[i]];
+    }
+    check(ws_index_create(device, metric, n, (uint32_t)dim, sorted.data(), labels_.data(), order.data(), 1, &idx_),
+          "ws_index_create");
+  }
+
+  // PostfilterVamanaIndex over the points as given (postfilter_vamana.h:91-124)
+  void init_unsorted(const float* points, const float* labels, size_t n, size_t dim, int metric, int device) {
+    n_ = n; dim_ = dim;
+    labels_.assign(labels, labels + n);
+    check(ws_index_create(device, metric, n, (uint32_t)dim, points, labels, nullptr, 0, &idx_), "ws_index_create");
+  }
+
+  int32_t add_cached_graph(const BuildParams& bp, size_t start, size_t count, float min_label, float max_label) {
+    if (bp.cache_path.empty())
+      throw std::runtime_error("BuildParams.cache_path is empty: this engine loads the reference builder's graph "
+                               "cache (postfilter_vamana.h:54-61) and does not build graphs");
+    std::string path = graph_filename(bp, min_label, max_label, count);
+    std::ifstream probe(path, std::ios::binary);
+    if (!probe)
+      throw std::runtime_error("graph cache miss: " + path +
+                               " — build it with the reference builder (oracle/build_ref_cache.py); "
+                               "graph construction is outside this engine's hot path");
+    probe.close();
+    GraphFile g = read_graph_file(path);
+    if ((size_t)g.n != count) throw std::runtime_error("graph " + path + " has " + std::to_string(g.n) + " nodes, expected " + std::to_string(count));
+    int32_t node = -1;
+    check(ws_index_add_graph(idx_, start, count, (uint32_t)g.max_degree, g.degrees.data(), g.edges.data(), &node),
+          "ws_index_add_graph");
+    return node;
+  }
+
+  ws_index* get() const { return idx_; }
+  size_t size() const { return n_; }
+  size_t dim() const { return dim_; }
+  const std::vector<float>& labels() const { return labels_; }
+
+ private:
+  ws_index* idx_ = nullptr;
+  size_t n_ = 0, dim_ = 0;
+  std::vector<float> labels_;
+};
+
+struct BatchResult {
+  std::vector<uint32_t> ids;
+  std::vector<float> dists;
+};
+
+// ---- PrefilterIndex (src/prefiltering.h) -------------------------------------------------------
+class PrefilterIndex {
+ public:
+  PrefilterIndex(const float* points, const float* labels, size_t n, size_t dim, int metric, const BuildParams&,
+                 int device = default_device()) {
+    arena_.init_sorted(points, labels, n, dim, metric, device);
+    check(ws_index_finalize(arena_.get()), "ws_index_finalize");
+  }
+  // prefiltering.h:124-146
+  void batch_search(const float* queries, const float* filters, uint64_t nq, const QueryParams& qp, uint32_t* ids,
+                    float* dists) {
+    if (qp.k < 1) throw std::runtime_error("k must be >= 1");
+    check(ws_prefilter_batch(arena_.get(), queries, filters, nq, (uint32_t)qp.k, ids, dists, 0), "ws_prefilter_batch");
+  }
+  Arena& arena() { return arena_; }
+  size_t dim() const { return arena_.dim(); }
+
+ private:
+  Arena arena_;
+};
+
+// ---- PostfilterVamanaIndex (src/postfilter_vamana.h) -------------------------------------------
+class PostfilterVamanaIndex {
+ public:
+  PostfilterVamanaIndex(const float* points, const float* labels, size_t n, size_t dim, int metric,
+                        const BuildParams& bp, int device = default_device()) {
+    arena_.init_unsorted(points, labels, n, dim, metric, device);
+    float mn = *std::min_element(labels, labels + n), mx = *std::max_element(labels, labels + n);
+    node_ = arena_.add_cached_graph(bp, 0, n, mn, mx);
+    check(ws_index_finalize(arena_.get()), "ws_index_finalize");
+  }
+  // postfilter_vamana.h:191-219 (missing slots: id 0xFFFFFFFF, FLT_MAX)
+  void batch_search(const float* queries, const float* filters, uint64_t nq, const QueryParams& qp, uint32_t* ids,
+                    float* dists) {
+    ws_query_params c = qp.to_c();
+    check(ws_postfilter_batch(arena_.get(), node_, queries, filters, nq, &c, WS_PAD_MINUS1, ids, dists, 0),
+          "ws_postfilter_batch");
+  }
+  Arena& arena() { return arena_; }
+  size_t dim() const { return arena_.dim(); }
+
+ private:
+  Arena arena_;
+  int32_t node_ = -1;
+};
+
+// ---- RangeFilterTreeIndex with Vamana sub-indices (src/range_filter_tree.h) --------------------
+class VamanaRangeFilterTreeIndex {
+ public:
+  VamanaRangeFilterTreeIndex(const float* points, const float* labels, size_t n, size_t dim, int metric,
+                             int32_t cutoff, size_t split_factor, const BuildParams& bp,
+                             int device = default_device()) {
+    if (split_factor < 2) throw std::runtime_error("split_factor must be at least 2");
+    arena_.init_sorted(points, labels, n, dim, metric, device);
+    const std::vector<float>& sl = arena_.labels();
+    // range_filter_tree.h:129-189
+    offsets_.push_back({0, (uint64_t)n});
+    while ((int64_t)offsets_.back()[1] > (int64_t)cutoff) {
+      const std::vector<uint64_t>& last = offsets_.back();
+      size_t last_nb = last.size() - 1;
+      std::vector<uint64_t> next(last_nb * split_factor + 1);
+      next.back() = n;
+      for (size_t b = 0; b < last_nb; b++) {
+        uint64_t ls = last[b], le = last[b + 1], size = le - ls;
+        uint64_t large = (size + split_factor - 1) / split_factor;
+        uint64_t small = large - 1;
+        uint64_t n_large = size - small * split_factor;
+        for (size_t i = 0; i < split_factor; i++) {
+          uint64_t s = i < n_large ? ls + i * large : ls + n_large * large + (i - n_large) * small;
+          next[b * split_factor + i] = s;
+        }
+      }
+      for (size_t i = 0; i + 1 < next.size(); i++)
+        if (next[i + 1] <= next[i]) throw std::runtime_error("cutoff/split_factor produce an empty bucket");
+      offsets_.push_back(std::move(next));
+    }
+    std::vector<uint32_t> row_nb;
+    std::vector<uint64_t> off_flat;
+    std::vector<int32_t> nodes_flat;
+    for (auto& row : offsets_) {
+      row_nb.push_back((uint32_t)row.size() - 1);
+      off_flat.insert(off_flat.end(), row.begin(), row.end());
+      for (size_t b = 0; b + 1 < row.size(); b++)
+        nodes_flat.push_back(arena_.add_cached_graph(bp, row[b], row[b + 1] - row[b], sl[row[b]], sl[row[b + 1] - 1]));
+    }
+    check(ws_index_set_wst(arena_.get(), (uint32_t)offsets_.size(), (uint32_t)split_factor, cutoff, row_nb.data(),
+                           off_flat.data(), nodes_flat.data()),
+          "ws_index_set_wst");
+    check(ws_index_finalize(arena_.get()), "ws_index_finalize");
+  }
+
+  // range_filter_tree.h:62-96: any method string other than the two named ones is "fenwick"
+  static int method_from_string(const std::string& m) {
+    if (m == "optimized_postfilter") return WS_METHOD_OPT_POSTFILTER;
+    if (m == "three_split") return WS_METHOD_THREE_SPLIT;
+    return WS_METHOD_FENWICK;
+  }
+  void batch_search(const float* queries, const float* filters, uint64_t nq, const std::string& query_method,
+                    const QueryParams& qp, uint32_t* ids, float* dists) {
+    ws_query_params c = qp.to_c();
+    check(ws_tree_batch(arena_.get(), method_from_string(query_method), queries, filters, nq, &c, ids, dists, 0),
+          "ws_tree_batch");
+  }
+  Arena& arena() { return arena_; }
+  size_t dim() const { return arena_.dim(); }
+  const std::vector<std::vector<uint64_t>>& bucket_offsets() const { return offsets_; }
+
+ private:
+  Arena arena_;
+  std::vector<std::vector<uint64_t>> offsets_;
+};
+
+// ---- SuperOptimizedPostfilterTree (src/super_optimized_postfilter_tree.h) ------------------------
+class SuperOptimizedPostfilterTree {
+ public:
+  SuperOptimizedPostfilterTree(const float* points, const float* labels, size_t n, size_t dim, int metric,
+                               int32_t cutoff, float split_factor, float shift_factor, const BuildParams& bp,
+                               int device = default_device()) {
+    // super_optimized_postfilter_tree.h:127-132
+    if (split_factor <= 1) throw std::runtime_error("split_factor must be greater than 1");
+    if (shift_factor >= 1 || shift_factor <= 0) throw std::runtime_error("shift_factor must be between 0 and 1");
+    arena_.init_sorted(points, labels, n, dim, metric, device);
+    const std::vector<float>& sl = arena_.labels();
+    std::vector<uint64_t> sizes{(uint64_t)n}, shifts{0};
+    std::vector<uint32_t> row_nb{1};
+    std::vector<int32_t> nodes_flat;
+    nodes_flat.push_back(arena_.add_cached_graph(bp, 0, n, sl[0], sl[n - 1]));
+    // :145-170 — bucket size is evaluated in float, as the reference does
+    while ((int64_t)sizes.back() > (int64_t)cutoff) {
+      size_t last = sizes.back();
+      size_t bucket_size = (size_t)((last + split_factor - 1) / split_factor);
+      size_t bucket_shift = (size_t)std::ceil(bucket_size * shift_factor);
+      if (bucket_size == 0 || bucket_shift == 0 || bucket_size >= last) throw std::runtime_error("degenerate super tree row");
+      sizes.push_back(bucket_size);
+      shifts.push_back(bucket_shift);
+      size_t nb = ((n - bucket_size) + bucket_shift - 1) / bucket_shift + 1;
+      row_nb.push_back((uint32_t)nb);
+      for (size_t b = 0; b < nb; b++) {
+        size_t s = b * bucket_shift, e = std::min(s + bucket_size, n);
+        nodes_flat.push_back(arena_.add_cached_graph(bp, s, e - s, sl[s], sl[e - 1]));
+      }
+    }
+    check(ws_index_set_super(arena_.get(), (uint32_t)sizes.size(), cutoff, sizes.data(), shifts.data(), row_nb.data(),
+                             nodes_flat.data()),
+          "ws_index_set_super");
+    check(ws_index_finalize(arena_.get()), "ws_index_finalize");
+    sizes_ = sizes; shifts_ = shifts;
+  }
+  // super_optimized_postfilter_tree.h:60-87
+  void batch_search(const float* queries, const float* filters, uint64_t nq, const QueryParams& qp, uint32_t* ids,
+                    float* dists) {
+    ws_query_params c = qp.to_c();
+    check(ws_tree_batch(arena_.get(), WS_METHOD_SUPER_POSTFILTER, queries, filters, nq, &c, ids, dists, 0),
+          "ws_tree_batch");
+  }
+  Arena& arena() { return arena_; }
+  size_t dim() const { return arena_.dim(); }
+  const std::vector<uint64_t>& bucket_sizes() const { return sizes_; }
+  const std::vector<uint64_t>& bucket_shifts() const { return shifts_; }
+
+ private:
+  Arena arena_;
+  std::vector<uint64_t> sizes_, shifts_;
+};
+
+}  // namespace wsann

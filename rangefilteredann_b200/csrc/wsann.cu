@@ -1,0 +1,934 @@
+// wsann.cu — libwsann_cuda.so: HBM arena management, batch orchestration and the C ABI
+// declared in include/wsann.h.  No PyTorch, no CPU fallback: every *_batch call needs a
+// CUDA device and returns WS_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/wsann.h"
+#include "ws_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int ws_fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define WS_CUDA(expr)                                                                       \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return ws_fail(_e == cudaErrorMemoryAllocation ? WS_ERR_OOM : WS_ERR_CUDA,            \
+                     "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,      \
+                     __LINE__);                                                             \
+  } while (0)
+
+#define WS_TRY(expr)            \
+  do {                          \
+    int _s = (expr);            \
+    if (_s != WS_OK) return _s; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// index object
+// ------------------------------------------------------------------------------------------
+static const uint32_t kBeamTierCaps[3] = {64, 256, 1024};  // shared-memory-visited tiers
+static const uint32_t kBeamCapLarge = 12288;                // global-bitmap tier
+static const uint32_t kMaxK = WS_TOPK_BUF / 2;
+static const size_t kAdjSlabBytes = 256ull << 20;
+
+struct WsDevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct ws_index {
+  int device = -1;  // -1: host-only geometry index (decomposition tests)
+  int metric = 0;
+  uint64_t n = 0;
+  uint32_t dim = 0, dpad = 0;
+  bool label_sorted = false;
+  bool finalized = false;
+  bool has_decode = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int num_sms = 0;
+  size_t smem_optin = 0;
+
+  // device arena
+  float* d_vecs = nullptr;
+  float* d_labels = nullptr;
+  uint32_t* d_decode = nullptr;
+  WsNode* d_nodes = nullptr;
+  std::vector<void*> adj_slabs;
+  size_t slab_used = 0;
+  uint64_t hbm_bytes = 0;
+
+  // host mirrors
+  std::vector<float> h_labels;
+  std::vector<WsNode> h_nodes;
+  uint32_t R = 0;
+  uint32_t max_node_count = 0;
+
+  // geometry (host copies own the storage the host WsGeom points to)
+  std::vector<uint32_t> wst_nb, wst_off_ptr, wst_node_ptr;
+  std::vector<uint64_t> wst_off;
+  std::vector<int32_t> wst_nodes;
+  std::vector<uint64_t> sup_size, sup_shift;
+  std::vector<uint32_t> sup_nb, sup_node_ptr;
+  std::vector<int32_t> sup_nodes;
+  uint32_t wst_rows = 0, split = 0, sup_rows = 0;
+  int32_t cutoff = 0, sup_cutoff = 0;
+  WsGeom hgeom{};
+  WsGeom dgeom{};
+  std::vector<void*> geom_dev_allocs;
+
+  // options
+  int64_t opt_expand = 1;
+  int64_t opt_skip_query_id = 1;
+  int64_t opt_scan_chunk = 8192;
+  int64_t opt_hash_factor = 32;  // smem visited-table entries per unit of beam capacity
+
+  // scratch (grown on demand)
+  WsDevBuf tasks, res_keys, res_cnt, counts, queues, ctrl, d_queries, d_windows, d_ids, d_dists,
+      bitmap, flush;
+  unsigned long long* d_stats = nullptr;
+  uint64_t launches = 0;
+};
+
+static int ws_ensure(ws_index* idx, WsDevBuf& b, size_t bytes) {
+  if (b.bytes >= bytes) return WS_OK;
+  if (b.p) {
+    WS_CUDA(cudaStreamSynchronize(idx->stream));
+    WS_CUDA(cudaFree(b.p));
+    idx->hbm_bytes -= b.bytes;
+    b.p = nullptr;
+    b.bytes = 0;
+  }
+  size_t want = bytes + bytes / 4 + 256;
+  WS_CUDA(cudaMalloc(&b.p, want));
+  b.bytes = want;
+  idx->hbm_bytes += want;
+  return WS_OK;
+}
+
+static uint32_t ws_dim_round_up(uint32_t dim) {
+  // point_range.h:39-44 with sizeof(T) = 4: rows are a multiple of 64 bytes
+  uint64_t bytes = (uint64_t)dim * 4;
+  if (bytes % 64 == 0) return dim;
+  return (uint32_t)(((bytes / 64) + 1) * 64 / 4);
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* ws_last_error(void) { return g_last_error.c_str(); }
+int ws_abi_version(void) { return WSANN_ABI_VERSION; }
+
+int ws_device_count(int* count) {
+  if (!count) return ws_fail(WS_ERR_BADARG, "count is null");
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return ws_fail(WS_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  }
+  *count = c;
+  return WS_OK;
+}
+
+int ws_index_create(int device, int metric, uint64_t n, uint32_t dim, const float* vectors,
+                    const float* labels, const uint32_t* decode, int label_sorted,
+                    ws_index** out) {
+  if (!out) return ws_fail(WS_ERR_BADARG, "out is null");
+  *out = nullptr;
+  if (n == 0 || dim == 0) return ws_fail(WS_ERR_BADARG, "empty index (n=%llu dim=%u)", (unsigned long long)n, dim);
+  if (n >= (1ull << 31)) return ws_fail(WS_ERR_BADARG, "n=%llu exceeds the 2^31 ranks one arena addresses", (unsigned long long)n);
+  if (metric != WS_METRIC_L2 && metric != WS_METRIC_MIPS) return ws_fail(WS_ERR_BADARG, "unknown metric %d", metric);
+  if (!labels) return ws_fail(WS_ERR_BADARG, "labels is null");
+  if (label_sorted)
+    for (uint64_t i = 1; i < n; i++)
+      if (labels[i] < labels[i - 1]) return ws_fail(WS_ERR_BADARG, "labels not sorted at %llu", (unsigned long long)i);
+  ws_index* idx = new ws_index();
+  idx->device = device;
+  idx->metric = metric;
+  idx->n = n;
+  idx->dim = dim;
+  idx->dpad = ws_dim_round_up(dim);
+  idx->label_sorted = label_sorted != 0;
+  idx->h_labels.assign(labels, labels + n);
+  if (device < 0) {  // host-only geometry index
+    *out = idx;
+    return WS_OK;
+  }
+  if (!vectors) { delete idx; return ws_fail(WS_ERR_BADARG, "vectors is null"); }
+  if (idx->dpad > 1024) { delete idx; return ws_fail(WS_ERR_BADARG, "dim %u: padded rows above 1024 floats are not supported", dim); }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || device >= ndev) {
+    delete idx;
+    return ws_fail(WS_ERR_CUDA, "no usable CUDA device %d (%s); this engine has no CPU fallback", device,
+                   e != cudaSuccess ? cudaGetErrorString(e) : "index out of range");
+  }
+#define WS_CREATE_CUDA(expr)                                                                 \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      ws_index_destroy(idx);                                                                 \
+      return ws_fail(_e == cudaErrorMemoryAllocation ? WS_ERR_OOM : WS_ERR_CUDA, "%s: %s", #expr, \
+                     cudaGetErrorString(_e));                                                \
+    }                                                                                        \
+  } while (0)
+  WS_CREATE_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  WS_CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
+  idx->num_sms = prop.multiProcessorCount;
+  idx->smem_optin = prop.sharedMemPerBlockOptin;
+  WS_CREATE_CUDA(cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking));
+  WS_CREATE_CUDA(cudaEventCreate(&idx->ev0));
+  WS_CREATE_CUDA(cudaEventCreate(&idx->ev1));
+  size_t vbytes = (size_t)n * idx->dpad * sizeof(float);
+  WS_CREATE_CUDA(cudaMalloc(&idx->d_vecs, vbytes));
+  idx->hbm_bytes += vbytes;
+  if (idx->dpad == dim) {
+    WS_CREATE_CUDA(cudaMemcpy(idx->d_vecs, vectors, vbytes, cudaMemcpyHostToDevice));
+  } else {  // zero-filled pad (the reference leaves it uninitialised)
+    WS_CREATE_CUDA(cudaMemset(idx->d_vecs, 0, vbytes));
+    WS_CREATE_CUDA(cudaMemcpy2D(idx->d_vecs, (size_t)idx->dpad * 4, vectors, (size_t)dim * 4, (size_t)dim * 4, n,
+                                cudaMemcpyHostToDevice));
+  }
+  WS_CREATE_CUDA(cudaMalloc(&idx->d_labels, n * sizeof(float)));
+  WS_CREATE_CUDA(cudaMemcpy(idx->d_labels, labels, n * sizeof(float), cudaMemcpyHostToDevice));
+  idx->hbm_bytes += n * sizeof(float);
+  if (decode) {
+    WS_CREATE_CUDA(cudaMalloc(&idx->d_decode, n * sizeof(uint32_t)));
+    WS_CREATE_CUDA(cudaMemcpy(idx->d_decode, decode, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    idx->hbm_bytes += n * sizeof(uint32_t);
+    idx->has_decode = true;
+  }
+  WS_CREATE_CUDA(cudaMalloc(&idx->d_stats, 8 * sizeof(unsigned long long)));
+  WS_CREATE_CUDA(cudaMemset(idx->d_stats, 0, 8 * sizeof(unsigned long long)));
+#undef WS_CREATE_CUDA
+  *out = idx;
+  return WS_OK;
+}
+
+void ws_index_destroy(ws_index* idx) {
+  if (!idx) return;
+  if (idx->device >= 0) {
+    cudaSetDevice(idx->device);
+    if (idx->stream) cudaStreamSynchronize(idx->stream);
+    cudaFree(idx->d_vecs);
+    cudaFree(idx->d_labels);
+    cudaFree(idx->d_decode);
+    cudaFree(idx->d_stats);
+    for (void* p : idx->adj_slabs) cudaFree(p);
+    for (void* p : idx->geom_dev_allocs) cudaFree(p);
+    WsDevBuf* bufs[] = {&idx->tasks, &idx->res_keys, &idx->res_cnt, &idx->counts, &idx->queues, &idx->ctrl,
+                        &idx->d_queries, &idx->d_windows, &idx->d_ids, &idx->d_dists, &idx->bitmap, &idx->flush};
+    for (WsDevBuf* b : bufs) cudaFree(b->p);
+    if (idx->ev0) cudaEventDestroy(idx->ev0);
+    if (idx->ev1) cudaEventDestroy(idx->ev1);
+    if (idx->stream) cudaStreamDestroy(idx->stream);
+  }
+  delete idx;
+}
+
+int ws_index_add_graph(ws_index* idx, uint64_t start, uint64_t count, uint32_t max_degree,
+                       const int32_t* degrees, const int32_t* edges, int32_t* node_out) {
+  if (!idx || !node_out) return ws_fail(WS_ERR_BADARG, "null argument");
+  if (idx->finalized) return ws_fail(WS_ERR_STATE, "index already finalized");
+  if (count == 0 || start + count > idx->n) return ws_fail(WS_ERR_BADARG, "graph range [%llu,+%llu) outside the arena", (unsigned long long)start, (unsigned long long)count);
+  if (max_degree == 0 || max_degree > 128) return ws_fail(WS_ERR_BADARG, "max_degree %u unsupported (1..128)", max_degree);
+  uint32_t R = (max_degree + 3u) & ~3u;
+  if (idx->R == 0) idx->R = R;
+  if (idx->R != R) return ws_fail(WS_ERR_BADARG, "all graphs of one index must share max_degree (%u vs %u)", idx->R, R);
+  WsNode node;
+  node.adj = nullptr;
+  node.start = (uint32_t)start;
+  node.count = (uint32_t)count;
+  if (idx->device >= 0) {
+    if (!degrees || !edges) return ws_fail(WS_ERR_BADARG, "degrees/edges null");
+    WS_CUDA(cudaSetDevice(idx->device));
+    size_t bytes = (size_t)count * R * sizeof(int32_t);
+    std::vector<int32_t> rows((size_t)count * R, -1);
+    size_t off = 0;
+    for (uint64_t i = 0; i < count; i++) {
+      int32_t deg = degrees[i];
+      if (deg < 0 || (uint32_t)deg > max_degree) return ws_fail(WS_ERR_BADARG, "degree %d of local node %llu out of range", deg, (unsigned long long)i);
+      for (int32_t j = 0; j < deg; j++) {
+        int32_t v = edges[off + j];
+        if (v < 0 || (uint64_t)v >= count) return ws_fail(WS_ERR_BADARG, "edge %d of local node %llu outside the graph", v, (unsigned long long)i);
+        rows[i * R + j] = v;
+      }
+      off += deg;
+    }
+    void* dst = nullptr;
+    size_t aligned = (bytes + 255) & ~(size_t)255;
+    if (aligned > kAdjSlabBytes) {
+      WS_CUDA(cudaMalloc(&dst, aligned));
+      idx->adj_slabs.insert(idx->adj_slabs.begin(), dst);  // keep the bump slab last
+      idx->hbm_bytes += aligned;
+      if (idx->adj_slabs.size() == 1) idx->slab_used = kAdjSlabBytes;  // no bump slab yet
+    } else {
+      if (idx->adj_slabs.empty() || idx->slab_used + aligned > kAdjSlabBytes) {
+        void* slab = nullptr;
+        WS_CUDA(cudaMalloc(&slab, kAdjSlabBytes));
+        idx->adj_slabs.push_back(slab);
+        idx->slab_used = 0;
+        idx->hbm_bytes += kAdjSlabBytes;
+      }
+      dst = (char*)idx->adj_slabs.back() + idx->slab_used;
+      idx->slab_used += aligned;
+    }
+    WS_CUDA(cudaMemcpy(dst, rows.data(), bytes, cudaMemcpyHostToDevice));
+    node.adj = (const int32_t*)dst;
+  }
+  idx->h_nodes.push_back(node);
+  idx->max_node_count = std::max<uint32_t>(idx->max_node_count, (uint32_t)count);
+  *node_out = (int32_t)idx->h_nodes.size() - 1;
+  return WS_OK;
+}
+
+int ws_index_set_wst(ws_index* idx, uint32_t rows, uint32_t split_factor, int32_t cutoff,
+                     const uint32_t* row_nb, const uint64_t* offsets_flat,
+                     const int32_t* node_ids_flat) {
+  if (!idx || !row_nb || !offsets_flat || !node_ids_flat) return ws_fail(WS_ERR_BADARG, "null argument");
+  if (idx->finalized) return ws_fail(WS_ERR_STATE, "index already finalized");
+  if (!idx->label_sorted) return ws_fail(WS_ERR_BADARG, "tree geometry needs a label-sorted arena");
+  if (rows == 0 || split_factor < 2) return ws_fail(WS_ERR_BADARG, "rows=%u split_factor=%u", rows, split_factor);
+  idx->wst_rows = rows;
+  idx->split = split_factor;
+  idx->cutoff = cutoff;
+  idx->wst_nb.assign(row_nb, row_nb + rows);
+  idx->wst_off_ptr.resize(rows);
+  idx->wst_node_ptr.resize(rows);
+  size_t no = 0, nn = 0;
+  for (uint32_t r = 0; r < rows; r++) {
+    idx->wst_off_ptr[r] = (uint32_t)no;
+    idx->wst_node_ptr[r] = (uint32_t)nn;
+    no += (size_t)row_nb[r] + 1;
+    nn += row_nb[r];
+  }
+  idx->wst_off.assign(offsets_flat, offsets_flat + no);
+  idx->wst_nodes.assign(node_ids_flat, node_ids_flat + nn);
+  for (uint32_t r = 0; r < rows; r++) {
+    const uint64_t* o = &idx->wst_off[idx->wst_off_ptr[r]];
+    if (o[0] != 0 || o[row_nb[r]] != idx->n) return ws_fail(WS_ERR_BADARG, "row %u offsets do not span [0,n)", r);
+    for (uint32_t b = 0; b < row_nb[r]; b++) {
+      if (o[b + 1] <= o[b]) return ws_fail(WS_ERR_BADARG, "row %u bucket %u empty", r, b);
+      int32_t h = idx->wst_nodes[idx->wst_node_ptr[r] + b];
+      if (h < 0 || (size_t)h >= idx->h_nodes.size()) return ws_fail(WS_ERR_BADARG, "row %u bucket %u: bad node handle %d", r, b, h);
+      if (idx->h_nodes[h].start != o[b] || idx->h_nodes[h].count != o[b + 1] - o[b])
+        return ws_fail(WS_ERR_BADARG, "row %u bucket %u: node range mismatch", r, b);
+    }
+  }
+  return WS_OK;
+}
+
+int ws_index_set_super(ws_index* idx, uint32_t rows, int32_t cutoff, const uint64_t* bucket_sizes,
+                       const uint64_t* bucket_shifts, const uint32_t* row_nb,
+                       const int32_t* node_ids_flat) {
+  if (!idx || !bucket_sizes || !bucket_shifts || !row_nb || !node_ids_flat) return ws_fail(WS_ERR_BADARG, "null argument");
+  if (idx->finalized) return ws_fail(WS_ERR_STATE, "index already finalized");
+  if (!idx->label_sorted) return ws_fail(WS_ERR_BADARG, "tree geometry needs a label-sorted arena");
+  if (rows == 0) return ws_fail(WS_ERR_BADARG, "rows=0");
+  idx->sup_rows = rows;
+  idx->sup_cutoff = cutoff;
+  idx->sup_size.assign(bucket_sizes, bucket_sizes + rows);
+  idx->sup_shift.assign(bucket_shifts, bucket_shifts + rows);
+  idx->sup_nb.assign(row_nb, row_nb + rows);
+  idx->sup_node_ptr.resize(rows);
+  size_t nn = 0;
+  for (uint32_t r = 0; r < rows; r++) {
+    idx->sup_node_ptr[r] = (uint32_t)nn;
+    nn += row_nb[r];
+    if (r > 0 && bucket_shifts[r] == 0) return ws_fail(WS_ERR_BADARG, "row %u shift is zero", r);
+  }
+  idx->sup_nodes.assign(node_ids_flat, node_ids_flat + nn);
+  for (size_t i = 0; i < nn; i++)
+    if (idx->sup_nodes[i] < 0 || (size_t)idx->sup_nodes[i] >= idx->h_nodes.size())
+      return ws_fail(WS_ERR_BADARG, "bad node handle %d", idx->sup_nodes[i]);
+  return WS_OK;
+}
+
+}  // extern "C"
+
+template <typename T>
+static int ws_upload(ws_index* idx, const std::vector<T>& v, const T** out) {
+  *out = nullptr;
+  if (v.empty()) return WS_OK;
+  void* p = nullptr;
+  WS_CUDA(cudaMalloc(&p, v.size() * sizeof(T)));
+  WS_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  idx->geom_dev_allocs.push_back(p);
+  idx->hbm_bytes += v.size() * sizeof(T);
+  *out = (const T*)p;
+  return WS_OK;
+}
+
+extern "C" {
+
+int ws_index_finalize(ws_index* idx) {
+  if (!idx) return ws_fail(WS_ERR_BADARG, "null index");
+  if (idx->finalized) return ws_fail(WS_ERR_STATE, "index already finalized");
+  WsGeom& h = idx->hgeom;
+  h.labels = idx->h_labels.data();
+  h.n = idx->n;
+  h.wst_rows = idx->wst_rows; h.split = idx->split; h.cutoff = idx->cutoff;
+  h.wst_nb = idx->wst_nb.data(); h.wst_off_ptr = idx->wst_off_ptr.data(); h.wst_off = idx->wst_off.data();
+  h.wst_node_ptr = idx->wst_node_ptr.data(); h.wst_nodes = idx->wst_nodes.data();
+  h.sup_rows = idx->sup_rows;
+  h.sup_size = idx->sup_size.data(); h.sup_shift = idx->sup_shift.data(); h.sup_nb = idx->sup_nb.data();
+  h.sup_node_ptr = idx->sup_node_ptr.data(); h.sup_nodes = idx->sup_nodes.data();
+  if (idx->device >= 0) {
+    WS_CUDA(cudaSetDevice(idx->device));
+    WsGeom& d = idx->dgeom;
+    d = h;
+    d.labels = idx->d_labels;
+    WS_TRY(ws_upload(idx, idx->wst_nb, &d.wst_nb));
+    WS_TRY(ws_upload(idx, idx->wst_off_ptr, &d.wst_off_ptr));
+    WS_TRY(ws_upload(idx, idx->wst_off, &d.wst_off));
+    WS_TRY(ws_upload(idx, idx->wst_node_ptr, &d.wst_node_ptr));
+    WS_TRY(ws_upload(idx, idx->wst_nodes, &d.wst_nodes));
+    WS_TRY(ws_upload(idx, idx->sup_size, &d.sup_size));
+    WS_TRY(ws_upload(idx, idx->sup_shift, &d.sup_shift));
+    WS_TRY(ws_upload(idx, idx->sup_nb, &d.sup_nb));
+    WS_TRY(ws_upload(idx, idx->sup_node_ptr, &d.sup_node_ptr));
+    WS_TRY(ws_upload(idx, idx->sup_nodes, &d.sup_nodes));
+    const WsNode* dn = nullptr;
+    WS_TRY(ws_upload(idx, idx->h_nodes, &dn));
+    idx->d_nodes = const_cast<WsNode*>(dn);  // storage owned through geom_dev_allocs
+  }
+  idx->finalized = true;
+  return WS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// batch orchestration
+// ------------------------------------------------------------------------------------------
+}  // extern "C"
+
+static uint32_t ws_task_capacity(const ws_index* idx, int mode) {
+  auto scan_tasks = [&](uint64_t rows) { return (uint32_t)(rows / (uint64_t)idx->opt_scan_chunk + 2); };
+  if (mode == WS_MODE_POSTFILTER || mode == WS_METHOD_SUPER_POSTFILTER) return 1;
+  if (mode == WS_MODE_PREFILTER) return scan_tasks(idx->n);
+  // B-WST methods
+  uint64_t split = idx->split, rows = idx->wst_rows;
+  uint64_t graph = split * split + split + 2 + 2 * (split - 1) * (rows ? rows - 1 : 0);
+  uint64_t last_bucket = 1;
+  if (rows) last_bucket = idx->wst_off[idx->wst_off_ptr[rows - 1] + 1];
+  uint64_t first_bucket_prev = rows >= 2 ? idx->wst_off[idx->wst_off_ptr[rows - 2] + 1] : idx->n;
+  // an uncovered window is shorter than ~2 buckets of the row above the last one
+  uint64_t scans = 2ull * scan_tasks(std::max<uint64_t>(2 * first_bucket_prev, 4 * last_bucket));
+  uint64_t fen = graph + scans;
+  if (mode == WS_METHOD_THREE_SPLIT) return (uint32_t)(3 * fen);
+  return (uint32_t)fen;
+}
+
+template <int KQ, int METRIC>
+static cudaError_t ws_launch_beam_t(bool global_seen, int grid, size_t smem, cudaStream_t s, const WsBeamArgs& a) {
+  cudaError_t e;
+  if (global_seen) {
+    e = cudaFuncSetAttribute(ws_beam_kernel<KQ, METRIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ws_beam_kernel<KQ, METRIC, true><<<grid, WS_CTA_THREADS, smem, s>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(ws_beam_kernel<KQ, METRIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ws_beam_kernel<KQ, METRIC, false><<<grid, WS_CTA_THREADS, smem, s>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+template <int KQ, int METRIC>
+static cudaError_t ws_beam_occupancy_t(bool global_seen, size_t smem, int* blocks) {
+  cudaError_t e;
+  if (global_seen) {
+    e = cudaFuncSetAttribute(ws_beam_kernel<KQ, METRIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_beam_kernel<KQ, METRIC, true>, WS_CTA_THREADS, smem);
+  }
+  e = cudaFuncSetAttribute(ws_beam_kernel<KQ, METRIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_beam_kernel<KQ, METRIC, false>, WS_CTA_THREADS, smem);
+}
+
+template <int KQ, int METRIC>
+static cudaError_t ws_launch_scan_t(int grid, size_t smem, cudaStream_t s, const WsScanArgs& a) {
+  cudaError_t e = cudaFuncSetAttribute(ws_scan_kernel<KQ, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  ws_scan_kernel<KQ, METRIC><<<grid, WS_CTA_THREADS, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+#define WS_DISPATCH_KQ(KQV, METRICV, CALL)                                    \
+  do {                                                                        \
+    if ((METRICV) == 0) {                                                     \
+      switch (KQV) {                                                          \
+        case 1: CALL(1, 0); break;                                            \
+        case 2: CALL(2, 0); break;                                            \
+        case 3: CALL(3, 0); break;                                            \
+        case 4: CALL(4, 0); break;                                            \
+        case 8: CALL(8, 0); break;                                            \
+        case 16: CALL(16, 0); break;                                          \
+        default: CALL(32, 0); break;                                          \
+      }                                                                       \
+    } else {                                                                  \
+      switch (KQV) {                                                          \
+        case 1: CALL(1, 1); break;                                            \
+        case 2: CALL(2, 1); break;                                            \
+        case 3: CALL(3, 1); break;                                            \
+        case 4: CALL(4, 1); break;                                            \
+        case 8: CALL(8, 1); break;                                            \
+        case 16: CALL(16, 1); break;                                          \
+        default: CALL(32, 1); break;                                          \
+      }                                                                       \
+    }                                                                         \
+  } while (0)
+
+static int ws_pick_kq(uint32_t dpad) {
+  uint32_t need = (dpad / 4 + WS_TEAM - 1) / WS_TEAM;
+  const int opts[] = {1, 2, 3, 4, 8, 16, 32};
+  for (int o : opts)
+    if ((uint32_t)o >= need) return o;
+  return 32;
+}
+
+struct WsBatchPlan {
+  int mode;
+  int32_t node;
+  uint32_t k;
+  ws_query_params qp;
+  uint32_t pad_id;
+  bool use_decode;
+};
+
+static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* queries, const float* windows,
+                        uint64_t nq, uint32_t* ids, float* dists, uint32_t flags) {
+  if (!idx) return ws_fail(WS_ERR_BADARG, "null index");
+  if (idx->device < 0) return ws_fail(WS_ERR_CUDA, "host-only geometry index: no CUDA device, and this engine has no CPU fallback");
+  if (!idx->finalized) return ws_fail(WS_ERR_STATE, "ws_index_finalize has not been called");
+  if (nq == 0) return WS_OK;
+  if (!queries || !windows || !ids || !dists) return ws_fail(WS_ERR_BADARG, "null buffer");
+  if (nq > (1ull << 24)) return ws_fail(WS_ERR_BADARG, "nq=%llu above 2^24 per batch", (unsigned long long)nq);
+  const uint32_t k = plan.k;
+  if (k == 0 || k > kMaxK) return ws_fail(WS_ERR_BADARG, "k=%u outside 1..%u", k, kMaxK);
+  const bool needs_graph = plan.mode != WS_MODE_PREFILTER;
+  const ws_query_params& qp = plan.qp;
+  if (needs_graph) {
+    if (idx->h_nodes.empty()) return ws_fail(WS_ERR_STATE, "index has no graphs");
+    if (qp.beam_size < 1) return ws_fail(WS_ERR_BADARG, "beam_size=%lld", (long long)qp.beam_size);
+    if (qp.postfiltering_max_beam > (int64_t)kBeamCapLarge)
+      return ws_fail(WS_ERR_BADARG, "postfiltering_max_beam=%lld above the %u this build keeps in shared memory",
+                     (long long)qp.postfiltering_max_beam, kBeamCapLarge);
+    if (qp.final_beam_multiply < 1) return ws_fail(WS_ERR_BADARG, "final_beam_multiply=%lld", (long long)qp.final_beam_multiply);
+  }
+  if ((plan.mode == WS_MODE_PREFILTER || plan.mode <= 3) && !idx->label_sorted)
+    return ws_fail(WS_ERR_STATE, "this query needs a label-sorted arena");
+  if (plan.mode <= 2 && idx->wst_rows == 0) return ws_fail(WS_ERR_STATE, "no B-WST geometry set");
+  if (plan.mode == 3 && idx->sup_rows == 0) return ws_fail(WS_ERR_STATE, "no super-postfilter geometry set");
+  if (plan.mode == WS_MODE_POSTFILTER && (plan.node < 0 || (size_t)plan.node >= idx->h_nodes.size()))
+    return ws_fail(WS_ERR_BADARG, "bad node handle %d", plan.node);
+
+  WS_CUDA(cudaSetDevice(idx->device));
+  cudaStream_t st = idx->stream;
+  const uint32_t cap = ws_task_capacity(idx, plan.mode);
+  const size_t slots = (size_t)nq * cap;
+  if (slots >= (1ull << 32)) return ws_fail(WS_ERR_BADARG, "batch too large: %llu task slots", (unsigned long long)slots);
+
+  // ---- scratch
+  WS_TRY(ws_ensure(idx, idx->tasks, slots * sizeof(WsTask)));
+  WS_TRY(ws_ensure(idx, idx->res_keys, slots * k * sizeof(uint64_t)));
+  WS_TRY(ws_ensure(idx, idx->res_cnt, slots * sizeof(uint32_t)));
+  WS_TRY(ws_ensure(idx, idx->counts, nq * sizeof(uint32_t)));
+  WS_TRY(ws_ensure(idx, idx->queues, 5 * slots * sizeof(uint32_t)));
+  WS_TRY(ws_ensure(idx, idx->ctrl, 64 * sizeof(uint32_t)));
+  const bool dev_ptrs = (flags & WS_FLAG_DEVICE_PTRS) != 0;
+  const float* dq = queries;
+  const float* dw = windows;
+  uint32_t* dids = ids;
+  float* ddists = dists;
+  if (!dev_ptrs) {
+    WS_TRY(ws_ensure(idx, idx->d_queries, nq * idx->dim * sizeof(float)));
+    WS_TRY(ws_ensure(idx, idx->d_windows, nq * 2 * sizeof(float)));
+    WS_TRY(ws_ensure(idx, idx->d_ids, nq * k * sizeof(uint32_t)));
+    WS_TRY(ws_ensure(idx, idx->d_dists, nq * k * sizeof(float)));
+    WS_CUDA(cudaMemcpyAsync(idx->d_queries.p, queries, nq * idx->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+    WS_CUDA(cudaMemcpyAsync(idx->d_windows.p, windows, nq * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    dq = (const float*)idx->d_queries.p;
+    dw = (const float*)idx->d_windows.p;
+    dids = (uint32_t*)idx->d_ids.p;
+    ddists = (float*)idx->d_dists.p;
+  }
+  // ctrl layout: [0..4] queue counts (graph tiers 0..3, scan = 4), [8..12] queue heads, [16] overflow
+  uint32_t* ctrl = (uint32_t*)idx->ctrl.p;
+  WS_CUDA(cudaMemsetAsync(ctrl, 0, 64 * sizeof(uint32_t), st));
+  uint32_t* queues = (uint32_t*)idx->queues.p;
+
+  // ---- tiers: which launch takes fresh graph tasks
+  const int kq = ws_pick_kq(idx->dpad);
+  int first_tier = 3;
+  if (needs_graph) {
+    for (int t = 0; t < 3; t++)
+      if ((uint64_t)qp.beam_size <= kBeamTierCaps[t]) { first_tier = t; break; }
+  }
+
+  // ---- K3 decomposition
+  WsDecompArgs da;
+  da.g = idx->dgeom;
+  da.p.beam = needs_graph ? (uint32_t)std::min<int64_t>(qp.beam_size, 0x7fffffff) : 0;
+  da.p.has_ratio = qp.has_min_query_to_bucket_ratio;
+  da.p.min_ratio = qp.min_query_to_bucket_ratio;
+  da.p.scan_chunk = (uint32_t)idx->opt_scan_chunk;
+  da.mode = plan.mode;
+  da.node = plan.node;
+  da.windows = dw;
+  da.nq = (uint32_t)nq;
+  da.cap = cap;
+  da.tasks = (WsTask*)idx->tasks.p;
+  da.counts = (uint32_t*)idx->counts.p;
+  da.gq = queues + (size_t)first_tier * slots;
+  da.gq_count = ctrl + first_tier;
+  da.sq = queues + 4 * slots;
+  da.sq_count = ctrl + 4;
+  da.overflow = ctrl + 16;
+  da.stats = idx->d_stats;
+  ws_decompose_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(da);
+  WS_CUDA(cudaGetLastError());
+  idx->launches++;
+
+  // ---- K2 beam search, one persistent launch per tier
+  if (needs_graph) {
+    const uint32_t E = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(8, idx->opt_expand));
+    uint32_t cand_cap = 64;
+    while (cand_cap < E * idx->R) cand_cap <<= 1;
+    for (int t = first_tier; t < 4; t++) {
+      const bool large = (t == 3);
+      const uint32_t beam_cap = large ? kBeamCapLarge : kBeamTierCaps[t];
+      if (t > first_tier && (int64_t)(large ? kBeamTierCaps[2] : kBeamTierCaps[t - 1]) >= qp.postfiltering_max_beam)
+        break;  // no task can need a beam this large
+      uint32_t hash_entries = 0;
+      if (!large) {
+        hash_entries = 1024;
+        while (hash_entries < (uint64_t)idx->opt_hash_factor * beam_cap) hash_entries <<= 1;
+      }
+      size_t smem = (size_t)2 * beam_cap * 8 + (size_t)cand_cap * 24 + (size_t)idx->dpad * 4 + (size_t)hash_entries * 4;
+      if (smem > idx->smem_optin) return ws_fail(WS_ERR_BADARG, "beam tier %d needs %zu B of shared memory (> %zu)", t, smem, idx->smem_optin);
+      int occ = 0;
+#define WS_OCC(KQ_, M_) { cudaError_t _e = ws_beam_occupancy_t<KQ_, M_>(large, smem, &occ); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(_e)); }
+      WS_DISPATCH_KQ(kq, idx->metric, WS_OCC);
+#undef WS_OCC
+      if (occ < 1) return ws_fail(WS_ERR_CUDA, "beam kernel does not fit on an SM (smem %zu)", smem);
+      int grid = idx->num_sms * occ;
+      WsBeamArgs ba;
+      ba.vecs = idx->d_vecs; ba.labels = idx->d_labels; ba.nodes = idx->d_nodes; ba.queries = dq;
+      ba.dim = idx->dim; ba.dpad = idx->dpad; ba.R = idx->R;
+      ba.tasks = (WsTask*)idx->tasks.p; ba.res_keys = (uint64_t*)idx->res_keys.p; ba.res_cnt = (uint32_t*)idx->res_cnt.p;
+      ba.k = k;
+      ba.q_in = queues + (size_t)t * slots; ba.q_in_count = ctrl + t; ba.q_head = ctrl + 8 + t;
+      ba.q_out = (t < 3) ? queues + (size_t)(t + 1) * slots : nullptr;
+      ba.q_out_count = (t < 3) ? ctrl + t + 1 : nullptr;
+      ba.beam_cap = beam_cap; ba.hash_mask = hash_entries ? hash_entries - 1 : 0; ba.cand_cap = cand_cap;
+      ba.expand = E; ba.skip_query_id = (int32_t)idx->opt_skip_query_id;
+      ba.max_beam = qp.postfiltering_max_beam; ba.final_mult = qp.final_beam_multiply;
+      ba.limit = qp.limit > 0 ? qp.limit : (1ll << 62);
+      ba.degree_limit = qp.degree_limit > 0 ? qp.degree_limit : (1ll << 62);
+      ba.bitmap = nullptr; ba.bitmap_words = 0;
+      if (large) {
+        ba.bitmap_words = ((uint64_t)idx->max_node_count + 31) / 32;
+        ba.bitmap_words = (ba.bitmap_words + 31) & ~31ull;
+        WS_TRY(ws_ensure(idx, idx->bitmap, (size_t)grid * ba.bitmap_words * sizeof(uint32_t)));
+        ba.bitmap = (uint32_t*)idx->bitmap.p;
+      }
+      ba.stats = idx->d_stats;
+#define WS_LB(KQ_, M_) { cudaError_t _e = ws_launch_beam_t<KQ_, M_>(large, grid, smem, st, ba); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "beam kernel launch (tier %d): %s", t, cudaGetErrorString(_e)); }
+      WS_DISPATCH_KQ(kq, idx->metric, WS_LB);
+#undef WS_LB
+      idx->launches++;
+    }
+  }
+
+  // ---- K1 scans
+  if (plan.mode != WS_MODE_POSTFILTER && plan.mode != WS_METHOD_SUPER_POSTFILTER) {
+    WsScanArgs sa;
+    sa.vecs = idx->d_vecs; sa.queries = dq; sa.dim = idx->dim; sa.dpad = idx->dpad;
+    sa.tasks = (const WsTask*)idx->tasks.p; sa.res_keys = (uint64_t*)idx->res_keys.p; sa.res_cnt = (uint32_t*)idx->res_cnt.p;
+    sa.k = k;
+    sa.q_in = queues + 4 * slots; sa.q_in_count = ctrl + 4; sa.q_head = ctrl + 8 + 4;
+    sa.stats = idx->d_stats;
+    size_t smem = (size_t)WS_TOPK_BUF * 8 + (size_t)idx->dpad * 4;
+    int grid = idx->num_sms * 8;
+#define WS_LS(KQ_, M_) { cudaError_t _e = ws_launch_scan_t<KQ_, M_>(grid, smem, st, sa); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "scan kernel launch: %s", cudaGetErrorString(_e)); }
+    WS_DISPATCH_KQ(kq, idx->metric, WS_LS);
+#undef WS_LS
+    idx->launches++;
+  }
+
+  // ---- K4 merge + decode
+  {
+    WsMergeArgs ma;
+    ma.counts = (const uint32_t*)idx->counts.p; ma.cap = cap;
+    ma.res_keys = (const uint64_t*)idx->res_keys.p; ma.res_cnt = (const uint32_t*)idx->res_cnt.p;
+    ma.k = k; ma.decode = plan.use_decode ? idx->d_decode : nullptr; ma.pad_id = plan.pad_id;
+    ma.nq = (uint32_t)nq; ma.ids = dids; ma.dists = ddists;
+    int grid = (int)std::min<uint64_t>(nq, (uint64_t)idx->num_sms * 16);
+    ws_merge_kernel<<<grid, WS_CTA_THREADS, 0, st>>>(ma);
+    WS_CUDA(cudaGetLastError());
+    idx->launches++;
+  }
+
+  if (!dev_ptrs) {
+    uint32_t h_overflow = 0;
+    WS_CUDA(cudaMemcpyAsync(ids, dids, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    WS_CUDA(cudaMemcpyAsync(dists, ddists, nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    WS_CUDA(cudaMemcpyAsync(&h_overflow, ctrl + 16, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    WS_CUDA(cudaStreamSynchronize(st));
+    if (h_overflow) return ws_fail(WS_ERR_STATE, "task slot capacity %u overflowed (internal bound too small)", cap);
+  }
+  return WS_OK;
+}
+
+extern "C" {
+
+int ws_prefilter_batch(ws_index* idx, const float* queries, const float* windows, uint64_t nq,
+                       uint32_t k, uint32_t* ids, float* dists, uint32_t flags) {
+  WsBatchPlan p{};
+  p.mode = WS_MODE_PREFILTER;
+  p.node = -1;
+  p.k = k;
+  p.pad_id = 0xFFFFFFFFu;
+  p.use_decode = idx && idx->has_decode;
+  return ws_run_batch(idx, p, queries, windows, nq, ids, dists, flags);
+}
+
+int ws_postfilter_batch(ws_index* idx, int32_t node, const float* queries, const float* windows,
+                        uint64_t nq, const ws_query_params* qp, int pad, uint32_t* ids,
+                        float* dists, uint32_t flags) {
+  if (!qp) return ws_fail(WS_ERR_BADARG, "null query params");
+  if (qp->k < 1 || qp->k > kMaxK) return ws_fail(WS_ERR_BADARG, "k=%lld outside 1..%u", (long long)qp->k, kMaxK);
+  WsBatchPlan p{};
+  p.mode = WS_MODE_POSTFILTER;
+  p.node = node;
+  p.k = (uint32_t)qp->k;
+  p.qp = *qp;
+  p.pad_id = pad == WS_PAD_ZERO ? 0u : 0xFFFFFFFFu;
+  p.use_decode = idx && idx->has_decode;
+  return ws_run_batch(idx, p, queries, windows, nq, ids, dists, flags);
+}
+
+int ws_tree_batch(ws_index* idx, int method, const float* queries, const float* windows,
+                  uint64_t nq, const ws_query_params* qp, uint32_t* ids, float* dists,
+                  uint32_t flags) {
+  if (!qp) return ws_fail(WS_ERR_BADARG, "null query params");
+  if (method < 0 || method > 3) return ws_fail(WS_ERR_BADARG, "unknown method %d", method);
+  if (qp->k < 1 || qp->k > kMaxK) return ws_fail(WS_ERR_BADARG, "k=%lld outside 1..%u", (long long)qp->k, kMaxK);
+  WsBatchPlan p{};
+  p.mode = method;
+  p.node = -1;
+  p.k = (uint32_t)qp->k;
+  p.qp = *qp;
+  p.pad_id = 0u;
+  p.use_decode = idx && idx->has_decode;
+  return ws_run_batch(idx, p, queries, windows, nq, ids, dists, flags);
+}
+
+// ---- plumbing ---------------------------------------------------------------------------
+int ws_index_device(const ws_index* idx, int* device) {
+  if (!idx || !device) return ws_fail(WS_ERR_BADARG, "null argument");
+  *device = idx->device;
+  return WS_OK;
+}
+#define WS_NEED_DEVICE(idx)                                                     \
+  if (!(idx)) return ws_fail(WS_ERR_BADARG, "null index");                      \
+  if ((idx)->device < 0) return ws_fail(WS_ERR_CUDA, "host-only geometry index"); \
+  WS_CUDA(cudaSetDevice((idx)->device));
+
+int ws_index_sync(ws_index* idx) {
+  WS_NEED_DEVICE(idx);
+  WS_CUDA(cudaStreamSynchronize(idx->stream));
+  uint32_t h_overflow = 0;
+  if (idx->ctrl.p) {
+    WS_CUDA(cudaMemcpy(&h_overflow, (uint32_t*)idx->ctrl.p + 16, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (h_overflow) return ws_fail(WS_ERR_STATE, "task slot capacity overflowed in the last batch");
+  }
+  return WS_OK;
+}
+int ws_device_alloc(ws_index* idx, size_t bytes, void** dptr) {
+  WS_NEED_DEVICE(idx);
+  if (!dptr) return ws_fail(WS_ERR_BADARG, "null dptr");
+  WS_CUDA(cudaMalloc(dptr, bytes));
+  return WS_OK;
+}
+int ws_device_free(ws_index* idx, void* dptr) {
+  WS_NEED_DEVICE(idx);
+  WS_CUDA(cudaStreamSynchronize(idx->stream));
+  WS_CUDA(cudaFree(dptr));
+  return WS_OK;
+}
+int ws_host_alloc_pinned(size_t bytes, void** hptr) {
+  if (!hptr) return ws_fail(WS_ERR_BADARG, "null hptr");
+  WS_CUDA(cudaMallocHost(hptr, bytes));
+  return WS_OK;
+}
+int ws_host_free_pinned(void* hptr) {
+  WS_CUDA(cudaFreeHost(hptr));
+  return WS_OK;
+}
+int ws_copy_h2d(ws_index* idx, void* dst, const void* src, size_t bytes) {
+  WS_NEED_DEVICE(idx);
+  WS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, idx->stream));
+  WS_CUDA(cudaStreamSynchronize(idx->stream));
+  return WS_OK;
+}
+int ws_copy_d2h(ws_index* idx, void* dst, const void* src, size_t bytes) {
+  WS_NEED_DEVICE(idx);
+  WS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, idx->stream));
+  WS_CUDA(cudaStreamSynchronize(idx->stream));
+  return WS_OK;
+}
+int ws_timer_start(ws_index* idx) {
+  WS_NEED_DEVICE(idx);
+  WS_CUDA(cudaEventRecord(idx->ev0, idx->stream));
+  return WS_OK;
+}
+int ws_timer_stop(ws_index* idx, float* elapsed_ms) {
+  WS_NEED_DEVICE(idx);
+  if (!elapsed_ms) return ws_fail(WS_ERR_BADARG, "null elapsed_ms");
+  WS_CUDA(cudaEventRecord(idx->ev1, idx->stream));
+  WS_CUDA(cudaEventSynchronize(idx->ev1));
+  WS_CUDA(cudaEventElapsedTime(elapsed_ms, idx->ev0, idx->ev1));
+  return WS_OK;
+}
+int ws_flush_l2(ws_index* idx) {
+  WS_NEED_DEVICE(idx);
+  const size_t bytes = 256ull << 20;  // 2x the 126 MB L2
+  WS_TRY(ws_ensure(idx, idx->flush, bytes));
+  ws_fill_kernel<<<idx->num_sms * 8, 256, 0, idx->stream>>>((uint4*)idx->flush.p, bytes / 16);
+  WS_CUDA(cudaGetLastError());
+  return WS_OK;
+}
+
+int ws_index_get_stats(ws_index* idx, ws_stats* out) {
+  WS_NEED_DEVICE(idx);
+  if (!out) return ws_fail(WS_ERR_BADARG, "null out");
+  unsigned long long h[8];
+  WS_CUDA(cudaStreamSynchronize(idx->stream));
+  WS_CUDA(cudaMemcpy(h, idx->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+  out->graph_searches = h[WS_ST_SEARCHES];
+  out->visited = h[WS_ST_VISITED];
+  out->dist_cmps = h[WS_ST_DISTCMPS];
+  out->scan_points = h[WS_ST_SCANPTS];
+  out->graph_tasks = h[WS_ST_GTASKS];
+  out->scan_tasks = h[WS_ST_STASKS];
+  out->escalated_tasks = h[WS_ST_ESCALATED];
+  out->reserved = 0;
+  return WS_OK;
+}
+int ws_index_reset_stats(ws_index* idx) {
+  WS_NEED_DEVICE(idx);
+  WS_CUDA(cudaStreamSynchronize(idx->stream));
+  WS_CUDA(cudaMemset(idx->d_stats, 0, 8 * sizeof(unsigned long long)));
+  return WS_OK;
+}
+int ws_index_launch_count(const ws_index* idx, uint64_t* out) {
+  if (!idx || !out) return ws_fail(WS_ERR_BADARG, "null argument");
+  *out = idx->launches;
+  return WS_OK;
+}
+int ws_index_set_option(ws_index* idx, const char* name, int64_t value) {
+  if (!idx || !name) return ws_fail(WS_ERR_BADARG, "null argument");
+  std::string s(name);
+  if (s == "expand_width") {
+    if (value < 1 || value > 8) return ws_fail(WS_ERR_BADARG, "expand_width must be 1..8");
+    idx->opt_expand = value;
+  } else if (s == "emulate_query_id_skip") {
+    idx->opt_skip_query_id = value != 0;
+  } else if (s == "scan_chunk") {
+    if (value < 256) return ws_fail(WS_ERR_BADARG, "scan_chunk must be >= 256");
+    idx->opt_scan_chunk = value;
+  } else if (s == "hash_factor") {
+    if (value < 1 || value > 64) return ws_fail(WS_ERR_BADARG, "hash_factor must be 1..64");
+    idx->opt_hash_factor = value;
+  } else {
+    return ws_fail(WS_ERR_BADARG, "unknown option '%s'", name);
+  }
+  return WS_OK;
+}
+int ws_index_hbm_bytes(const ws_index* idx, uint64_t* out) {
+  if (!idx || !out) return ws_fail(WS_ERR_BADARG, "null argument");
+  *out = idx->hbm_bytes;
+  return WS_OK;
+}
+
+int ws_index_task_capacity(ws_index* idx, int method, uint32_t* cap) {
+  if (!idx || !cap) return ws_fail(WS_ERR_BADARG, "null argument");
+  if (!idx->finalized) return ws_fail(WS_ERR_STATE, "ws_index_finalize has not been called");
+  *cap = ws_task_capacity(idx, method);
+  return WS_OK;
+}
+
+int ws_debug_decompose_host(ws_index* idx, int method, const float* windows, uint64_t nq,
+                            const ws_query_params* qp, uint32_t cap, int64_t* out_tasks,
+                            uint32_t* out_counts) {
+  if (!idx || !windows || !qp || !out_tasks || !out_counts) return ws_fail(WS_ERR_BADARG, "null argument");
+  if (!idx->finalized) return ws_fail(WS_ERR_STATE, "ws_index_finalize has not been called");
+  if (method < 0 || (method > 3 && method != WS_MODE_PREFILTER)) return ws_fail(WS_ERR_BADARG, "unknown method %d", method);
+  if (method <= 2 && idx->wst_rows == 0) return ws_fail(WS_ERR_STATE, "no B-WST geometry set");
+  if (method == 3 && idx->sup_rows == 0) return ws_fail(WS_ERR_STATE, "no super-postfilter geometry set");
+  WsDecompParams p;
+  p.beam = (uint32_t)qp->beam_size;
+  p.has_ratio = qp->has_min_query_to_bucket_ratio;
+  p.min_ratio = qp->min_query_to_bucket_ratio;
+  p.scan_chunk = (uint32_t)idx->opt_scan_chunk;
+  std::vector<WsTask> slots(cap);
+  for (uint64_t q = 0; q < nq; q++) {
+    WsEmitter em;
+    em.slots = slots.data(); em.cap = cap; em.count = 0; em.overflow = 0; em.query = (uint32_t)q;
+    em.beam = p.beam; em.scan_chunk = p.scan_chunk;
+    float lo = windows[2 * q], hi = windows[2 * q + 1];
+    switch (method) {
+      case 0: ws_decompose_fenwick(idx->hgeom, lo, hi, 0, em); break;
+      case 1: ws_decompose_opt_postfilter(idx->hgeom, lo, hi, p, em); break;
+      case 2: ws_decompose_three_split(idx->hgeom, lo, hi, p, em); break;
+      case 3: ws_decompose_super(idx->hgeom, lo, hi, em); break;
+      default: {
+        uint64_t s = ws_prefilter_bound(idx->hgeom.labels, idx->n, lo);
+        uint64_t e = ws_prefilter_bound(idx->hgeom.labels, idx->n, hi);
+        em.scan(s, e, lo, hi);
+      }
+    }
+    if (em.overflow) return ws_fail(WS_ERR_STATE, "query %llu overflowed capacity %u", (unsigned long long)q, cap);
+    out_counts[q] = em.count;
+    for (uint32_t i = 0; i < cap; i++) {
+      int64_t* o = out_tasks + ((size_t)q * cap + i) * 4;
+      if (i < em.count) {
+        const WsTask& t = slots[i];
+        o[0] = t.node;
+        if (t.node >= 0) { o[1] = idx->h_nodes[t.node].start; o[2] = o[1] + idx->h_nodes[t.node].count; }
+        else { o[1] = t.a; o[2] = t.b; }
+        o[3] = t.flags;
+      } else {
+        o[0] = o[1] = o[2] = o[3] = -2;
+      }
+    }
+  }
+  return WS_OK;
+}
+
+}  // extern "C"

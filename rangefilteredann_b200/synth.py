@@ -1,0 +1,134 @@
+"""Deterministic synthetic inputs of the shapes BASELINE.json names.
+
+Nothing here is on the query hot path: it produces the vectors / labels / windows /
+ground truth that both the reference (oracle/_ref) and this engine are fed.
+
+Recipes mirror the reference's dataset scripts:
+  * windows  — generate_datasets/filter_generation_utils.py:9-74
+               (`generate_random_query_filter_ranges`, follow_data_distribution=True)
+  * ground truth — generate_datasets/filter_generation_utils.py:142-168 (closed interval)
+  * angular sets are L2-normalised — generate_datasets/generate_ann_benchmarks_datasets.py:42-44
+"""
+from __future__ import annotations
+
+import numpy as np
+
+FILTER_POWERS = list(range(-16, 1))  # filter_generation_utils.py:5
+TOP_K = 10                           # filter_generation_utils.py:6
+
+
+def make_vectors(n: int, d: int, rng: np.random.Generator, centers: np.ndarray,
+                 normalize: bool = False) -> np.ndarray:
+    """256-centre Gaussian mixture, sigma 0.5."""
+    out = np.empty((n, d), dtype=np.float32)
+    step = 1 << 18
+    for s in range(0, n, step):
+        e = min(n, s + step)
+        c = rng.integers(0, centers.shape[0], size=e - s)
+        out[s:e] = centers[c] + 0.5 * rng.standard_normal((e - s, d), dtype=np.float32)
+    if normalize:
+        out /= np.linalg.norm(out, axis=1, keepdims=True)
+    return out
+
+
+def make_dataset(n: int, d: int, nq: int, seed: int = 0, angular: bool = False,
+                 label_kind: str = "unique"):
+    """Returns (data[n,d] f32, queries[nq,d] f32, labels[n] f32).
+
+    label_kind:
+      "unique"    rng.permutation(n)/n as fp32 — unique for n <= 2^24 (avoids the
+                  equal-label sort-order hazard)
+      "uniform"   rng.uniform(0,1)
+      "timestamp" RedCaps-like integer seconds (generate_redcaps_data.py:77-80)
+    """
+    rng = np.random.default_rng(seed)
+    centers = rng.standard_normal((256, d)).astype(np.float32)
+    data = make_vectors(n, d, rng, centers, normalize=angular)
+    queries = make_vectors(nq, d, rng, centers, normalize=angular)
+    if label_kind == "unique":
+        labels = (rng.permutation(n).astype(np.float64) / n).astype(np.float32)
+    elif label_kind == "uniform":
+        labels = rng.uniform(0, 1, size=n).astype(np.float32)
+    elif label_kind == "timestamp":
+        labels = (1.2e9 + rng.integers(0, int(3.5e8), size=n)).astype(np.float32)
+    else:
+        raise ValueError(label_kind)
+    return data, queries, labels
+
+
+def make_windows(labels: np.ndarray, power: int, nq: int, seed: int) -> np.ndarray:
+    """Window recipe of filter_generation_utils.py:9-52 for fraction 2**power.
+
+    Returned as float32 [nq,2]: the boundary casts windows to pair<float,float>
+    (prefiltering.h:126) so both implementations see exactly these values.
+    """
+    rng = np.random.default_rng(seed)
+    s = np.sort(labels.astype(np.float64))
+    n = len(s)
+    frac = 2.0 ** power
+    if frac == 1:
+        lo = s[0] - rng.integers(1, 100)
+        hi = s[-1] + rng.integers(1, 100)
+        return np.tile(np.array([[lo, hi]], dtype=np.float32), (nq, 1))
+    m = int(n * frac)
+    start = rng.integers(0, n - m, size=nq)
+    end = start + m
+    lo_v, hi_v = s[start], s[end]
+    gap_l = np.where(start > 0, lo_v - s[np.maximum(start - 1, 0)], 1.0)
+    gap_r = np.where(end < n - 1, s[np.minimum(end + 1, n - 1)] - hi_v, 1.0)
+    lo = lo_v - rng.uniform(size=nq) * gap_l
+    hi = hi_v + rng.uniform(size=nq) * gap_r
+    return np.stack([lo, hi], axis=1).astype(np.float32)
+
+
+def ground_truth(data: np.ndarray, queries: np.ndarray, labels: np.ndarray,
+                 windows: np.ndarray, k: int = TOP_K, angular: bool = False) -> np.ndarray:
+    """Brute-force closed-interval top-k (filter_generation_utils.py:142-168), numpy.
+
+    Slices the label-sorted copy so cost is O(sum of window sizes). Pads with -1 when
+    a window holds fewer than k points.
+    """
+    order = np.argsort(labels, kind="stable")
+    sl = labels[order]
+    sd = data[order]
+    gt = np.full((len(queries), k), -1, dtype=np.int64)
+    for i, q in enumerate(queries):
+        a = np.searchsorted(sl, windows[i, 0], side="left")
+        b = np.searchsorted(sl, windows[i, 1], side="right")
+        if b <= a:
+            continue
+        x = sd[a:b]
+        if angular:
+            dist = -(x @ q)
+        else:
+            diff = x - q
+            dist = np.einsum("ij,ij->i", diff, diff)
+        kk = min(k, b - a)
+        idx = np.argpartition(dist, kk - 1)[:kk] if kk < b - a else np.arange(b - a)
+        idx = idx[np.argsort(dist[idx], kind="stable")]
+        gt[i, :kk] = order[a + idx]
+    return gt
+
+
+def recall(results: np.ndarray, gt: np.ndarray, k: int = TOP_K) -> float:
+    """compute_recall as the driver CALLS it (run_our_method.py:174-180,256: arguments
+    swapped, so the denominator is the number of distinct returned ids)."""
+    tot = 0.0
+    for i in range(len(results)):
+        res = set(int(x) for x in results[i][:k])
+        g = set(int(x) for x in gt[i][:k])
+        tot += len(res & g) / len(res)
+    return tot / len(results)
+
+
+def recall_std(results: np.ndarray, gt: np.ndarray, k: int = TOP_K) -> float:
+    """|top-k ∩ GT| / |GT| averaged (the textbook definition; GT pads (-1) ignored)."""
+    tot = 0.0
+    for i in range(len(results)):
+        g = set(int(x) for x in gt[i][:k] if x >= 0)
+        if not g:
+            tot += 1.0
+            continue
+        res = set(int(x) for x in results[i][:k])
+        tot += len(res & g) / len(g)
+    return tot / len(results)

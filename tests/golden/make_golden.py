@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Generates tests/golden/* from the UNMODIFIED reference (oracle/_ref), in the build
+container where /root/reference exists.  Committed outputs:
+
+  tiny/{wst,super,flat}/*.bin   the reference builder's graph files for the `tiny` dataset
+                                (3000 x 16, seed 7; rangefilteredann_b200.synth.make_dataset)
+  tiny_ref_outputs.npz          reference batch_search ids/dists for every query method on
+                                fixed windows (incl. the edge cases of SURVEY.md App. D)
+
+Run: python tests/golden/make_golden.py      (after `make -C oracle ref`)
+"""
+import os
+import shutil
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+os.environ["PARLAY_NUM_THREADS"] = "8"
+
+from conftest import _load_ext, find_ext  # noqa: E402
+from rangefilteredann_b200 import synth  # noqa: E402
+from golden_cases import tiny_cases, TINY  # noqa: E402
+
+
+def main():
+    ref = _load_ext(find_ext(os.path.join(ROOT, "oracle", "_ref")))
+    data, queries, labels = synth.make_dataset(TINY["n"], TINY["d"], TINY["nq"], TINY["seed"])
+    out = {}
+    tiny_dir = os.path.join(HERE, "tiny")
+    for kind in ("wst", "super", "flat"):
+        os.makedirs(os.path.join(tiny_dir, kind), exist_ok=True)
+    bp = lambda kind: ref.BuildParams(64, 500, 1.0, os.path.join(tiny_dir, kind) + "/")
+    tree = ref.VamanaRangeFilterTreeIndexFloatEuclidian(data, labels, TINY["cutoff"], 2, bp("wst"))
+    sup = ref.SuperOptimizedPostfilterTreeIndexFloatEuclidian(data, labels, TINY["cutoff"], 2.0, 0.5, bp("super"))
+    flat = ref.PostfilterVamanaIndexFloatEuclidian(data, labels, bp("flat"))
+    pre = ref.PrefilterIndexFloatEuclidian(data, labels)
+    for name, windows, qkw in tiny_cases(labels):
+        nq = len(windows)
+        q = queries[:nq]
+        qp = ref.QueryParams(10, qkw["beam"], 1.35, 10_000_000, 10_000, qkw["mult"], qkw["max_beam"], qkw.get("ratio"), False)
+        out[f"{name}/windows"] = windows
+        if qkw.get("prefilter", True):
+            ids, d = pre.batch_search(q, windows, nq, qp)
+            out[f"{name}/prefilter/ids"], out[f"{name}/prefilter/dists"] = ids, d
+        for method in ("fenwick", "optimized_postfilter", "three_split"):
+            if method == "fenwick" and qkw.get("skip_fenwick"):
+                continue
+            ids, d = tree.batch_search(q, windows, nq, method, qp)
+            out[f"{name}/{method}/ids"], out[f"{name}/{method}/dists"] = ids, d
+        ids, d = sup.batch_search(q, windows, nq, qp)
+        out[f"{name}/super/ids"], out[f"{name}/super/dists"] = ids, d
+        ids, d = flat.batch_search(q, windows, nq, qp)
+        out[f"{name}/flat/ids"], out[f"{name}/flat/dists"] = ids, d
+    np.savez_compressed(os.path.join(HERE, "tiny_ref_outputs.npz"), **out)
+    print("wrote", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,38 @@
+"""Window sets shared by the golden generator and the parity tests."""
+import numpy as np
+
+from rangefilteredann_b200 import synth
+
+TINY = dict(n=3000, d=16, nq=64, seed=7, cutoff=500)
+
+
+def tiny_cases(labels):
+    """Yields (name, windows[nq,2] f32, query-param dict)."""
+    n = len(labels)
+    s = np.sort(labels.astype(np.float64))
+    cases = []
+    # random windows of several fractions (filter_generation_utils.py recipe)
+    for power in (-8, -5, -3, -1, 0):
+        w = synth.make_windows(labels, power, TINY["nq"], seed=100 + power)
+        # the prefilter reads past its frontier when a window holds < k points
+        # (prefiltering.h:139-142), so only compare it where that cannot happen
+        cases.append((f"pow{power}", w, dict(beam=20, mult=2, max_beam=10000, prefilter=power > -8)))
+    # SURVEY.md Appendix D style windows expressed in ranks -> labels (midpoints)
+    def mid(r):  # a value strictly between rank r-1 and rank r
+        r = int(r)
+        if r <= 0:
+            return s[0] - 0.01
+        if r >= n:
+            return s[-1] + 0.01
+        return 0.5 * (s[r - 1] + s[r])
+    rank_windows = [(101, 2601), (701, 1601), (11, 391), (1401, 1701), (375, 1126), (0, 3000),
+                    (0, 375), (2000, 2626), (1499, 1501), (5, 20), (2990, 3000), (750, 1500)]
+    w = np.array([[mid(a), mid(b)] for a, b in rank_windows], dtype=np.float32)
+    cases.append(("appendixD", w, dict(beam=10, mult=1, max_beam=10000, prefilter=False)))
+    # small max beam: doubling stops early and slots stay padded
+    w = synth.make_windows(labels, -6, 32, seed=55)
+    cases.append(("maxbeam40", w, dict(beam=10, mult=1, max_beam=40, prefilter=True)))
+    # ratio fallback of optimized_postfilter (range_filter_tree.h:460-466)
+    w = synth.make_windows(labels, -3, 32, seed=56)
+    cases.append(("ratio", w, dict(beam=20, mult=1, max_beam=10000, ratio=1.5, prefilter=True)))
+    return cases
