@@ -1,0 +1,66 @@
+"""CPU: pins the oracle restatement (oracle/wsann_oracle.cpp) against golden vectors produced
+by the unmodified reference (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from golden_cases import TINY, tiny_cases
+from oracle_api import Oracle
+from rangefilteredann_b200 import synth
+
+PADS = {"prefilter": 0xFFFFFFFF, "flat": 0xFFFFFFFF}
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    data, queries, labels = synth.make_dataset(TINY["n"], TINY["d"], TINY["nq"], TINY["seed"])
+    gold = np.load(os.path.join(GOLDEN, "tiny_ref_outputs.npz"))
+    cache = lambda kind: os.path.join(GOLDEN, "tiny", kind) + "/"
+    orc = dict(
+        wst=Oracle("wst", data, labels, cache("wst"), cutoff=TINY["cutoff"]),
+        sup=Oracle("super", data, labels, cache("super"), cutoff=TINY["cutoff"]),
+        flat=Oracle("flat", data, labels, cache("flat")),
+        pre=Oracle("prefilter", data, labels, None),
+    )
+    return dict(queries=queries, labels=labels, gold=gold, orc=orc, cases=tiny_cases(labels))
+
+
+def _oracle_for(t, method):
+    return {"prefilter": t["orc"]["pre"], "super": t["orc"]["sup"], "flat": t["orc"]["flat"]}.get(method, t["orc"]["wst"])
+
+
+@pytest.mark.parametrize("method", ["prefilter", "fenwick", "optimized_postfilter", "three_split", "super", "flat"])
+def test_oracle_matches_reference_bit_for_bit(tiny, method):
+    checked = 0
+    for name, windows, qkw in tiny["cases"]:
+        key = f"{name}/{method}/ids"
+        if key not in tiny["gold"]:
+            continue
+        rids, rd = tiny["gold"][key], tiny["gold"][f"{name}/{method}/dists"]
+        q = tiny["queries"][: len(windows)]
+        ids, d = _oracle_for(tiny, method).batch(method, q, windows, k=10, beam=qkw["beam"], mult=qkw["mult"],
+                                                 max_beam=qkw["max_beam"], ratio=qkw.get("ratio"),
+                                                 pad_id=PADS.get(method, 0))
+        # distances: the reference-order mode reproduces the AVX summation exactly
+        assert np.array_equal(d, rd), f"{name}/{method}: distances differ (max rel {np.max(np.abs(d - rd) / np.maximum(np.abs(rd), 1e-30)):.3g})"
+        # ids: identical except inside groups of exactly equal distance (unstable sort in the reference)
+        diff = ids != rids
+        if diff.any():
+            for i, j in zip(*np.nonzero(diff)):
+                assert (rd[i] == rd[i, j]).sum() > 1 or rd[i, j] == rd[i, -1], f"{name}/{method} row {i} col {j}"
+        checked += 1
+    assert checked > 0
+
+
+def test_device_order_mode_is_close(tiny):
+    """dist_mode 1 (the kernels' summation order) differs from the reference order only in
+    the last bits."""
+    data, queries, labels = synth.make_dataset(TINY["n"], TINY["d"], TINY["nq"], TINY["seed"])
+    o1 = Oracle("prefilter", data, labels, None, dist_mode=1)
+    w = synth.make_windows(labels, -3, 32, seed=9)
+    i0, d0 = tiny["orc"]["pre"].batch("prefilter", queries[:32], w, pad_id=0xFFFFFFFF)
+    i1, d1 = o1.batch("prefilter", queries[:32], w, pad_id=0xFFFFFFFF)
+    assert np.allclose(d0, d1, rtol=1e-5)
+    assert (i0 == i1).mean() > 0.99
