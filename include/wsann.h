@@ -87,7 +87,7 @@ typedef struct ws_stats {
   uint64_t graph_tasks;        /* (query,node) sub-index queries dispatched              */
   uint64_t scan_tasks;         /* (query,slice) brute-force tasks dispatched             */
   uint64_t escalated_tasks;    /* tasks that left the first beam tier                    */
-  uint64_t reserved;
+  uint64_t beam_sum;           /* sum of beamSize over graph_searches (frontier bytes) */
 } ws_stats;
 
 typedef struct ws_index ws_index; /* opaque: one HBM arena on one device */
@@ -176,9 +176,14 @@ int ws_index_reset_stats(ws_index* idx);
 int ws_index_launch_count(const ws_index* idx, uint64_t* out);
 /* tuning knobs: "expand_width" (nodes expanded per beam-search step, default 1 = reference
  * order), "emulate_query_id_skip" (beamSearch.h:128 `a == p.id()`, default 1),
- * "scan_chunk" (rows per brute-force task) */
+ * "scan_chunk" (rows per brute-force task), "profile_kernels", "hash_factor" */
 int ws_index_set_option(ws_index* idx, const char* name, int64_t value);
 int ws_index_hbm_bytes(const ws_index* idx, uint64_t* out);
+/* With option "profile_kernels" = 1 every kernel launch is bracketed by CUDA events on the
+ * index stream.  Returns accumulated milliseconds / launch counts per kernel kind:
+ * 0 decompose, 1..3 beam search (shared-memory tiers 64/256/1024), 4 beam search (large
+ * tier), 5 scan, 6 merge, 7 unused.  ms_out / launches_out are [8]. */
+int ws_index_kernel_times(ws_index* idx, double* ms_out, uint64_t* launches_out, int reset);
 
 /* Host-side evaluation of the window→task decomposition, same code the device runs
  * (testing hook: lets CPU-only CI check the tree logic; performs no search).

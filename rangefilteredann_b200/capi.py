@@ -26,7 +26,7 @@ class QueryParamsC(C.Structure):
 
 class StatsC(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("graph_searches", "visited", "dist_cmps", "scan_points", "graph_tasks",
-                                           "scan_tasks", "escalated_tasks", "reserved")]
+                                           "scan_tasks", "escalated_tasks", "beam_sum")]
 
 
 def query_params(k=10, beam=10, final_multiply=1, max_beam=10000, ratio=None, cut=1.35, limit=10_000_000,
@@ -70,6 +70,7 @@ def lib() -> C.CDLL:
         L.ws_index_reset_stats.argtypes = [vp]
         L.ws_index_launch_count.argtypes = [vp, C.POINTER(u64)]
         L.ws_index_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+        L.ws_index_kernel_times.argtypes = [vp, vp, vp, C.c_int]
         L.ws_index_hbm_bytes.argtypes = [vp, C.POINTER(u64)]
         L.ws_index_task_capacity.argtypes = [vp, C.c_int, C.POINTER(u32)]
         L.ws_debug_decompose_host.argtypes = [vp, C.c_int, vp, u64, C.POINTER(QueryParamsC), u32, vp, vp]
@@ -141,7 +142,7 @@ class Handle:
     def stats(self) -> dict:
         s = StatsC()
         check(lib().ws_index_get_stats(self.raw, C.byref(s)), "ws_index_get_stats")
-        return {n: getattr(s, n) for n, _ in StatsC._fields_ if n != "reserved"}
+        return {n: getattr(s, n) for n, _ in StatsC._fields_}
 
     def reset_stats(self):
         check(lib().ws_index_reset_stats(self.raw), "ws_index_reset_stats")
@@ -153,6 +154,14 @@ class Handle:
 
     def set_option(self, name: str, value: int):
         check(lib().ws_index_set_option(self.raw, name.encode(), int(value)), "ws_index_set_option")
+
+    KERNEL_KINDS = ("decompose", "beam64", "beam256", "beam1024", "beam_large", "scan", "merge", "unused")
+
+    def kernel_times(self, reset=True) -> dict:
+        ms = np.zeros(8, np.float64)
+        n = np.zeros(8, np.uint64)
+        check(lib().ws_index_kernel_times(self.raw, ptr(ms), ptr(n), 1 if reset else 0), "ws_index_kernel_times")
+        return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(self.KERNEL_KINDS) if n[i]}
 
     def hbm_bytes(self) -> int:
         v = C.c_uint64()

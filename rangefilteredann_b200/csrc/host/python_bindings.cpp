@@ -82,7 +82,8 @@ static void add_variant(py::module_& m, const std::string& sfx) {
              Batch b = check_batch(queries, filters, num_queries, self.dim());
              return run(b.nq, qp.k, [&](unsigned int* ids, float* dists) { self.batch_search(b.queries, b.filters, b.nq, qp, ids, dists); });
            },
-           "queries"_a, "filters"_a, "num_queries"_a, "query_params"_a);
+           "queries"_a, "filters"_a, "num_queries"_a, "query_params"_a)
+      .def("_arena_handle", [](Prefilter& self) { return (uintptr_t)self.arena().get(); });
 
   py::class_<Postfilter>(m, ("PostfilterVamanaIndex" + sfx).c_str())
       .def(py::init([](FArray points, FArray filters, BuildParams bp) {
@@ -95,7 +96,8 @@ static void add_variant(py::module_& m, const std::string& sfx) {
              Batch b = check_batch(queries, filters, num_queries, self.dim());
              return run(b.nq, qp.k, [&](unsigned int* ids, float* dists) { self.batch_search(b.queries, b.filters, b.nq, qp, ids, dists); });
            },
-           "queries"_a, "filters"_a, "num_queries"_a, "query_params"_a);
+           "queries"_a, "filters"_a, "num_queries"_a, "query_params"_a)
+      .def("_arena_handle", [](Postfilter& self) { return (uintptr_t)self.arena().get(); });
 
   py::class_<Tree>(m, ("VamanaRangeFilterTreeIndex" + sfx).c_str())
       .def(py::init([](FArray points, FArray filter_values, int32_t cutoff, size_t split_factor, BuildParams bp) {

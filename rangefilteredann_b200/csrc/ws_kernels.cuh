@@ -22,7 +22,7 @@ enum { WS_MODE_PREFILTER = 10, WS_MODE_POSTFILTER = 11 };
 
 // stats slots (unsigned long long[8]) — order of ws_stats
 enum { WS_ST_SEARCHES = 0, WS_ST_VISITED, WS_ST_DISTCMPS, WS_ST_SCANPTS, WS_ST_GTASKS, WS_ST_STASKS,
-       WS_ST_ESCALATED, WS_ST_RESERVED };
+       WS_ST_ESCALATED, WS_ST_BEAMSUM };
 
 // ------------------------------------------------------------------------------------------
 // K3: decomposition
@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(WS_CTA_THREADS) ws_beam_kernel(WsBeamArgs A) {
         atomicAdd(A.stats + WS_ST_SEARCHES, 1ull);
         atomicAdd(A.stats + WS_ST_VISITED, nvis);
         atomicAdd(A.stats + WS_ST_DISTCMPS, ncmp);
+        atomicAdd(A.stats + WS_ST_BEAMSUM, (unsigned long long)B);
       }
       // ------------------------------------------------------------------ end beam_search
       if (phase == 1) break;

@@ -51,6 +51,7 @@ static const uint32_t kBeamTierCaps[3] = {64, 256, 1024};  // shared-memory-visi
 static const uint32_t kBeamCapLarge = 12288;                // global-bitmap tier
 static const uint32_t kMaxK = WS_TOPK_BUF / 2;
 static const size_t kAdjSlabBytes = 256ull << 20;
+#define WS_NUM_KERNEL_KINDS 8  // 0 decompose, 1-3 beam tiers 64/256/1024, 4 beam large, 5 scan, 6 merge
 
 struct WsDevBuf {
   void* p = nullptr;
@@ -109,6 +110,42 @@ struct ws_index {
       bitmap, flush;
   unsigned long long* d_stats = nullptr;
   uint64_t launches = 0;
+
+  // optional per-kernel CUDA-event timing (ws_index_kernel_times)
+  int64_t opt_profile = 0;
+  std::vector<cudaEvent_t> ev_pool;
+  struct EvPair { int kind; size_t a, b; };
+  std::vector<EvPair> ev_pairs;
+  size_t ev_used = 0;
+  double kernel_ms[WS_NUM_KERNEL_KINDS] = {0};
+  uint64_t kernel_launches[WS_NUM_KERNEL_KINDS] = {0};
+};
+
+// brackets one kernel launch with events on the index stream when profiling is on
+struct WsKernelScope {
+  ws_index* idx;
+  int kind;
+  size_t a = 0;
+  bool on;
+  static size_t grab(ws_index* idx) {
+    if (idx->ev_used == idx->ev_pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      idx->ev_pool.push_back(e);
+    }
+    return idx->ev_used++;
+  }
+  WsKernelScope(ws_index* i, int k) : idx(i), kind(k), on(i->opt_profile != 0) {
+    if (on) { a = grab(idx); cudaEventRecord(idx->ev_pool[a], idx->stream); }
+  }
+  ~WsKernelScope() {
+    idx->launches++;
+    if (on) {
+      size_t b = grab(idx);
+      cudaEventRecord(idx->ev_pool[b], idx->stream);
+      idx->ev_pairs.push_back({kind, a, b});
+    }
+  }
 };
 
 static int ws_ensure(ws_index* idx, WsDevBuf& b, size_t bytes) {
@@ -242,6 +279,7 @@ void ws_index_destroy(ws_index* idx) {
     WsDevBuf* bufs[] = {&idx->tasks, &idx->res_keys, &idx->res_cnt, &idx->counts, &idx->queues, &idx->ctrl,
                         &idx->d_queries, &idx->d_windows, &idx->d_ids, &idx->d_dists, &idx->bitmap, &idx->flush};
     for (WsDevBuf* b : bufs) cudaFree(b->p);
+    for (cudaEvent_t e : idx->ev_pool) cudaEventDestroy(e);
     if (idx->ev0) cudaEventDestroy(idx->ev0);
     if (idx->ev1) cudaEventDestroy(idx->ev1);
     if (idx->stream) cudaStreamDestroy(idx->stream);
@@ -609,9 +647,11 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
   da.sq_count = ctrl + 4;
   da.overflow = ctrl + 16;
   da.stats = idx->d_stats;
-  ws_decompose_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(da);
+  {
+    WsKernelScope ks(idx, 0);
+    ws_decompose_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(da);
+  }
   WS_CUDA(cudaGetLastError());
-  idx->launches++;
 
   // ---- K2 beam search, one persistent launch per tier
   if (needs_graph) {
@@ -658,9 +698,11 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
       }
       ba.stats = idx->d_stats;
 #define WS_LB(KQ_, M_) { cudaError_t _e = ws_launch_beam_t<KQ_, M_>(large, grid, smem, st, ba); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "beam kernel launch (tier %d): %s", t, cudaGetErrorString(_e)); }
-      WS_DISPATCH_KQ(kq, idx->metric, WS_LB);
+      {
+        WsKernelScope ks(idx, 1 + t);
+        WS_DISPATCH_KQ(kq, idx->metric, WS_LB);
+      }
 #undef WS_LB
-      idx->launches++;
     }
   }
 
@@ -675,9 +717,11 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
     size_t smem = (size_t)WS_TOPK_BUF * 8 + (size_t)idx->dpad * 4;
     int grid = idx->num_sms * 8;
 #define WS_LS(KQ_, M_) { cudaError_t _e = ws_launch_scan_t<KQ_, M_>(grid, smem, st, sa); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "scan kernel launch: %s", cudaGetErrorString(_e)); }
-    WS_DISPATCH_KQ(kq, idx->metric, WS_LS);
+    {
+      WsKernelScope ks(idx, 5);
+      WS_DISPATCH_KQ(kq, idx->metric, WS_LS);
+    }
 #undef WS_LS
-    idx->launches++;
   }
 
   // ---- K4 merge + decode
@@ -688,9 +732,11 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
     ma.k = k; ma.decode = plan.use_decode ? idx->d_decode : nullptr; ma.pad_id = plan.pad_id;
     ma.nq = (uint32_t)nq; ma.ids = dids; ma.dists = ddists;
     int grid = (int)std::min<uint64_t>(nq, (uint64_t)idx->num_sms * 16);
-    ws_merge_kernel<<<grid, WS_CTA_THREADS, 0, st>>>(ma);
+    {
+      WsKernelScope ks(idx, 6);
+      ws_merge_kernel<<<grid, WS_CTA_THREADS, 0, st>>>(ma);
+    }
     WS_CUDA(cudaGetLastError());
-    idx->launches++;
   }
 
   if (!dev_ptrs) {
@@ -837,7 +883,7 @@ int ws_index_get_stats(ws_index* idx, ws_stats* out) {
   out->graph_tasks = h[WS_ST_GTASKS];
   out->scan_tasks = h[WS_ST_STASKS];
   out->escalated_tasks = h[WS_ST_ESCALATED];
-  out->reserved = 0;
+  out->beam_sum = h[WS_ST_BEAMSUM];
   return WS_OK;
 }
 int ws_index_reset_stats(ws_index* idx) {
@@ -862,6 +908,8 @@ int ws_index_set_option(ws_index* idx, const char* name, int64_t value) {
   } else if (s == "scan_chunk") {
     if (value < 256) return ws_fail(WS_ERR_BADARG, "scan_chunk must be >= 256");
     idx->opt_scan_chunk = value;
+  } else if (s == "profile_kernels") {
+    idx->opt_profile = value != 0;
   } else if (s == "hash_factor") {
     if (value < 1 || value > 64) return ws_fail(WS_ERR_BADARG, "hash_factor must be 1..64");
     idx->opt_hash_factor = value;
@@ -870,6 +918,25 @@ int ws_index_set_option(ws_index* idx, const char* name, int64_t value) {
   }
   return WS_OK;
 }
+int ws_index_kernel_times(ws_index* idx, double* ms_out, uint64_t* launches_out, int reset) {
+  WS_NEED_DEVICE(idx);
+  WS_CUDA(cudaStreamSynchronize(idx->stream));
+  for (const ws_index::EvPair& p : idx->ev_pairs) {
+    float ms = 0.f;
+    WS_CUDA(cudaEventElapsedTime(&ms, idx->ev_pool[p.a], idx->ev_pool[p.b]));
+    idx->kernel_ms[p.kind] += ms;
+    idx->kernel_launches[p.kind]++;
+  }
+  idx->ev_pairs.clear();
+  idx->ev_used = 0;
+  for (int i = 0; i < WS_NUM_KERNEL_KINDS; i++) {
+    if (ms_out) ms_out[i] = idx->kernel_ms[i];
+    if (launches_out) launches_out[i] = idx->kernel_launches[i];
+    if (reset) { idx->kernel_ms[i] = 0; idx->kernel_launches[i] = 0; }
+  }
+  return WS_OK;
+}
+
 int ws_index_hbm_bytes(const ws_index* idx, uint64_t* out) {
   if (!idx || !out) return ws_fail(WS_ERR_BADARG, "null argument");
   *out = idx->hbm_bytes;

@@ -23,7 +23,7 @@ os.environ["PARLAY_NUM_THREADS"] = "8"
 
 from conftest import _load_ext, find_ext  # noqa: E402
 from rangefilteredann_b200 import synth  # noqa: E402
-from golden_cases import tiny_cases, TINY  # noqa: E402
+from golden_cases import tiny_cases, tiny_mips_cases, TINY, TINY_MIPS  # noqa: E402
 
 
 def main():
@@ -56,6 +56,30 @@ def main():
         ids, d = flat.batch_search(q, windows, nq, qp)
         out[f"{name}/flat/ids"], out[f"{name}/flat/dists"] = ids, d
     np.savez_compressed(os.path.join(HERE, "tiny_ref_outputs.npz"), **out)
+
+    # ---- MIPS variant (Mips_Point, padded rows)
+    out = {}
+    data, queries, labels = synth.make_dataset(TINY_MIPS["n"], TINY_MIPS["d"], TINY_MIPS["nq"], TINY_MIPS["seed"], angular=True)
+    mdir = os.path.join(HERE, "tiny_mips")
+    for kind in ("wst", "super"):
+        os.makedirs(os.path.join(mdir, kind), exist_ok=True)
+    bpm = lambda kind: ref.BuildParams(64, 500, 1.0, os.path.join(mdir, kind) + "/")
+    tree = ref.VamanaRangeFilterTreeIndexFloatMips(data, labels, TINY_MIPS["cutoff"], 2, bpm("wst"))
+    sup = ref.SuperOptimizedPostfilterTreeIndexFloatMips(data, labels, TINY_MIPS["cutoff"], 2.0, 0.5, bpm("super"))
+    pre = ref.PrefilterIndexFloatMips(data, labels)
+    for name, windows, qkw in tiny_mips_cases(labels):
+        nq = len(windows)
+        q = queries[:nq]
+        qp = ref.QueryParams(10, qkw["beam"], 1.35, 10_000_000, 10_000, qkw["mult"], qkw["max_beam"], None, False)
+        out[f"{name}/windows"] = windows
+        ids, d = pre.batch_search(q, windows, nq, qp)
+        out[f"{name}/prefilter/ids"], out[f"{name}/prefilter/dists"] = ids, d
+        for method in ("fenwick", "optimized_postfilter", "three_split"):
+            ids, d = tree.batch_search(q, windows, nq, method, qp)
+            out[f"{name}/{method}/ids"], out[f"{name}/{method}/dists"] = ids, d
+        ids, d = sup.batch_search(q, windows, nq, qp)
+        out[f"{name}/super/ids"], out[f"{name}/super/dists"] = ids, d
+    np.savez_compressed(os.path.join(HERE, "tiny_mips_ref_outputs.npz"), **out)
     print("wrote", len(out), "arrays")
 
 

@@ -4,6 +4,7 @@ import numpy as np
 from rangefilteredann_b200 import synth
 
 TINY = dict(n=3000, d=16, nq=64, seed=7, cutoff=500)
+TINY_MIPS = dict(n=2000, d=24, nq=48, seed=8, cutoff=400)  # angular; 24 floats -> rows padded to 32
 
 
 def tiny_cases(labels):
@@ -35,4 +36,12 @@ def tiny_cases(labels):
     # ratio fallback of optimized_postfilter (range_filter_tree.h:460-466)
     w = synth.make_windows(labels, -3, 32, seed=56)
     cases.append(("ratio", w, dict(beam=20, mult=1, max_beam=10000, ratio=1.5, prefilter=True)))
+    return cases
+
+
+def tiny_mips_cases(labels):
+    cases = []
+    for power in (-6, -3, -1):
+        w = synth.make_windows(labels, power, TINY_MIPS["nq"], seed=200 + power)
+        cases.append((f"mips_pow{power}", w, dict(beam=10, mult=2, max_beam=10000, prefilter=True)))
     return cases

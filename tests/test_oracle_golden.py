@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN
-from golden_cases import TINY, tiny_cases
+from golden_cases import TINY, TINY_MIPS, tiny_cases, tiny_mips_cases
 from oracle_api import Oracle
 from rangefilteredann_b200 import synth
 
@@ -64,3 +64,20 @@ def test_device_order_mode_is_close(tiny):
     i1, d1 = o1.batch("prefilter", queries[:32], w, pad_id=0xFFFFFFFF)
     assert np.allclose(d0, d1, rtol=1e-5)
     assert (i0 == i1).mean() > 0.99
+
+
+@pytest.mark.parametrize("method", ["prefilter", "fenwick", "optimized_postfilter", "three_split", "super"])
+def test_oracle_matches_reference_mips(method):
+    data, queries, labels = synth.make_dataset(TINY_MIPS["n"], TINY_MIPS["d"], TINY_MIPS["nq"], TINY_MIPS["seed"], angular=True)
+    gold = np.load(os.path.join(GOLDEN, "tiny_mips_ref_outputs.npz"))
+    kind = {"prefilter": "prefilter", "super": "super"}.get(method, "wst")
+    cache = None if kind == "prefilter" else os.path.join(GOLDEN, "tiny_mips", kind) + "/"
+    orc = Oracle(kind, data, labels, cache, metric=1, cutoff=TINY_MIPS["cutoff"])
+    for name, windows, qkw in tiny_mips_cases(labels):
+        rids, rd = gold[f"{name}/{method}/ids"], gold[f"{name}/{method}/dists"]
+        ids, d = orc.batch(method, queries[: len(windows)], windows, beam=qkw["beam"], mult=qkw["mult"],
+                           max_beam=qkw["max_beam"], pad_id=PADS.get(method, 0))
+        assert np.array_equal(d, rd), f"{name}/{method}"
+        diff = ids != rids
+        for i, j in zip(*np.nonzero(diff)):
+            assert (rd[i] == rd[i, j]).sum() > 1 or rd[i, j] == rd[i, -1]
