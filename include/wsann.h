@@ -127,6 +127,22 @@ int ws_index_set_super(ws_index* idx, uint32_t rows, int32_t cutoff, const uint6
                        const uint64_t* bucket_shifts, const uint32_t* row_nb,
                        const int32_t* node_ids_flat);
 
+/* ---- graph construction on the device (setup path) ---------------------
+ * Builds one Vamana graph per [starts[i], starts[i]+counts[i]) range with the reference
+ * builder's algorithm (ParlayANN/algorithms/vamana/index.h:61-108,123-135,211-313: batch
+ * insertion with prefix doubling, beam search L, robustPrune alpha, reverse edges, final
+ * distance sort), all graphs in lock step, and registers them as nodes of the index.
+ * Used when a node's cache file (postfilter_vamana.h:54-61) is missing; the host then
+ * saves the result in the reference's .bin format so both implementations load the same
+ * graph.  The insertion order comes from `seed`, so graphs are valid Vamana graphs but not
+ * bit-identical to a reference-builder run. */
+int ws_build_graphs(ws_index* idx, uint32_t ngraphs, const uint64_t* starts, const uint64_t* counts,
+                    uint32_t max_degree, uint32_t beam_l, double alpha, uint64_t seed, int32_t* nodes_out);
+/* degrees[count] and rows[count][R] (-1 padded, R = *max_degree_out) of one node */
+int ws_index_get_graph(ws_index* idx, int32_t node, uint32_t* max_degree_out, int32_t* degrees, int32_t* rows);
+/* builder counters: points inserted, nodes expanded, distance evaluations, overflow re-prunes */
+int ws_index_build_stats(ws_index* idx, uint64_t* out4);
+
 /* Upload everything staged so far; must be called once before any *_batch call. */
 int ws_index_finalize(ws_index* idx);
 

@@ -14,9 +14,10 @@
 //   Graph file format                   ParlayANN/algorithms/utils/graph.h:126-196
 //   QueryParams / BuildParams           ParlayANN/algorithms/utils/types.h:77-140
 //
-// Graph CONSTRUCTION is not on this path: graphs are loaded from the
-// reference builder's cache files (postfilter_vamana.h:54-61,126-132).  A missing file is
-// an error, never a silently different graph.
+// Graphs are loaded from the reference builder's cache files (postfilter_vamana.h:54-61,
+// 126-132) whenever they exist.  Missing ones are built on the device with the same
+// algorithm and saved in the same format (Arena::realize_graphs), so the reference can load
+// them back and both implementations search identical graphs.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -154,23 +155,63 @@ class Arena {
     check(ws_index_create(device, metric, n, (uint32_t)dim, points, labels, nullptr, 0, &idx_), "ws_index_create");
   }
 
-  int32_t add_cached_graph(const BuildParams& bp, size_t start, size_t count, float min_label, float max_label) {
-    if (bp.cache_path.empty())
-      throw std::runtime_error("BuildParams.cache_path is empty: this engine loads the reference builder's graph "
-                               "cache (postfilter_vamana.h:54-61) and does not build graphs");
-    std::string path = graph_filename(bp, min_label, max_label, count);
-    std::ifstream probe(path, std::ios::binary);
-    if (!probe)
-      throw std::runtime_error("graph cache miss: " + path +
-                               " — build it with the reference builder (oracle/build_ref_cache.py); "
-                               "graph construction is outside this engine's hot path");
-    probe.close();
-    GraphFile g = read_graph_file(path);
-    if ((size_t)g.n != count) throw std::runtime_error("graph " + path + " has " + std::to_string(g.n) + " nodes, expected " + std::to_string(count));
-    int32_t node = -1;
-    check(ws_index_add_graph(idx_, start, count, (uint32_t)g.max_degree, g.degrees.data(), g.edges.data(), &node),
-          "ws_index_add_graph");
-    return node;
+  // Queue one node's graph.  Nothing is loaded or built until realize_graphs().
+  size_t plan_graph(size_t start, size_t count, float min_label, float max_label) {
+    plans_.push_back(Plan{start, count, min_label, max_label});
+    return plans_.size() - 1;
+  }
+
+  // Resolve every planned graph to a node handle, in plan order.  Graphs whose cache file
+  // exists (postfilter_vamana.h:54-61) are loaded; the missing ones are built together on
+  // the device with the reference builder's algorithm (ws_build_graphs) and — when
+  // cache_path is set — saved in the reference's format, so that the reference loads the
+  // same graphs.  WSANN_GRAPH_BUILD=0 turns a cache miss into an error instead.
+  std::vector<int32_t> realize_graphs(const BuildParams& bp) {
+    std::vector<int32_t> handles(plans_.size(), -1);
+    std::vector<size_t> missing;
+    for (size_t i = 0; i < plans_.size(); i++) {
+      const Plan& pl = plans_[i];
+      std::string path = bp.cache_path.empty() ? std::string() : graph_filename(bp, pl.min_label, pl.max_label, pl.count);
+      std::ifstream probe;
+      if (!path.empty()) probe.open(path, std::ios::binary);
+      if (path.empty() || !probe) { missing.push_back(i); continue; }
+      probe.close();
+      GraphFile g = read_graph_file(path);
+      if ((size_t)g.n != pl.count)
+        throw std::runtime_error("graph " + path + " has " + std::to_string(g.n) + " nodes, expected " + std::to_string(pl.count));
+      check(ws_index_add_graph(idx_, pl.start, pl.count, (uint32_t)g.max_degree, g.degrees.data(), g.edges.data(), &handles[i]),
+            "ws_index_add_graph");
+    }
+    if (!missing.empty()) {
+      const char* env = std::getenv("WSANN_GRAPH_BUILD");
+      if (env && std::string(env) == "0") {
+        const Plan& pl = plans_[missing[0]];
+        throw std::runtime_error("graph cache miss: " + graph_filename(bp, pl.min_label, pl.max_label, pl.count) +
+                                 " (and " + std::to_string(missing.size() - 1) + " more) with WSANN_GRAPH_BUILD=0");
+      }
+      int device = -1;
+      ws_index_device(idx_, &device);
+      if (device < 0) {  // host-only geometry index: nodes without adjacency
+        for (size_t i : missing)
+          check(ws_index_add_graph(idx_, plans_[i].start, plans_[i].count, (uint32_t)bp.R, nullptr, nullptr, &handles[i]), "ws_index_add_graph");
+      } else {
+        std::vector<uint64_t> starts, counts;
+        uint64_t rows = 0;
+        for (size_t i : missing) { starts.push_back(plans_[i].start); counts.push_back(plans_[i].count); rows += plans_[i].count; }
+        std::vector<int32_t> built(missing.size(), -1);
+        std::fprintf(stderr, "[wsann] %zu graph(s) missing from cache '%s': building %llu node-rows on the GPU (R=%ld L=%ld alpha=%g)\n",
+                     missing.size(), bp.cache_path.c_str(), (unsigned long long)rows, bp.R, bp.L, bp.alpha);
+        check(ws_build_graphs(idx_, (uint32_t)missing.size(), starts.data(), counts.data(), (uint32_t)bp.R, (uint32_t)bp.L,
+                              bp.alpha, 0x5eedull, built.data()),
+              "ws_build_graphs");
+        for (size_t m = 0; m < missing.size(); m++) {
+          handles[missing[m]] = built[m];
+          if (!bp.cache_path.empty()) save_graph(bp, plans_[missing[m]], built[m]);
+        }
+      }
+    }
+    plans_.clear();
+    return handles;
   }
 
   ws_index* get() const { return idx_; }
@@ -179,9 +220,40 @@ class Arena {
   const std::vector<float>& labels() const { return labels_; }
 
  private:
+  struct Plan {
+    size_t start, count;
+    float min_label, max_label;
+  };
+
+  // graph.h:174-196 layout, so the reference's Graph(char*) constructor reads it back
+  void save_graph(const BuildParams& bp, const Plan& pl, int32_t node) {
+    uint32_t R = 0;
+    std::vector<int32_t> deg(pl.count);
+    check(ws_index_get_graph(idx_, node, &R, nullptr, nullptr), "ws_index_get_graph");
+    std::vector<int32_t> rows(pl.count * (size_t)R);
+    check(ws_index_get_graph(idx_, node, &R, deg.data(), rows.data()), "ws_index_get_graph");
+    std::string path = graph_filename(bp, pl.min_label, pl.max_label, pl.count);
+    std::string tmp = path + ".tmp";
+    {
+      std::ofstream out(tmp, std::ios::binary);
+      if (!out) throw std::runtime_error("cannot write graph cache file " + tmp);
+      int32_t hdr[2] = {(int32_t)pl.count, (int32_t)bp.R};
+      out.write(reinterpret_cast<const char*>(hdr), 8);
+      out.write(reinterpret_cast<const char*>(deg.data()), 4ll * (long long)pl.count);
+      std::vector<int32_t> edges;
+      edges.reserve(pl.count * 32);
+      for (size_t i = 0; i < pl.count; i++)
+        for (int32_t j = 0; j < deg[i]; j++) edges.push_back(rows[i * R + j]);
+      out.write(reinterpret_cast<const char*>(edges.data()), 4ll * (long long)edges.size());
+      if (!out) throw std::runtime_error("short write on " + tmp);
+    }
+    if (std::rename(tmp.c_str(), path.c_str()) != 0) throw std::runtime_error("cannot rename " + tmp);
+  }
+
   ws_index* idx_ = nullptr;
   size_t n_ = 0, dim_ = 0;
   std::vector<float> labels_;
+  std::vector<Plan> plans_;
 };
 
 struct BatchResult {
@@ -217,7 +289,8 @@ class PostfilterVamanaIndex {
                         const BuildParams& bp, int device = default_device()) {
     arena_.init_unsorted(points, labels, n, dim, metric, device);
     float mn = *std::min_element(labels, labels + n), mx = *std::max_element(labels, labels + n);
-    node_ = arena_.add_cached_graph(bp, 0, n, mn, mx);
+    arena_.plan_graph(0, n, mn, mx);
+    node_ = arena_.realize_graphs(bp)[0];
     check(ws_index_finalize(arena_.get()), "ws_index_finalize");
   }
   // postfilter_vamana.h:191-219 (missing slots: id 0xFFFFFFFF, FLT_MAX)
@@ -267,13 +340,13 @@ class VamanaRangeFilterTreeIndex {
     }
     std::vector<uint32_t> row_nb;
     std::vector<uint64_t> off_flat;
-    std::vector<int32_t> nodes_flat;
     for (auto& row : offsets_) {
       row_nb.push_back((uint32_t)row.size() - 1);
       off_flat.insert(off_flat.end(), row.begin(), row.end());
       for (size_t b = 0; b + 1 < row.size(); b++)
-        nodes_flat.push_back(arena_.add_cached_graph(bp, row[b], row[b + 1] - row[b], sl[row[b]], sl[row[b + 1] - 1]));
+        arena_.plan_graph(row[b], row[b + 1] - row[b], sl[row[b]], sl[row[b + 1] - 1]);
     }
+    std::vector<int32_t> nodes_flat = arena_.realize_graphs(bp);
     check(ws_index_set_wst(arena_.get(), (uint32_t)offsets_.size(), (uint32_t)split_factor, cutoff, row_nb.data(),
                            off_flat.data(), nodes_flat.data()),
           "ws_index_set_wst");
@@ -314,8 +387,7 @@ class SuperOptimizedPostfilterTree {
     const std::vector<float>& sl = arena_.labels();
     std::vector<uint64_t> sizes{(uint64_t)n}, shifts{0};
     std::vector<uint32_t> row_nb{1};
-    std::vector<int32_t> nodes_flat;
-    nodes_flat.push_back(arena_.add_cached_graph(bp, 0, n, sl[0], sl[n - 1]));
+    arena_.plan_graph(0, n, sl[0], sl[n - 1]);
     // :145-170 — bucket size is evaluated in float, as the reference does
     while ((int64_t)sizes.back() > (int64_t)cutoff) {
       size_t last = sizes.back();
@@ -328,9 +400,10 @@ class SuperOptimizedPostfilterTree {
       row_nb.push_back((uint32_t)nb);
       for (size_t b = 0; b < nb; b++) {
         size_t s = b * bucket_shift, e = std::min(s + bucket_size, n);
-        nodes_flat.push_back(arena_.add_cached_graph(bp, s, e - s, sl[s], sl[e - 1]));
+        arena_.plan_graph(s, e - s, sl[s], sl[e - 1]);
       }
     }
+    std::vector<int32_t> nodes_flat = arena_.realize_graphs(bp);
     check(ws_index_set_super(arena_.get(), (uint32_t)sizes.size(), cutoff, sizes.data(), shifts.data(), row_nb.data(),
                              nodes_flat.data()),
           "ws_index_set_super");

@@ -133,31 +133,216 @@ __device__ __forceinline__ int ws_cta_rank(bool flag, int* s_wc, int lane, int w
   return pre + __popc(bal & ((1u << lane) - 1u));
 }
 
+// Shared-memory working set of one beam search (pointers into the CTA's dynamic smem)
+struct WsBeamSmem {
+  uint64_t* fr;    // [beam_cap] frontier, keys = ord(dist)<<32 | id<<1 | visited
+  uint64_t* fo;    // [beam_cap] merge target (ping-pong)
+  uint64_t* ck;    // [cand_cap] candidate keys
+  uint64_t* ck2;   // [cand_cap] de-duplicated candidate keys
+  int* cid;        // [cand_cap] kept neighbour ids
+  int* cpos;       // [cand_cap] insertion ranks
+  int* hash;       // [hash_mask+1] visited table (GLOBAL_SEEN == false)
+  int* s_m;        // scalars
+  int* s_npick;
+  int* s_pick;     // [8]
+  int* s_wc;       // [4]
+};
+
+struct WsSearchCfg {
+  int R, E, dpad4;
+  uint32_t hash_mask;
+  long long limit, degree_limit;
+  uint32_t* bitmap;     // GLOBAL_SEEN: this CTA's slab
+};
+
+// One beam_search (beamSearch.h:51-184) with QP.beamSize = QP.k = B from local id 0 of `node`.
+// All WS_CTA_THREADS threads call it.  On return *frontier points at the final frontier
+// (sorted keys) and the return value is its length.  When vis_list != nullptr the expanded
+// nodes are appended to it in expansion order (keys as in the frontier) — the `visited`
+// sequence the Vamana builder prunes (vamana/index.h:258-262).
+template <int KQ, int METRIC, bool GLOBAL_SEEN>
+__device__ __forceinline__ int ws_beam_search(const WsBeamSmem& S, const WsSearchCfg& C, const WsNode& node,
+                                              const float4* vbase, const float4 (&q)[KQ], const int B,
+                                              const int skip_id, uint64_t** frontier,
+                                              unsigned long long* nvis_out, unsigned long long* ncmp_out,
+                                              uint64_t* vis_list, const int vis_cap) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tl = lane & (WS_TEAM - 1), team = tid / WS_TEAM;
+  const int NTEAMS = WS_CTA_THREADS / WS_TEAM;
+  const int R = C.R, E = C.E, dpad4 = C.dpad4;
+
+  if (!GLOBAL_SEEN) {
+    for (int i = tid; i <= (int)C.hash_mask; i += WS_CTA_THREADS) S.hash[i] = -1;
+  } else {
+    const int words = (int)((node.count + 31u) >> 5);
+    for (int i = tid; i < words; i += WS_CTA_THREADS) C.bitmap[i] = 0u;
+  }
+  {
+    float d0 = ws_team_dist<KQ, METRIC>(vbase, q, tl, dpad4, team == 0);
+    if (tid == 0) S.fr[0] = ws_key(d0, 0u);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (!GLOBAL_SEEN) ws_seen_smem(S.hash, C.hash_mask, 0); else ws_seen_bitmap(C.bitmap, 0);
+  }
+  int n = 1;
+  int scan_from = 0;
+  unsigned long long nvis = 0, ncmp = 1;
+  uint64_t* cur = S.fr;
+  uint64_t* oth = S.fo;
+
+  for (;;) {
+    if ((long long)nvis >= C.limit) break;
+    // ---- pick the first E unvisited frontier entries (E = 1: beamSearch.h:111)
+    __syncthreads();
+    if (tid == 0) *S.s_npick = 0;
+    __syncthreads();
+    for (int base = scan_from; base < n && *S.s_npick < E; base += WS_CTA_THREADS) {
+      int i = base + tid;
+      bool unv = i < n && !(cur[i] & 1ull);
+      int tot;
+      int prev = *S.s_npick;
+      int r = prev + ws_cta_rank(unv, S.s_wc, lane, warp, &tot);
+      if (unv && r < E) S.s_pick[r] = i;
+      __syncthreads();
+      if (tid == 0) *S.s_npick = min(E, prev + tot);
+      __syncthreads();
+    }
+    const int npick = *S.s_npick;
+    if (npick == 0) break;
+    const int last_pick = S.s_pick[npick - 1];
+    if (tid < npick) {
+      uint64_t key = cur[S.s_pick[tid]];
+      cur[S.s_pick[tid]] = key | 1ull;  // visited (beamSearch.h:114-117)
+      if (vis_list != nullptr && (int)nvis + tid < vis_cap) vis_list[(int)nvis + tid] = key;
+    }
+    if (tid == 0) *S.s_m = 0;
+    nvis += (unsigned long long)npick;
+    __syncthreads();
+
+    // ---- neighbours not seen before (beamSearch.h:123-131)
+    const int items = npick * R;
+    for (int base = 0; base < items; base += WS_CTA_THREADS) {
+      int it = base + tid;
+      int nb = -1;
+      bool keep = false;
+      if (it < items) {
+        int e = it / R, j = it - e * R;
+        uint32_t cur_id = (uint32_t)(cur[S.s_pick[e]] & 0xFFFFFFFFull) >> 1;
+        if ((long long)j < C.degree_limit) nb = __ldg(node.adj + (size_t)cur_id * R + j);
+        if (nb >= 0 && nb != skip_id)
+          keep = GLOBAL_SEEN ? !ws_seen_bitmap(C.bitmap, nb) : !ws_seen_smem(S.hash, C.hash_mask, nb);
+      }
+      unsigned bal = __ballot_sync(0xffffffffu, keep);
+      int wbase = 0;
+      if (lane == 0 && bal) wbase = atomicAdd(S.s_m, __popc(bal));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (keep) S.cid[wbase + __popc(bal & ((1u << lane) - 1u))] = nb;
+    }
+    __syncthreads();
+    const int m = *S.s_m;
+    if (m == 0) { scan_from = last_pick + 1; continue; }
+    ncmp += (unsigned long long)m;
+
+    // ---- distances; keep those under the cutoff (beamSearch.h:135-145)
+    const float cutoff = (n < B) ? (float)2147483647 : ws_unord((uint32_t)(cur[n - 1] >> 32));
+    const int mp = max(ws_pow2ceil(m), 2);
+    for (int jb = 0; jb < m; jb += NTEAMS) {
+      int j = jb + team;
+      bool valid = j < m;
+      int id = valid ? S.cid[j] : 0;
+      float d = ws_team_dist<KQ, METRIC>(vbase + (size_t)id * dpad4, q, tl, dpad4, valid);
+      if (valid && tl == 0) S.ck[j] = (d < cutoff) ? ws_key(d, (uint32_t)id << 1) : WS_KEY_MAX;
+    }
+    for (int i = m + tid; i < mp; i += WS_CTA_THREADS) S.ck[i] = WS_KEY_MAX;
+    __syncthreads();
+    ws_cta_sort(S.ck, mp, tid);  // beamSearch.h:148
+    int mc;
+    {
+      int lo = 0, hi = mp;
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (S.ck[mid] != WS_KEY_MAX) lo = mid + 1; else hi = mid; }
+      mc = lo;
+    }
+    if (mc == 0) { scan_from = last_pick + 1; continue; }
+
+    // ---- rank candidates against the frontier, dropping ones already in it
+    //      (the reference's set_union does the same de-duplication, beamSearch.h:151-154)
+    int mc2 = 0;
+    for (int base = 0; base < mc; base += WS_CTA_THREADS) {
+      int j = base + tid;
+      bool ok = false;
+      int p = 0;
+      uint64_t key = 0;
+      if (j < mc) {
+        key = S.ck[j];
+        p = ws_lb_shift1(cur, n, key >> 1);
+        ok = !(p < n && (cur[p] >> 1) == (key >> 1));
+      }
+      int tot;
+      int r = mc2 + ws_cta_rank(ok, S.s_wc, lane, warp, &tot);
+      if (ok) { S.ck2[r] = key; S.cpos[r] = p; }
+      mc2 += tot;
+    }
+    __syncthreads();
+    if (mc2 == 0) { scan_from = last_pick + 1; continue; }
+
+    // ---- merge into the other buffer, trim to the beam (beamSearch.h:151-172)
+    for (int i = tid; i < n; i += WS_CTA_THREADS) {
+      uint64_t key = cur[i];
+      int pos = i + ws_lb_shift1(S.ck2, mc2, key >> 1);
+      if (pos < B) oth[pos] = key;
+    }
+    for (int j = tid; j < mc2; j += WS_CTA_THREADS) {
+      int pos = S.cpos[j] + j;
+      if (pos < B) oth[pos] = S.ck2[j];
+    }
+    const int first_new = S.cpos[0];
+    n = min(n + mc2, B);
+    scan_from = min(last_pick + 1, first_new);
+    uint64_t* tmp = cur; cur = oth; oth = tmp;
+    // loop top has the barrier that publishes `oth` writes
+  }
+  __syncthreads();
+  *frontier = cur;
+  *nvis_out = nvis;
+  *ncmp_out = ncmp;
+  return n;
+}
+
+// carve the dynamic shared memory of a beam-search CTA
+__device__ __forceinline__ float* ws_carve_beam_smem(unsigned char* base, uint32_t beam_cap, uint32_t cand_cap,
+                                                     uint32_t dpad, WsBeamSmem& S) {
+  S.fr = reinterpret_cast<uint64_t*>(base);
+  S.fo = S.fr + beam_cap;
+  S.ck = S.fo + beam_cap;
+  S.ck2 = S.ck + cand_cap;
+  S.cid = reinterpret_cast<int*>(S.ck2 + cand_cap);
+  S.cpos = S.cid + cand_cap;
+  float* qs = reinterpret_cast<float*>(S.cpos + cand_cap);
+  S.hash = reinterpret_cast<int*>(qs + dpad);
+  return qs;
+}
+
 template <int KQ, int METRIC, bool GLOBAL_SEEN>
 __global__ void __launch_bounds__(WS_CTA_THREADS) ws_beam_kernel(WsBeamArgs A) {
   extern __shared__ __align__(16) unsigned char ws_smem[];
-  uint64_t* fr = reinterpret_cast<uint64_t*>(ws_smem);
-  uint64_t* fo = fr + A.beam_cap;
-  uint64_t* ck = fo + A.beam_cap;
-  uint64_t* ck2 = ck + A.cand_cap;
-  int* cid = reinterpret_cast<int*>(ck2 + A.cand_cap);
-  int* cpos = cid + A.cand_cap;
-  float* qs = reinterpret_cast<float*>(cpos + A.cand_cap);
-  int* hash = reinterpret_cast<int*>(qs + A.dpad);
+  WsBeamSmem S;
+  float* qs = ws_carve_beam_smem(ws_smem, A.beam_cap, A.cand_cap, A.dpad, S);
 
   __shared__ uint32_t s_task;
   __shared__ int s_m, s_npick, s_have;
   __shared__ int s_pick[8];
   __shared__ int s_wc[WS_CTA_THREADS / 32];
+  S.s_m = &s_m; S.s_npick = &s_npick; S.s_pick = s_pick; S.s_wc = s_wc;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tl = lane & (WS_TEAM - 1), team = tid / WS_TEAM;
-  const int NTEAMS = WS_CTA_THREADS / WS_TEAM;
+  const int tl = lane & (WS_TEAM - 1);
   const int dpad4 = A.dpad >> 2;
   const int K = (int)A.k;
-  const int R = (int)A.R;
-  const int E = (int)A.expand;
-  uint32_t* bitmap = GLOBAL_SEEN ? A.bitmap + (size_t)blockIdx.x * A.bitmap_words : nullptr;
+  WsSearchCfg C;
+  C.R = (int)A.R; C.E = (int)A.expand; C.dpad4 = dpad4; C.hash_mask = A.hash_mask;
+  C.limit = A.limit; C.degree_limit = A.degree_limit;
+  C.bitmap = GLOBAL_SEEN ? A.bitmap + (size_t)blockIdx.x * A.bitmap_words : nullptr;
 
   for (;;) {
     __syncthreads();
@@ -195,139 +380,13 @@ __global__ void __launch_bounds__(WS_CTA_THREADS) ws_beam_kernel(WsBeamArgs A) {
       }
       if (beam > (long long)A.beam_cap) { escalate = true; break; }
 
-      // ------------------------------------------------------------------ beam_search
-      // (beamSearch.h:51-184) with QP.beamSize = QP.k = beam, start point = local id 0
       const int B = (int)beam;
-      if (!GLOBAL_SEEN) {
-        for (int i = tid; i <= (int)A.hash_mask; i += WS_CTA_THREADS) hash[i] = -1;
-      } else {
-        const int words = (int)((node.count + 31u) >> 5);
-        for (int i = tid; i < words; i += WS_CTA_THREADS) bitmap[i] = 0u;
-      }
-      {
-        float d0 = ws_team_dist<KQ, METRIC>(vbase, q, tl, dpad4, team == 0);
-        if (tid == 0) fr[0] = ws_key(d0, 0u);
-      }
-      __syncthreads();
-      if (tid == 0) {
-        if (!GLOBAL_SEEN) ws_seen_smem(hash, A.hash_mask, 0); else ws_seen_bitmap(bitmap, 0);
-      }
-      int n = 1;
-      int scan_from = 0;
-      unsigned long long nvis = 0, ncmp = 1;
-      uint64_t* cur = fr;
-      uint64_t* oth = fo;
-
-      for (;;) {
-        if ((long long)nvis >= A.limit) break;
-        // ---- pick the first E unvisited frontier entries (E = 1: beamSearch.h:111)
-        __syncthreads();
-        if (tid == 0) s_npick = 0;
-        __syncthreads();
-        for (int base = scan_from; base < n && s_npick < E; base += WS_CTA_THREADS) {
-          int i = base + tid;
-          bool unv = i < n && !(cur[i] & 1ull);
-          int tot;
-          int prev = s_npick;
-          int r = prev + ws_cta_rank(unv, s_wc, lane, warp, &tot);
-          if (unv && r < E) s_pick[r] = i;
-          __syncthreads();
-          if (tid == 0) s_npick = min(E, prev + tot);
-          __syncthreads();
-        }
-        const int npick = s_npick;
-        if (npick == 0) break;
-        const int last_pick = s_pick[npick - 1];
-        if (tid < npick) cur[s_pick[tid]] |= 1ull;  // visited (beamSearch.h:114-117)
-        if (tid == 0) s_m = 0;
-        nvis += (unsigned long long)npick;
-        __syncthreads();
-
-        // ---- neighbours not seen before (beamSearch.h:123-131)
-        const int items = npick * R;
-        for (int base = 0; base < items; base += WS_CTA_THREADS) {
-          int it = base + tid;
-          int nb = -1;
-          bool keep = false;
-          if (it < items) {
-            int e = it / R, j = it - e * R;
-            uint32_t cur_id = (uint32_t)(cur[s_pick[e]] & 0xFFFFFFFFull) >> 1;
-            if ((long long)j < A.degree_limit) nb = __ldg(node.adj + (size_t)cur_id * R + j);
-            if (nb >= 0 && nb != skip_id)
-              keep = GLOBAL_SEEN ? !ws_seen_bitmap(bitmap, nb) : !ws_seen_smem(hash, A.hash_mask, nb);
-          }
-          unsigned bal = __ballot_sync(0xffffffffu, keep);
-          int wbase = 0;
-          if (lane == 0 && bal) wbase = atomicAdd(&s_m, __popc(bal));
-          wbase = __shfl_sync(0xffffffffu, wbase, 0);
-          if (keep) cid[wbase + __popc(bal & ((1u << lane) - 1u))] = nb;
-        }
-        __syncthreads();
-        const int m = s_m;
-        if (m == 0) { scan_from = last_pick + 1; continue; }
-        ncmp += (unsigned long long)m;
-
-        // ---- distances; keep those under the cutoff (beamSearch.h:135-145)
-        const float cutoff = (n < B) ? (float)2147483647 : ws_unord((uint32_t)(cur[n - 1] >> 32));
-        const int mp = max(ws_pow2ceil(m), 2);
-        for (int jb = 0; jb < m; jb += NTEAMS) {
-          int j = jb + team;
-          bool valid = j < m;
-          int id = valid ? cid[j] : 0;
-          float d = ws_team_dist<KQ, METRIC>(vbase + (size_t)id * dpad4, q, tl, dpad4, valid);
-          if (valid && tl == 0) ck[j] = (d < cutoff) ? ws_key(d, (uint32_t)id << 1) : WS_KEY_MAX;
-        }
-        for (int i = m + tid; i < mp; i += WS_CTA_THREADS) ck[i] = WS_KEY_MAX;
-        __syncthreads();
-        ws_cta_sort(ck, mp, tid);  // beamSearch.h:148
-        int mc;
-        {
-          int lo = 0, hi = mp;
-          while (lo < hi) { int mid = (lo + hi) >> 1; if (ck[mid] != WS_KEY_MAX) lo = mid + 1; else hi = mid; }
-          mc = lo;
-        }
-        if (mc == 0) { scan_from = last_pick + 1; continue; }
-
-        // ---- rank candidates against the frontier, dropping ones already in it
-        //      (the reference's set_union does the same de-duplication, beamSearch.h:151-154)
-        int mc2 = 0;
-        for (int base = 0; base < mc; base += WS_CTA_THREADS) {
-          int j = base + tid;
-          bool ok = false;
-          int p = 0;
-          uint64_t key = 0;
-          if (j < mc) {
-            key = ck[j];
-            p = ws_lb_shift1(cur, n, key >> 1);
-            ok = !(p < n && (cur[p] >> 1) == (key >> 1));
-          }
-          int tot;
-          int r = mc2 + ws_cta_rank(ok, s_wc, lane, warp, &tot);
-          if (ok) { ck2[r] = key; cpos[r] = p; }
-          mc2 += tot;
-        }
-        __syncthreads();
-        if (mc2 == 0) { scan_from = last_pick + 1; continue; }
-
-        // ---- merge into the other buffer, trim to the beam (beamSearch.h:151-172)
-        for (int i = tid; i < n; i += WS_CTA_THREADS) {
-          uint64_t key = cur[i];
-          int pos = i + ws_lb_shift1(ck2, mc2, key >> 1);
-          if (pos < B) oth[pos] = key;
-        }
-        for (int j = tid; j < mc2; j += WS_CTA_THREADS) {
-          int pos = cpos[j] + j;
-          if (pos < B) oth[pos] = ck2[j];
-        }
-        const int first_new = cpos[0];
-        n = min(n + mc2, B);
-        scan_from = min(last_pick + 1, first_new);
-        uint64_t* tmp = cur; cur = oth; oth = tmp;
-        // loop top has the barrier that publishes `oth` writes
-      }
+      uint64_t* cur;
+      unsigned long long nvis, ncmp;
+      const int n = ws_beam_search<KQ, METRIC, GLOBAL_SEEN>(S, C, node, vbase, q, B, skip_id, &cur, &nvis, &ncmp,
+                                                            nullptr, 0);
 
       // ---- raw_query's label predicate, closed interval (postfilter_vamana.h:234-251)
-      __syncthreads();
       if (tid == 0) s_have = 0;
       __syncthreads();
       for (int base = 0; base < n && s_have < K; base += WS_CTA_THREADS) {
@@ -357,7 +416,7 @@ __global__ void __launch_bounds__(WS_CTA_THREADS) ws_beam_kernel(WsBeamArgs A) {
         atomicAdd(A.stats + WS_ST_DISTCMPS, ncmp);
         atomicAdd(A.stats + WS_ST_BEAMSUM, (unsigned long long)B);
       }
-      // ------------------------------------------------------------------ end beam_search
+      __syncthreads();
       if (phase == 1) break;
       if (have < K) beam *= 2;
     }

@@ -13,6 +13,10 @@
 
 #include "../../include/wsann.h"
 #include "ws_kernels.cuh"
+#include "ws_build.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <random>
 
 // ------------------------------------------------------------------------------------------
 // error plumbing
@@ -77,6 +81,8 @@ struct ws_index {
   uint32_t* d_decode = nullptr;
   WsNode* d_nodes = nullptr;
   std::vector<void*> adj_slabs;
+  std::vector<void*> build_allocs;   // adjacency/degree arrays produced by ws_build_graphs
+  std::vector<int32_t*> node_deg;     // per node: device degree array (built graphs) or nullptr
   size_t slab_used = 0;
   uint64_t hbm_bytes = 0;
 
@@ -103,7 +109,9 @@ struct ws_index {
   int64_t opt_expand = 1;
   int64_t opt_skip_query_id = 1;
   int64_t opt_scan_chunk = 8192;
-  int64_t opt_hash_factor = 32;  // smem visited-table entries per unit of beam capacity
+  int64_t opt_hash_factor = 32;
+  int64_t opt_build_expand = 1;  // nodes expanded per step while BUILDING graphs
+  uint64_t build_stats[4] = {0, 0, 0, 0};  // inserts, visited, dist_cmps, overflow re-prunes  // smem visited-table entries per unit of beam capacity
 
   // scratch (grown on demand)
   WsDevBuf tasks, res_keys, res_cnt, counts, queues, ctrl, d_queries, d_windows, d_ids, d_dists,
@@ -275,6 +283,7 @@ void ws_index_destroy(ws_index* idx) {
     cudaFree(idx->d_decode);
     cudaFree(idx->d_stats);
     for (void* p : idx->adj_slabs) cudaFree(p);
+    for (void* p : idx->build_allocs) cudaFree(p);
     for (void* p : idx->geom_dev_allocs) cudaFree(p);
     WsDevBuf* bufs[] = {&idx->tasks, &idx->res_keys, &idx->res_cnt, &idx->counts, &idx->queues, &idx->ctrl,
                         &idx->d_queries, &idx->d_windows, &idx->d_ids, &idx->d_dists, &idx->bitmap, &idx->flush};
@@ -338,6 +347,7 @@ int ws_index_add_graph(ws_index* idx, uint64_t start, uint64_t count, uint32_t m
     node.adj = (const int32_t*)dst;
   }
   idx->h_nodes.push_back(node);
+  idx->node_deg.push_back(nullptr);
   idx->max_node_count = std::max<uint32_t>(idx->max_node_count, (uint32_t)count);
   *node_out = (int32_t)idx->h_nodes.size() - 1;
   return WS_OK;
@@ -870,6 +880,258 @@ int ws_flush_l2(ws_index* idx) {
   return WS_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// GPU graph construction (ws_build.cuh) — setup path, not the query hot path
+// ------------------------------------------------------------------------------------------
+}  // extern "C"
+
+// the reference's batch schedule (vamana/index.h:225-268)
+static void ws_build_schedule(size_t n, std::vector<std::pair<uint32_t, uint32_t>>& out) {
+  out.clear();
+  size_t m = n, inc = 0, count = 0;
+  size_t max_batch = std::min(static_cast<size_t>(0.02 * static_cast<float>(n)), (size_t)1000000ul);
+  if (max_batch == 0) max_batch = n;
+  while (count < m) {
+    size_t floor, ceiling;
+    if (std::pow(2.0, (double)inc) <= (double)max_batch) {
+      floor = static_cast<size_t>(std::pow(2.0, (double)inc)) - 1;
+      ceiling = std::min(static_cast<size_t>(std::pow(2.0, (double)(inc + 1))), m) - 1;
+      count = std::min(static_cast<size_t>(std::pow(2.0, (double)(inc + 1))), m) - 1;
+    } else {
+      floor = count;
+      ceiling = std::min(count + max_batch, m);
+      count += max_batch;
+    }
+    if (ceiling > floor) out.push_back({(uint32_t)floor, (uint32_t)ceiling});
+    inc++;
+  }
+}
+
+template <int KQ, int METRIC>
+static cudaError_t ws_launch_build_insert_t(int grid, size_t smem, cudaStream_t s, const WsBuildArgs& a) {
+  cudaError_t e = cudaFuncSetAttribute(ws_build_insert_kernel<KQ, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  ws_build_insert_kernel<KQ, METRIC><<<grid, WS_CTA_THREADS, smem, s>>>(a);
+  return cudaGetLastError();
+}
+template <int KQ, int METRIC>
+static cudaError_t ws_build_insert_occ_t(size_t smem, int* blocks) {
+  cudaError_t e = cudaFuncSetAttribute(ws_build_insert_kernel<KQ, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_build_insert_kernel<KQ, METRIC>, WS_CTA_THREADS, smem);
+}
+template <int KQ, int METRIC>
+static cudaError_t ws_launch_build_reverse_t(int grid, cudaStream_t s, const WsBuildRevArgs& a) {
+  ws_build_reverse_kernel<KQ, METRIC><<<grid, WS_CTA_THREADS, 0, s>>>(a);
+  return cudaGetLastError();
+}
+template <int KQ, int METRIC>
+static cudaError_t ws_launch_build_sort_t(int grid, cudaStream_t s, const WsBuildSortArgs& a) {
+  ws_build_sortadj_kernel<KQ, METRIC><<<grid, WS_CTA_THREADS, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+extern "C" {
+
+int ws_build_graphs(ws_index* idx, uint32_t ngraphs, const uint64_t* starts, const uint64_t* counts,
+                    uint32_t max_degree, uint32_t beam_l, double alpha, uint64_t seed, int32_t* nodes_out) {
+  WS_NEED_DEVICE(idx);
+  if (idx->finalized) return ws_fail(WS_ERR_STATE, "index already finalized");
+  if (!starts || !counts || !nodes_out || ngraphs == 0) return ws_fail(WS_ERR_BADARG, "null/empty argument");
+  if (max_degree == 0 || max_degree > 128) return ws_fail(WS_ERR_BADARG, "max_degree %u unsupported (1..128)", max_degree);
+  if (beam_l < 1 || beam_l > 1024) return ws_fail(WS_ERR_BADARG, "build beam L=%u outside 1..1024", beam_l);
+  const uint32_t R = (max_degree + 3u) & ~3u;
+  if (idx->R == 0) idx->R = R;
+  if (idx->R != R) return ws_fail(WS_ERR_BADARG, "all graphs of one index must share max_degree (%u vs %u)", idx->R, R);
+  cudaStream_t st = idx->stream;
+
+  // ---- layout + insertion orders + schedules
+  std::vector<WsBuildGraph> g(ngraphs);
+  std::vector<std::vector<std::pair<uint32_t, uint32_t>>> sched(ngraphs);
+  uint64_t rows = 0;
+  size_t max_rounds = 0;
+  for (uint32_t i = 0; i < ngraphs; i++) {
+    if (counts[i] == 0 || starts[i] + counts[i] > idx->n) return ws_fail(WS_ERR_BADARG, "graph %u range outside the arena", i);
+    g[i].start = (uint32_t)starts[i];
+    g[i].count = (uint32_t)counts[i];
+    g[i].row_off = (uint32_t)rows;
+    g[i].floor = g[i].ceil = g[i].task_off = 0;
+    rows += counts[i];
+    ws_build_schedule(counts[i], sched[i]);
+    max_rounds = std::max(max_rounds, sched[i].size());
+  }
+  if (rows >= (1ull << 32)) return ws_fail(WS_ERR_BADARG, "too many node-rows for one build call");
+  std::vector<int32_t> perm(rows);
+  size_t max_tasks = 0;
+  {
+    std::vector<size_t> per_round(max_rounds, 0);
+    for (uint32_t i = 0; i < ngraphs; i++) {
+      std::mt19937_64 rng(seed * 0x9E3779B97F4A7C15ull + i);
+      int32_t* p = perm.data() + g[i].row_off;
+      for (uint32_t j = 0; j < g[i].count; j++) p[j] = (int32_t)j;
+      for (uint32_t j = g[i].count; j > 1; j--) std::swap(p[j - 1], p[rng() % j]);
+      for (size_t r = 0; r < sched[i].size(); r++) per_round[r] += sched[i][r].second - sched[i][r].first;
+    }
+    for (size_t v : per_round) max_tasks = std::max(max_tasks, v);
+  }
+
+  int32_t *d_adj = nullptr, *d_deg = nullptr, *d_perm = nullptr, *d_new_out = nullptr, *d_new_cnt = nullptr;
+  WsBuildGraph* d_graphs = nullptr;
+  uint64_t *d_pairs = nullptr, *d_pairs2 = nullptr;
+  uint32_t *d_heads = nullptr, *d_ctrl = nullptr;
+  void* d_temp = nullptr;
+  size_t temp_bytes = 0;
+  unsigned long long* d_bstats = nullptr;
+  const size_t max_pairs = max_tasks * R;
+  cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, d_pairs, d_pairs2, (int)max_pairs, 0, 64, st);
+  auto cleanup = [&]() {
+    cudaFree(d_perm); cudaFree(d_new_out); cudaFree(d_new_cnt); cudaFree(d_graphs); cudaFree(d_pairs);
+    cudaFree(d_pairs2); cudaFree(d_heads); cudaFree(d_ctrl); cudaFree(d_temp); cudaFree(d_bstats);
+  };
+#define WS_B(expr)                                                                                   \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      cleanup();                                                                                     \
+      cudaFree(d_adj); cudaFree(d_deg);                                                              \
+      return ws_fail(_e == cudaErrorMemoryAllocation ? WS_ERR_OOM : WS_ERR_CUDA, "%s: %s (graph build)", #expr, cudaGetErrorString(_e)); \
+    }                                                                                                \
+  } while (0)
+  WS_B(cudaMalloc(&d_adj, rows * R * sizeof(int32_t)));
+  WS_B(cudaMalloc(&d_deg, rows * sizeof(int32_t)));
+  WS_B(cudaMalloc(&d_perm, rows * sizeof(int32_t)));
+  WS_B(cudaMalloc(&d_new_out, std::max<size_t>(1, max_tasks) * R * sizeof(int32_t)));
+  WS_B(cudaMalloc(&d_new_cnt, std::max<size_t>(1, max_tasks) * sizeof(int32_t)));
+  WS_B(cudaMalloc(&d_graphs, ngraphs * sizeof(WsBuildGraph)));
+  WS_B(cudaMalloc(&d_pairs, std::max<size_t>(1, max_pairs) * sizeof(uint64_t)));
+  WS_B(cudaMalloc(&d_pairs2, std::max<size_t>(1, max_pairs) * sizeof(uint64_t)));
+  WS_B(cudaMalloc(&d_heads, std::max<size_t>(1, max_pairs) * sizeof(uint32_t)));
+  WS_B(cudaMalloc(&d_ctrl, 16 * sizeof(uint32_t)));
+  WS_B(cudaMalloc(&d_temp, std::max<size_t>(16, temp_bytes)));
+  WS_B(cudaMalloc(&d_bstats, 8 * sizeof(unsigned long long)));
+  WS_B(cudaMemsetAsync(d_bstats, 0, 8 * sizeof(unsigned long long), st));
+  WS_B(cudaMemcpyAsync(d_perm, perm.data(), rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  ws_fill_i32_kernel<<<idx->num_sms * 8, 256, 0, st>>>(d_adj, rows * R, -1);
+  WS_B(cudaMemsetAsync(d_deg, 0, rows * sizeof(int32_t), st));
+
+  const int kq = ws_pick_kq(idx->dpad);
+  uint32_t beam_cap = 64;
+  while (beam_cap < beam_l) beam_cap <<= 1;
+  const uint32_t E = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(8, idx->opt_build_expand));
+  uint32_t cand_cap = 64;
+  while (cand_cap < E * R) cand_cap <<= 1;
+  const uint32_t hash_entries = 8192;
+  const size_t smem = (size_t)2 * beam_cap * 8 + (size_t)cand_cap * 24 + (size_t)idx->dpad * 4 + (size_t)hash_entries * 4 +
+                      (size_t)WS_BUILD_VCAP * 8;
+  int occ = 0;
+#define WS_OCCB(KQ_, M_) { WS_B((ws_build_insert_occ_t<KQ_, M_>(smem, &occ))); }
+  WS_DISPATCH_KQ(kq, idx->metric, WS_OCCB);
+#undef WS_OCCB
+  if (occ < 1) { cleanup(); cudaFree(d_adj); cudaFree(d_deg); return ws_fail(WS_ERR_CUDA, "build kernel does not fit (smem %zu)", smem); }
+
+  for (size_t r = 0; r < max_rounds; r++) {
+    uint32_t ntasks = 0;
+    for (uint32_t i = 0; i < ngraphs; i++) {
+      g[i].task_off = ntasks;
+      if (r < sched[i].size()) { g[i].floor = sched[i][r].first; g[i].ceil = sched[i][r].second; }
+      else { g[i].floor = g[i].ceil = 0; }
+      ntasks += g[i].ceil - g[i].floor;
+    }
+    if (ntasks == 0) continue;
+    WS_B(cudaMemcpyAsync(d_graphs, g.data(), ngraphs * sizeof(WsBuildGraph), cudaMemcpyHostToDevice, st));
+    WS_B(cudaMemsetAsync(d_ctrl, 0, 16 * sizeof(uint32_t), st));
+    WsBuildArgs a;
+    a.vecs = idx->d_vecs; a.dim = idx->dim; a.dpad = idx->dpad; a.R = R;
+    a.adj = d_adj; a.deg = d_deg; a.perm = d_perm; a.graphs = d_graphs; a.ngraphs = ngraphs; a.ntasks = ntasks;
+    a.head = d_ctrl + 0; a.new_out = d_new_out; a.new_cnt = d_new_cnt; a.pairs = d_pairs; a.pair_count = d_ctrl + 1;
+    a.L = beam_l; a.beam_cap = beam_cap; a.hash_mask = hash_entries - 1; a.cand_cap = cand_cap; a.expand = E;
+    a.alpha = alpha; a.stats = d_bstats;
+    const int grid = (int)std::min<uint64_t>(ntasks, (uint64_t)idx->num_sms * occ);
+#define WS_LBI(KQ_, M_) { WS_B((ws_launch_build_insert_t<KQ_, M_>(grid, smem, st, a))); }
+    WS_DISPATCH_KQ(kq, idx->metric, WS_LBI);
+#undef WS_LBI
+    ws_build_apply_kernel<<<(ntasks + 7) / 8, 256, 0, st>>>(a);
+    WS_B(cudaGetLastError());
+    uint32_t npairs = 0;
+    WS_B(cudaMemcpyAsync(&npairs, d_ctrl + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    WS_B(cudaStreamSynchronize(st));
+    if (npairs == 0) continue;
+    WS_B(cub::DeviceRadixSort::SortKeys(d_temp, temp_bytes, d_pairs, d_pairs2, (int)npairs, 0, 64, st));
+    ws_build_heads_kernel<<<(npairs + 255) / 256, 256, 0, st>>>(d_pairs2, npairs, d_heads, d_ctrl + 2);
+    WS_B(cudaGetLastError());
+    uint32_t nheads = 0;
+    WS_B(cudaMemcpyAsync(&nheads, d_ctrl + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    WS_B(cudaStreamSynchronize(st));
+    WsBuildRevArgs ra;
+    ra.vecs = idx->d_vecs; ra.dim = idx->dim; ra.dpad = idx->dpad; ra.R = R; ra.adj = d_adj; ra.deg = d_deg;
+    ra.graphs = d_graphs; ra.ngraphs = ngraphs; ra.pairs = d_pairs2; ra.npairs = npairs; ra.heads = d_heads;
+    ra.nheads = nheads; ra.head = d_ctrl + 3; ra.alpha = alpha; ra.stats = d_bstats;
+    const int rgrid = (int)std::min<uint64_t>(nheads, (uint64_t)idx->num_sms * 8);
+#define WS_LBR(KQ_, M_) { WS_B((ws_launch_build_reverse_t<KQ_, M_>(rgrid, st, ra))); }
+    WS_DISPATCH_KQ(kq, idx->metric, WS_LBR);
+#undef WS_LBR
+  }
+  {
+    WsBuildSortArgs sa;
+    sa.vecs = idx->d_vecs; sa.dim = idx->dim; sa.dpad = idx->dpad; sa.R = R; sa.adj = d_adj; sa.deg = d_deg;
+    sa.graphs = d_graphs; sa.ngraphs = ngraphs; sa.rows = (uint32_t)rows;
+    const int sgrid = (int)std::min<uint64_t>(rows, (uint64_t)idx->num_sms * 16);
+#define WS_LBS(KQ_, M_) { WS_B((ws_launch_build_sort_t<KQ_, M_>(sgrid, st, sa))); }
+    WS_DISPATCH_KQ(kq, idx->metric, WS_LBS);
+#undef WS_LBS
+  }
+  unsigned long long hs[8];
+  WS_B(cudaMemcpyAsync(hs, d_bstats, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  WS_B(cudaStreamSynchronize(st));
+#undef WS_B
+  cleanup();
+  idx->build_stats[0] += hs[0]; idx->build_stats[1] += hs[1]; idx->build_stats[2] += hs[2]; idx->build_stats[3] += hs[3];
+  idx->build_allocs.push_back(d_adj);
+  idx->build_allocs.push_back(d_deg);
+  idx->hbm_bytes += rows * R * sizeof(int32_t) + rows * sizeof(int32_t);
+  for (uint32_t i = 0; i < ngraphs; i++) {
+    WsNode node;
+    node.adj = d_adj + (size_t)g[i].row_off * R;
+    node.start = g[i].start;
+    node.count = g[i].count;
+    idx->h_nodes.push_back(node);
+    idx->node_deg.push_back(d_deg + g[i].row_off);
+    idx->max_node_count = std::max<uint32_t>(idx->max_node_count, g[i].count);
+    nodes_out[i] = (int32_t)idx->h_nodes.size() - 1;
+  }
+  return WS_OK;
+}
+
+// degrees[count] and rows[count][R] (-1 padded) of a node, for saving in the reference's
+// graph format (graph.h:174-196)
+int ws_index_get_graph(ws_index* idx, int32_t node, uint32_t* max_degree_out, int32_t* degrees, int32_t* rows) {
+  WS_NEED_DEVICE(idx);
+  if (node < 0 || (size_t)node >= idx->h_nodes.size()) return ws_fail(WS_ERR_BADARG, "bad node handle %d", node);
+  const WsNode& nd = idx->h_nodes[node];
+  if (max_degree_out) *max_degree_out = idx->R;
+  if (rows) WS_CUDA(cudaMemcpy(rows, nd.adj, (size_t)nd.count * idx->R * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (degrees) {
+    if (idx->node_deg[node]) {
+      WS_CUDA(cudaMemcpy(degrees, idx->node_deg[node], (size_t)nd.count * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    } else {
+      if (!rows) return ws_fail(WS_ERR_BADARG, "degrees of a loaded graph need the rows buffer too");
+      for (uint32_t i = 0; i < nd.count; i++) {
+        int32_t d = 0;
+        while (d < (int32_t)idx->R && rows[(size_t)i * idx->R + d] >= 0) d++;
+        degrees[i] = d;
+      }
+    }
+  }
+  return WS_OK;
+}
+
+int ws_index_build_stats(ws_index* idx, uint64_t* out4) {
+  if (!idx || !out4) return ws_fail(WS_ERR_BADARG, "null argument");
+  for (int i = 0; i < 4; i++) out4[i] = idx->build_stats[i];
+  return WS_OK;
+}
+
 int ws_index_get_stats(ws_index* idx, ws_stats* out) {
   WS_NEED_DEVICE(idx);
   if (!out) return ws_fail(WS_ERR_BADARG, "null out");
@@ -908,6 +1170,9 @@ int ws_index_set_option(ws_index* idx, const char* name, int64_t value) {
   } else if (s == "scan_chunk") {
     if (value < 256) return ws_fail(WS_ERR_BADARG, "scan_chunk must be >= 256");
     idx->opt_scan_chunk = value;
+  } else if (s == "build_expand_width") {
+    if (value < 1 || value > 8) return ws_fail(WS_ERR_BADARG, "build_expand_width must be 1..8");
+    idx->opt_build_expand = value;
   } else if (s == "profile_kernels") {
     idx->opt_profile = value != 0;
   } else if (s == "hash_factor") {

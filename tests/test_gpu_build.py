@@ -1,0 +1,95 @@
+"""GPU: the device-side Vamana builder (ws_build_graphs) — used only when a node's graph
+cache file is missing.  Checks the saved files are valid reference-format graphs, that the
+oracle (and the reference itself, when present) searching those files agrees with the
+engine, and that graph quality (recall at equal beam) matches reference-built graphs."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from golden_cases import TINY
+from oracle_api import Oracle
+from rangefilteredann_b200 import synth
+from test_gpu_golden import rows_equal_up_to_ties
+
+pytestmark = pytest.mark.gpu
+
+
+def read_graph(path):
+    raw = open(path, "rb").read()
+    n, maxdeg = struct.unpack("<ii", raw[:8])
+    deg = np.frombuffer(raw, dtype="<i4", count=n, offset=8)
+    edges = np.frombuffer(raw, dtype="<i4", offset=8 + 4 * n)
+    assert len(edges) == deg.sum()
+    return n, maxdeg, deg, edges
+
+
+@pytest.fixture(scope="module")
+def built(engine, tmp_path_factory):
+    cache = str(tmp_path_factory.mktemp("gpu_built")) + "/"
+    data, queries, labels = synth.make_dataset(TINY["n"], TINY["d"], TINY["nq"], TINY["seed"])
+    tree = engine.VamanaRangeFilterTreeIndexFloatEuclidian(data, labels, TINY["cutoff"], 2,
+                                                           engine.BuildParams(64, 500, 1.0, cache))
+    return dict(cache=cache, data=data, queries=queries, labels=labels, tree=tree)
+
+
+def test_saved_files_are_valid_reference_graphs(built):
+    files = sorted(os.listdir(built["cache"]))
+    assert len(files) == 15  # rows of 1, 2, 4, 8 buckets (3000 -> 375)
+    total_deg = 0
+    for f in files:
+        n, maxdeg, deg, edges = read_graph(os.path.join(built["cache"], f))
+        assert maxdeg == 64 and f.endswith(f"_{n}.bin")
+        assert deg.min() >= 0 and deg.max() <= 64
+        assert edges.min() >= 0 and edges.max() < n
+        off = np.concatenate([[0], np.cumsum(deg)])
+        for i in range(0, n, max(1, n // 50)):
+            row = edges[off[i]:off[i + 1]]
+            assert i not in row and len(set(row.tolist())) == len(row)
+        assert (deg > 0).mean() > 0.99
+        total_deg += deg.mean()
+    assert 5 < total_deg / len(files) < 64
+
+
+def test_oracle_on_built_graphs_is_bit_identical(engine, built):
+    orc = Oracle("wst", built["data"], built["labels"], built["cache"], dist_mode=1, cutoff=TINY["cutoff"])
+    qp = engine.QueryParams(10, 20, 1.35, 10_000_000, 10_000, 2, 10000, None, False)
+    for power in (-5, -2, 0):
+        w = synth.make_windows(built["labels"], power, 48, seed=power + 7)
+        q = built["queries"][:48]
+        for method in ("fenwick", "optimized_postfilter", "three_split"):
+            ids, d = built["tree"].batch_search(q, w, 48, method, qp)
+            oids, od = orc.batch(method, q, w, beam=20, mult=2)
+            assert np.array_equal(ids, oids) and np.array_equal(d, od), (power, method)
+
+
+def test_reference_loads_built_graphs(engine, ref, built):
+    rtree = ref.VamanaRangeFilterTreeIndexFloatEuclidian(built["data"], built["labels"], TINY["cutoff"], 2,
+                                                         ref.BuildParams(64, 500, 1.0, built["cache"]))
+    assert len(os.listdir(built["cache"])) == 15  # it loaded, it did not rebuild
+    w = synth.make_windows(built["labels"], -2, 48, seed=3)
+    q = built["queries"][:48]
+    qp = engine.QueryParams(10, 20, 1.35, 10_000_000, 10_000, 1, 10000, None, False)
+    rqp = ref.QueryParams(10, 20, 1.35, 10_000_000, 10_000, 1, 10000, None, False)
+    for method in ("fenwick", "optimized_postfilter"):
+        ids, d = built["tree"].batch_search(q, w, 48, method, qp)
+        rids, rd = rtree.batch_search(q, w, 48, method, rqp)
+        assert rows_equal_up_to_ties(ids, d, rids, rd).mean() >= 0.95
+
+
+def test_built_graph_quality_matches_reference_builder(engine, built):
+    """recall@10 at equal beam on GPU-built vs reference-built graphs (tests/golden/tiny)."""
+    ref_tree = engine.VamanaRangeFilterTreeIndexFloatEuclidian(
+        built["data"], built["labels"], TINY["cutoff"], 2,
+        engine.BuildParams(64, 500, 1.0, os.path.join(GOLDEN, "tiny", "wst") + "/"))
+    for power in (-3, -1, 0):
+        w = synth.make_windows(built["labels"], power, TINY["nq"], seed=90 + power)
+        gt = synth.ground_truth(built["data"], built["queries"], built["labels"], w)
+        for beam in (10, 40):
+            qp = engine.QueryParams(10, beam, 1.35, 10_000_000, 10_000, 1, 10000, None, False)
+            for method in ("fenwick", "optimized_postfilter"):
+                r_new = synth.recall_std(built["tree"].batch_search(built["queries"], w, len(w), method, qp)[0], gt)
+                r_ref = synth.recall_std(ref_tree.batch_search(built["queries"], w, len(w), method, qp)[0], gt)
+                assert r_new >= r_ref - 0.03, (power, beam, method, r_new, r_ref)

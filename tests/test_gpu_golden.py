@@ -115,6 +115,6 @@ def test_errors_match_reference_behaviour(engine):
         engine.PrefilterIndexFloatEuclidian(data[0], np.zeros(10, dtype=np.float32))  # ndim != 2
     with pytest.raises(RuntimeError):
         engine.PrefilterIndexFloatEuclidian(data, np.zeros(9, dtype=np.float32))  # length mismatch
-    with pytest.raises(RuntimeError):
+    with pytest.raises(RuntimeError, match="split_factor"):
         engine.SuperOptimizedPostfilterTreeIndexFloatEuclidian(data, np.arange(10, dtype=np.float32), 5, 1.0, 0.5,
                                                                engine.BuildParams(64, 500, 1.0, "/nonexistent/"))
