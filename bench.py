@@ -290,7 +290,15 @@ def run_engine(args, rank, world, local_rank):
     runner = EngineRunner(tree, cfg["nq"], cfg["d"])
     runner.upload(queries, windows)
     h = runner.h
-    table = choose_operating_points(runner, gts, rank)
+    if args.ops_file and os.path.exists(args.ops_file):
+        saved = json.load(open(args.ops_file))
+        table = {int(p): {m: dict(op=tuple(v["op"]), recall=v["recall"], ms=v["ms"]) for m, v in pm.items()}
+                 for p, pm in saved.items()}
+    else:
+        table = choose_operating_points(runner, gts, rank)
+        if args.ops_file and rank == 0:
+            json.dump({str(p): {m: dict(op=list(v["op"]), recall=v["recall"], ms=v["ms"]) for m, v in pm.items()}
+                       for p, pm in table.items()}, open(args.ops_file, "w"))
     ops = {p: min(table[p].values(), key=lambda v: v["ms"])["op"] for p in POWERS}
     nq_step = cfg["nq"] * len(POWERS)
 
@@ -565,6 +573,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1000)
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     ap.add_argument("--ref-sample", type=int, default=200)
+    ap.add_argument("--ops-file", default=None, help="save / reuse the swept operating points (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
     rank = int(os.environ.get("RANK", 0))

@@ -589,3 +589,262 @@ __global__ void ws_fill_kernel(uint4* p, size_t n16) {
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n16; i += stride) p[i] = make_uint4(0u, 0u, 0u, 0u);
 }
+
+// ------------------------------------------------------------------------------------------
+// K2w: warp-per-task beam search for small beams (B <= 128, R <= 64)
+//
+// Same algorithm, same results as ws_beam_kernel (bit-identical frontiers), but one WARP owns
+// a task: no CTA barriers, every reduction is a ballot/shuffle, the 64 candidate keys are
+// sorted in registers.  Many more searches are resident per SM (each needs ~10 KB of shared
+// memory), which is what hides the two dependent HBM latencies of every expansion.
+// ------------------------------------------------------------------------------------------
+#define WS_WARPS_PER_CTA 4
+
+__device__ __forceinline__ bool ws_seen_warp(volatile int* table, uint32_t mask, int id) {
+  // plain loads/stores: lanes of one warp may race on a slot, which can only lose an
+  // insertion (a later recomputation), never report an unseen id as seen
+  uint32_t h = ws_hash32((uint32_t)id) & mask;
+#pragma unroll 1
+  for (int p = 0; p < WS_HASH_PROBES; p++) {
+    uint32_t s = (h + p) & mask;
+    int v = table[s];
+    if (v == id) return true;
+    if (v == -1) { table[s] = id; return false; }
+  }
+  table[h] = id;
+  return false;
+}
+
+__device__ __forceinline__ uint64_t ws_shfl_xor_u64(uint64_t v, int m) {
+  uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m);
+  uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// ascending bitonic sort of 64 keys held two per lane: element i lives in lane (i & 31),
+// register (i >> 5)
+__device__ __forceinline__ void ws_warp_sort64(uint64_t& k0, uint64_t& k1, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 64; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j == 32) {
+        uint64_t lo = k0 < k1 ? k0 : k1, hi = k0 < k1 ? k1 : k0;
+        k0 = lo; k1 = hi;
+      } else {
+        uint64_t o0 = ws_shfl_xor_u64(k0, j), o1 = ws_shfl_xor_u64(k1, j);
+        const bool lower = (lane & j) == 0;
+        const bool up0 = (lane & k) == 0;          // element lane
+        const bool up1 = ((lane + 32) & k) == 0;   // element lane + 32
+        k0 = (up0 == lower) ? (k0 < o0 ? k0 : o0) : (k0 < o0 ? o0 : k0);
+        k1 = (up1 == lower) ? (k1 < o1 ? k1 : o1) : (k1 < o1 ? o1 : k1);
+      }
+    }
+  }
+}
+
+template <int KQ, int METRIC>
+__global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32) ws_beam_warp_kernel(WsBeamArgs A) {
+  extern __shared__ __align__(16) unsigned char ws_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tl = lane & (WS_TEAM - 1), team = lane / WS_TEAM;  // 4 teams per warp
+  const uint32_t CAP = A.beam_cap;
+  const size_t per_warp = (size_t)2 * CAP * 8 + 64 * 8 * 2 + 64 * 4 * 2 + (size_t)(A.hash_mask + 1) * 4;
+  unsigned char* base = ws_smem + per_warp * warp;
+  uint64_t* fr = reinterpret_cast<uint64_t*>(base);
+  uint64_t* fo = fr + CAP;
+  uint64_t* ck = fo + CAP;        // [64]
+  uint64_t* ck2 = ck + 64;        // [64]
+  int* cpos = reinterpret_cast<int*>(ck2 + 64);  // [64]
+  int* cid = cpos + 64;           // [64]
+  volatile int* hash = cid + 64;  // [hash_mask + 1]
+
+  const int dpad4 = A.dpad >> 2;
+  const int K = (int)A.k;
+  const int R = (int)A.R;
+  const unsigned lt = (1u << lane) - 1u;
+
+  for (;;) {
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(A.q_head, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= *A.q_in_count) break;
+    const uint32_t slot = A.q_in[t];
+    const WsTask task = A.tasks[slot];
+    const WsNode node = A.nodes[task.node];
+    float4 q[KQ];
+    {
+      const float* qrow = A.queries + (size_t)task.query * A.dim;
+#pragma unroll
+      for (int i = 0; i < KQ; i++) {
+        const int c = (tl + WS_TEAM * i) * 4;
+        q[i].x = (c + 0 < (int)A.dim) ? __ldg(qrow + c + 0) : 0.f;
+        q[i].y = (c + 1 < (int)A.dim) ? __ldg(qrow + c + 1) : 0.f;
+        q[i].z = (c + 2 < (int)A.dim) ? __ldg(qrow + c + 2) : 0.f;
+        q[i].w = (c + 3 < (int)A.dim) ? __ldg(qrow + c + 3) : 0.f;
+      }
+    }
+    const float4* vbase = reinterpret_cast<const float4*>(A.vecs + (size_t)node.start * A.dpad);
+    const int skip_id = A.skip_query_id ? (int)task.query : -1;
+
+    long long beam = task.beam;
+    int phase = (task.flags & WS_TF_FINAL) ? 1 : 0;
+    const long long mult = (task.flags & WS_TF_MULT1) ? 1 : A.final_mult;
+    int have = 0;
+    bool escalate = false;
+    if (!(task.flags & WS_TF_RESUMED) && lane == 0) A.res_cnt[slot] = 0;
+
+    for (;;) {  // PostfilterVamanaIndex::query (postfilter_vamana.h:141-188)
+      if (phase == 0) {
+        if (!(have < K && beam < A.max_beam)) {
+          long long fin = beam * mult;
+          if (fin > A.max_beam) fin = A.max_beam;
+          if (fin > beam) { beam = fin; phase = 1; } else break;
+        }
+      }
+      if (beam > (long long)CAP) { escalate = true; break; }
+      const int B = (int)beam;
+
+      // ---- beam_search (beamSearch.h:51-184), QP.beamSize = QP.k = B, start = local id 0
+      for (int i = lane; i <= (int)A.hash_mask; i += 32) hash[i] = -1;
+      {
+        float d0 = ws_team_dist<KQ, METRIC>(vbase, q, tl, dpad4, team == 0);
+        d0 = __shfl_sync(0xffffffffu, d0, 0);
+        if (lane == 0) fr[0] = ws_key(d0, 0u);
+      }
+      __syncwarp();
+      if (lane == 0) ws_seen_warp(hash, A.hash_mask, 0);
+      __syncwarp();
+      int n = 1, scan_from = 0;
+      unsigned long long nvis = 0, ncmp = 1;
+      uint64_t* cur = fr;
+      uint64_t* oth = fo;
+
+      for (;;) {
+        if ((long long)nvis >= A.limit) break;
+        // first unvisited frontier entry (beamSearch.h:111)
+        int pick = -1;
+        for (int b0 = scan_from; b0 < n; b0 += 32) {
+          const int i = b0 + lane;
+          const bool unv = i < n && !(cur[i] & 1ull);
+          const unsigned bal = __ballot_sync(0xffffffffu, unv);
+          if (bal) { pick = b0 + __ffs(bal) - 1; break; }
+        }
+        if (pick < 0) break;
+        const uint64_t pkey = cur[pick];
+        const uint32_t cur_id = (uint32_t)(pkey & 0xFFFFFFFFull) >> 1;
+        __syncwarp();
+        if (lane == 0) cur[pick] = pkey | 1ull;  // visited (beamSearch.h:114-117)
+        nvis++;
+
+        // neighbours not seen before (beamSearch.h:123-131); two per lane
+        int nb0 = -1, nb1 = -1;
+        if (lane < R && (long long)lane < A.degree_limit) nb0 = __ldg(node.adj + (size_t)cur_id * R + lane);
+        if (lane + 32 < R && (long long)(lane + 32) < A.degree_limit) nb1 = __ldg(node.adj + (size_t)cur_id * R + lane + 32);
+        bool keep0 = nb0 >= 0 && nb0 != skip_id;
+        bool keep1 = nb1 >= 0 && nb1 != skip_id;
+        if (keep0) keep0 = !ws_seen_warp(hash, A.hash_mask, nb0);
+        __syncwarp();
+        if (keep1) keep1 = !ws_seen_warp(hash, A.hash_mask, nb1);
+        const unsigned bal0 = __ballot_sync(0xffffffffu, keep0), bal1 = __ballot_sync(0xffffffffu, keep1);
+        const int m0 = __popc(bal0), m = m0 + __popc(bal1);
+        if (m == 0) { scan_from = pick + 1; continue; }
+        if (keep0) cid[__popc(bal0 & lt)] = nb0;
+        if (keep1) cid[m0 + __popc(bal1 & lt)] = nb1;
+        ck[lane] = WS_KEY_MAX;
+        ck[lane + 32] = WS_KEY_MAX;
+        __syncwarp();
+        ncmp += (unsigned long long)m;
+
+        // distances; keep those under the cutoff (beamSearch.h:135-145); 4 teams x 2 rows in flight
+        const float cutoff = (n < B) ? (float)2147483647 : ws_unord((uint32_t)(cur[n - 1] >> 32));
+        for (int jb = 0; jb < m; jb += 8) {
+          const int ja = jb + team, jc = jb + 4 + team;
+          const bool va = ja < m, vc = jc < m;
+          const int ida = va ? cid[ja] : 0, idc = vc ? cid[jc] : 0;
+          const float da = ws_team_dist<KQ, METRIC>(vbase + (size_t)ida * dpad4, q, tl, dpad4, va);
+          const float dc = ws_team_dist<KQ, METRIC>(vbase + (size_t)idc * dpad4, q, tl, dpad4, vc);
+          if (tl == 0) {
+            if (va && da < cutoff) ck[ja] = ws_key(da, (uint32_t)ida << 1);
+            if (vc && dc < cutoff) ck[jc] = ws_key(dc, (uint32_t)idc << 1);
+          }
+        }
+        __syncwarp();
+        uint64_t k0 = ck[lane], k1 = ck[lane + 32];
+        ws_warp_sort64(k0, k1, lane);  // beamSearch.h:148
+        // rank candidates against the frontier, dropping ones already in it (set_union, :151-154)
+        bool ok0 = k0 != WS_KEY_MAX, ok1 = k1 != WS_KEY_MAX;
+        {  // a row can list a neighbour twice (graph.h:85-95 appends without de-duplication) and
+           // the racy visited table may let both copies through: equal keys are adjacent now
+          const uint64_t up0 = __shfl_up_sync(0xffffffffu, k0, 1);
+          uint64_t up1 = __shfl_up_sync(0xffffffffu, k1, 1);
+          const uint64_t last0 = __shfl_sync(0xffffffffu, k0, 31);
+          if (lane == 0) up1 = last0;
+          if (lane > 0 && up0 == k0) ok0 = false;
+          if (up1 == k1) ok1 = false;
+        }
+        int p0 = 0, p1 = 0;
+        if (ok0) { p0 = ws_lb_shift1(cur, n, k0 >> 1); ok0 = !(p0 < n && (cur[p0] >> 1) == (k0 >> 1)); }
+        if (ok1) { p1 = ws_lb_shift1(cur, n, k1 >> 1); ok1 = !(p1 < n && (cur[p1] >> 1) == (k1 >> 1)); }
+        const unsigned ba = __ballot_sync(0xffffffffu, ok0), bb = __ballot_sync(0xffffffffu, ok1);
+        const int ca = __popc(ba), mc2 = ca + __popc(bb);
+        if (mc2 == 0) { scan_from = pick + 1; continue; }
+        if (ok0) { const int r = __popc(ba & lt); ck2[r] = k0; cpos[r] = p0; }
+        if (ok1) { const int r = ca + __popc(bb & lt); ck2[r] = k1; cpos[r] = p1; }
+        __syncwarp();
+        // merge into the other buffer, trim to the beam (beamSearch.h:151-172)
+        for (int i = lane; i < n; i += 32) {
+          const uint64_t key = cur[i];
+          const int pos = i + ws_lb_shift1(ck2, mc2, key >> 1);
+          if (pos < B) oth[pos] = key;
+        }
+        for (int j = lane; j < mc2; j += 32) {
+          const int pos = cpos[j] + j;
+          if (pos < B) oth[pos] = ck2[j];
+        }
+        const int first_new = cpos[0];
+        n = min(n + mc2, B);
+        scan_from = min(pick + 1, first_new);
+        uint64_t* tmp = cur; cur = oth; oth = tmp;
+        __syncwarp();
+      }
+
+      // raw_query's label predicate, closed interval (postfilter_vamana.h:234-251)
+      have = 0;
+      for (int b0 = 0; b0 < n && have < K; b0 += 32) {
+        const int i = b0 + lane;
+        bool in = false;
+        uint64_t key = 0;
+        uint32_t rank = 0;
+        if (i < n) {
+          key = cur[i];
+          rank = node.start + ((uint32_t)(key & 0xFFFFFFFFull) >> 1);
+          const float lab = __ldg(A.labels + rank);
+          in = (lab >= task.lo) && (lab <= task.hi);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        const int r = have + __popc(bal & lt);
+        if (in && r < K) A.res_keys[(size_t)slot * K + r] = (key & 0xFFFFFFFF00000000ull) | rank;
+        have += __popc(bal);
+      }
+      if (lane == 0) {
+        A.res_cnt[slot] = (uint32_t)min(have, K);
+        atomicAdd(A.stats + WS_ST_SEARCHES, 1ull);
+        atomicAdd(A.stats + WS_ST_VISITED, nvis);
+        atomicAdd(A.stats + WS_ST_DISTCMPS, ncmp);
+        atomicAdd(A.stats + WS_ST_BEAMSUM, (unsigned long long)B);
+      }
+      __syncwarp();
+      if (phase == 1) break;
+      if (have < K) beam *= 2;
+    }
+
+    if (escalate && lane == 0 && A.q_out != nullptr) {
+      A.tasks[slot].beam = (uint32_t)beam;
+      A.tasks[slot].flags = task.flags | WS_TF_RESUMED | (phase ? WS_TF_FINAL : 0u);
+      const uint32_t pos = atomicAdd(A.q_out_count, 1u);
+      A.q_out[pos] = slot;
+      atomicAdd(A.stats + WS_ST_ESCALATED, 1ull);
+    }
+  }
+}

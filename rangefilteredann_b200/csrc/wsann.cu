@@ -51,11 +51,14 @@ static int ws_fail(int code, const char* fmt, ...) {
 // ------------------------------------------------------------------------------------------
 // index object
 // ------------------------------------------------------------------------------------------
-static const uint32_t kBeamTierCaps[3] = {64, 256, 1024};  // shared-memory-visited tiers
+// beam tiers: 0,1 = warp-per-task kernels (cap 64 / 128), 2,3 = CTA-per-task with a shared-memory
+// visited table (cap 256 / 1024), 4 = CTA-per-task with a global visited bitmap
+static const uint32_t kBeamTierCaps[4] = {64, 128, 256, 1024};
+#define WS_NUM_TIERS 5
 static const uint32_t kBeamCapLarge = 12288;                // global-bitmap tier
 static const uint32_t kMaxK = WS_TOPK_BUF / 2;
 static const size_t kAdjSlabBytes = 256ull << 20;
-#define WS_NUM_KERNEL_KINDS 8  // 0 decompose, 1-3 beam tiers 64/256/1024, 4 beam large, 5 scan, 6 merge
+#define WS_NUM_KERNEL_KINDS 8  // 0 decompose, 1-2 warp beam tiers 64/128, 3-4 CTA beam tiers 256/1024, 5 beam large, 6 scan, 7 merge
 
 struct WsDevBuf {
   void* p = nullptr;
@@ -110,6 +113,8 @@ struct ws_index {
   int64_t opt_skip_query_id = 1;
   int64_t opt_scan_chunk = 8192;
   int64_t opt_hash_factor = 32;
+  int64_t opt_warp_tiers = 1;    // use the warp-per-task kernels for beams <= 128
+  int64_t opt_warp_hash = 2048;  // visited-table entries per warp in those kernels
   int64_t opt_build_expand = 1;  // nodes expanded per step while BUILDING graphs
   uint64_t build_stats[4] = {0, 0, 0, 0};  // inserts, visited, dist_cmps, overflow re-prunes  // smem visited-table entries per unit of beam capacity
 
@@ -518,6 +523,20 @@ static cudaError_t ws_beam_occupancy_t(bool global_seen, size_t smem, int* block
 }
 
 template <int KQ, int METRIC>
+static cudaError_t ws_launch_beam_warp_t(int grid, size_t smem, cudaStream_t s, const WsBeamArgs& a) {
+  cudaError_t e = cudaFuncSetAttribute(ws_beam_warp_kernel<KQ, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  ws_beam_warp_kernel<KQ, METRIC><<<grid, WS_WARPS_PER_CTA * 32, smem, s>>>(a);
+  return cudaGetLastError();
+}
+template <int KQ, int METRIC>
+static cudaError_t ws_beam_warp_occupancy_t(size_t smem, int* blocks) {
+  cudaError_t e = cudaFuncSetAttribute(ws_beam_warp_kernel<KQ, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_beam_warp_kernel<KQ, METRIC>, WS_WARPS_PER_CTA * 32, smem);
+}
+
+template <int KQ, int METRIC>
 static cudaError_t ws_launch_scan_t(int grid, size_t smem, cudaStream_t s, const WsScanArgs& a) {
   cudaError_t e = cudaFuncSetAttribute(ws_scan_kernel<KQ, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -605,7 +624,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
   WS_TRY(ws_ensure(idx, idx->res_keys, slots * k * sizeof(uint64_t)));
   WS_TRY(ws_ensure(idx, idx->res_cnt, slots * sizeof(uint32_t)));
   WS_TRY(ws_ensure(idx, idx->counts, nq * sizeof(uint32_t)));
-  WS_TRY(ws_ensure(idx, idx->queues, 5 * slots * sizeof(uint32_t)));
+  WS_TRY(ws_ensure(idx, idx->queues, (WS_NUM_TIERS + 1) * slots * sizeof(uint32_t)));
   WS_TRY(ws_ensure(idx, idx->ctrl, 64 * sizeof(uint32_t)));
   const bool dev_ptrs = (flags & WS_FLAG_DEVICE_PTRS) != 0;
   const float* dq = queries;
@@ -624,16 +643,17 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
     dids = (uint32_t*)idx->d_ids.p;
     ddists = (float*)idx->d_dists.p;
   }
-  // ctrl layout: [0..4] queue counts (graph tiers 0..3, scan = 4), [8..12] queue heads, [16] overflow
+  // ctrl layout: [0..5] queue counts (beam tiers 0..4, scan = 5), [8..13] queue heads, [16] overflow
   uint32_t* ctrl = (uint32_t*)idx->ctrl.p;
   WS_CUDA(cudaMemsetAsync(ctrl, 0, 64 * sizeof(uint32_t), st));
   uint32_t* queues = (uint32_t*)idx->queues.p;
 
   // ---- tiers: which launch takes fresh graph tasks
   const int kq = ws_pick_kq(idx->dpad);
-  int first_tier = 3;
+  const int lowest_tier = (idx->R <= 64 && idx->opt_warp_tiers) ? 0 : 2;
+  int first_tier = WS_NUM_TIERS - 1;
   if (needs_graph) {
-    for (int t = 0; t < 3; t++)
+    for (int t = lowest_tier; t < WS_NUM_TIERS - 1; t++)
       if ((uint64_t)qp.beam_size <= kBeamTierCaps[t]) { first_tier = t; break; }
   }
 
@@ -653,8 +673,8 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
   da.counts = (uint32_t*)idx->counts.p;
   da.gq = queues + (size_t)first_tier * slots;
   da.gq_count = ctrl + first_tier;
-  da.sq = queues + 4 * slots;
-  da.sq_count = ctrl + 4;
+  da.sq = queues + (size_t)WS_NUM_TIERS * slots;
+  da.sq_count = ctrl + WS_NUM_TIERS;
   da.overflow = ctrl + 16;
   da.stats = idx->d_stats;
   {
@@ -668,20 +688,27 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
     const uint32_t E = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(8, idx->opt_expand));
     uint32_t cand_cap = 64;
     while (cand_cap < E * idx->R) cand_cap <<= 1;
-    for (int t = first_tier; t < 4; t++) {
-      const bool large = (t == 3);
+    for (int t = first_tier; t < WS_NUM_TIERS; t++) {
+      const bool large = (t == WS_NUM_TIERS - 1);
+      const bool warp_tier = t < 2;
       const uint32_t beam_cap = large ? kBeamCapLarge : kBeamTierCaps[t];
-      if (t > first_tier && (int64_t)(large ? kBeamTierCaps[2] : kBeamTierCaps[t - 1]) >= qp.postfiltering_max_beam)
+      if (t > first_tier && (int64_t)kBeamTierCaps[t - 1] >= qp.postfiltering_max_beam)
         break;  // no task can need a beam this large
       uint32_t hash_entries = 0;
-      if (!large) {
+      if (warp_tier) {
+        hash_entries = (uint32_t)idx->opt_warp_hash;
+      } else if (!large) {
         hash_entries = 1024;
         while (hash_entries < (uint64_t)idx->opt_hash_factor * beam_cap) hash_entries <<= 1;
       }
-      size_t smem = (size_t)2 * beam_cap * 8 + (size_t)cand_cap * 24 + (size_t)idx->dpad * 4 + (size_t)hash_entries * 4;
+      size_t smem;
+      if (warp_tier)
+        smem = (size_t)WS_WARPS_PER_CTA * ((size_t)2 * beam_cap * 8 + 64 * 8 * 2 + 64 * 4 * 2 + (size_t)hash_entries * 4);
+      else
+        smem = (size_t)2 * beam_cap * 8 + (size_t)cand_cap * 24 + (size_t)idx->dpad * 4 + (size_t)hash_entries * 4;
       if (smem > idx->smem_optin) return ws_fail(WS_ERR_BADARG, "beam tier %d needs %zu B of shared memory (> %zu)", t, smem, idx->smem_optin);
       int occ = 0;
-#define WS_OCC(KQ_, M_) { cudaError_t _e = ws_beam_occupancy_t<KQ_, M_>(large, smem, &occ); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(_e)); }
+#define WS_OCC(KQ_, M_) { cudaError_t _e = warp_tier ? ws_beam_warp_occupancy_t<KQ_, M_>(smem, &occ) : ws_beam_occupancy_t<KQ_, M_>(large, smem, &occ); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(_e)); }
       WS_DISPATCH_KQ(kq, idx->metric, WS_OCC);
 #undef WS_OCC
       if (occ < 1) return ws_fail(WS_ERR_CUDA, "beam kernel does not fit on an SM (smem %zu)", smem);
@@ -692,8 +719,8 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
       ba.tasks = (WsTask*)idx->tasks.p; ba.res_keys = (uint64_t*)idx->res_keys.p; ba.res_cnt = (uint32_t*)idx->res_cnt.p;
       ba.k = k;
       ba.q_in = queues + (size_t)t * slots; ba.q_in_count = ctrl + t; ba.q_head = ctrl + 8 + t;
-      ba.q_out = (t < 3) ? queues + (size_t)(t + 1) * slots : nullptr;
-      ba.q_out_count = (t < 3) ? ctrl + t + 1 : nullptr;
+      ba.q_out = !large ? queues + (size_t)(t + 1) * slots : nullptr;
+      ba.q_out_count = !large ? ctrl + t + 1 : nullptr;
       ba.beam_cap = beam_cap; ba.hash_mask = hash_entries ? hash_entries - 1 : 0; ba.cand_cap = cand_cap;
       ba.expand = E; ba.skip_query_id = (int32_t)idx->opt_skip_query_id;
       ba.max_beam = qp.postfiltering_max_beam; ba.final_mult = qp.final_beam_multiply;
@@ -707,7 +734,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
         ba.bitmap = (uint32_t*)idx->bitmap.p;
       }
       ba.stats = idx->d_stats;
-#define WS_LB(KQ_, M_) { cudaError_t _e = ws_launch_beam_t<KQ_, M_>(large, grid, smem, st, ba); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "beam kernel launch (tier %d): %s", t, cudaGetErrorString(_e)); }
+#define WS_LB(KQ_, M_) { cudaError_t _e = warp_tier ? ws_launch_beam_warp_t<KQ_, M_>(grid, smem, st, ba) : ws_launch_beam_t<KQ_, M_>(large, grid, smem, st, ba); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "beam kernel launch (tier %d): %s", t, cudaGetErrorString(_e)); }
       {
         WsKernelScope ks(idx, 1 + t);
         WS_DISPATCH_KQ(kq, idx->metric, WS_LB);
@@ -722,13 +749,13 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
     sa.vecs = idx->d_vecs; sa.queries = dq; sa.dim = idx->dim; sa.dpad = idx->dpad;
     sa.tasks = (const WsTask*)idx->tasks.p; sa.res_keys = (uint64_t*)idx->res_keys.p; sa.res_cnt = (uint32_t*)idx->res_cnt.p;
     sa.k = k;
-    sa.q_in = queues + 4 * slots; sa.q_in_count = ctrl + 4; sa.q_head = ctrl + 8 + 4;
+    sa.q_in = queues + (size_t)WS_NUM_TIERS * slots; sa.q_in_count = ctrl + WS_NUM_TIERS; sa.q_head = ctrl + 8 + WS_NUM_TIERS;
     sa.stats = idx->d_stats;
     size_t smem = (size_t)WS_TOPK_BUF * 8 + (size_t)idx->dpad * 4;
     int grid = idx->num_sms * 8;
 #define WS_LS(KQ_, M_) { cudaError_t _e = ws_launch_scan_t<KQ_, M_>(grid, smem, st, sa); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "scan kernel launch: %s", cudaGetErrorString(_e)); }
     {
-      WsKernelScope ks(idx, 5);
+      WsKernelScope ks(idx, 6);
       WS_DISPATCH_KQ(kq, idx->metric, WS_LS);
     }
 #undef WS_LS
@@ -743,7 +770,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
     ma.nq = (uint32_t)nq; ma.ids = dids; ma.dists = ddists;
     int grid = (int)std::min<uint64_t>(nq, (uint64_t)idx->num_sms * 16);
     {
-      WsKernelScope ks(idx, 6);
+      WsKernelScope ks(idx, 7);
       ws_merge_kernel<<<grid, WS_CTA_THREADS, 0, st>>>(ma);
     }
     WS_CUDA(cudaGetLastError());
@@ -1170,6 +1197,11 @@ int ws_index_set_option(ws_index* idx, const char* name, int64_t value) {
   } else if (s == "scan_chunk") {
     if (value < 256) return ws_fail(WS_ERR_BADARG, "scan_chunk must be >= 256");
     idx->opt_scan_chunk = value;
+  } else if (s == "warp_tiers") {
+    idx->opt_warp_tiers = value != 0;
+  } else if (s == "warp_hash") {
+    if (value < 256 || value > 16384 || (value & (value - 1))) return ws_fail(WS_ERR_BADARG, "warp_hash must be a power of two in 256..16384");
+    idx->opt_warp_hash = value;
   } else if (s == "build_expand_width") {
     if (value < 1 || value > 8) return ws_fail(WS_ERR_BADARG, "build_expand_width must be 1..8");
     idx->opt_build_expand = value;

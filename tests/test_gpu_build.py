@@ -39,6 +39,7 @@ def test_saved_files_are_valid_reference_graphs(built):
     files = sorted(os.listdir(built["cache"]))
     assert len(files) == 15  # rows of 1, 2, 4, 8 buckets (3000 -> 375)
     total_deg = 0
+    dup_rows = rows_seen = 0
     for f in files:
         n, maxdeg, deg, edges = read_graph(os.path.join(built["cache"], f))
         assert maxdeg == 64 and f.endswith(f"_{n}.bin")
@@ -47,10 +48,15 @@ def test_saved_files_are_valid_reference_graphs(built):
         off = np.concatenate([[0], np.cumsum(deg)])
         for i in range(0, n, max(1, n // 50)):
             row = edges[off[i]:off[i + 1]]
-            assert i not in row and len(set(row.tolist())) == len(row)
+            assert i not in row  # no self loops
+            rows_seen += 1
+            # append_neighbors (graph.h:85-95) does not de-duplicate; the reference builder's own
+            # graphs carry a few repeated neighbours too (68 of 12000 rows in tests/golden/tiny)
+            dup_rows += len(set(row.tolist())) != len(row)
         assert (deg > 0).mean() > 0.99
         total_deg += deg.mean()
     assert 5 < total_deg / len(files) < 64
+    assert dup_rows <= 0.05 * rows_seen
 
 
 def test_oracle_on_built_graphs_is_bit_identical(engine, built):

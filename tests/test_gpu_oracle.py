@@ -174,6 +174,26 @@ def test_expand_width_keeps_recall(tiny):
         h.set_option("expand_width", 1)
 
 
+def test_cta_tiers_match_warp_tiers(tiny):
+    """Beams <= 128 normally run on the warp-per-task kernels; with them disabled the
+    CTA-per-task kernels must give the same bits."""
+    h = capi.Handle.borrow(tiny.eng["wst"])
+    w = synth.make_windows(tiny.labels, -3, 48, seed=31)
+    q = tiny.queries[:48]
+    try:
+        h.set_option("warp_tiers", 0)
+        for beam, mult in ((10, 1), (40, 2), (100, 4)):
+            for method in ("fenwick", "optimized_postfilter", "three_split"):
+                tiny.assert_identical(method, q, w, beam=beam, mult=mult)
+    finally:
+        h.set_option("warp_tiers", 1)
+    try:
+        h.set_option("warp_hash", 256)  # a saturated visited table may only cost recomputation
+        tiny.assert_identical("optimized_postfilter", q, w, beam=60, mult=2)
+    finally:
+        h.set_option("warp_hash", 2048)
+
+
 def test_rejects_unsupported(tiny, engine):
     w = synth.make_windows(tiny.labels, -2, 4, seed=1)
     with pytest.raises(RuntimeError, match="postfiltering_max_beam"):
