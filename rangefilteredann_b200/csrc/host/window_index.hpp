@@ -25,6 +25,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <filesystem>
 #include <fstream>
 #include <limits>
 #include <memory>
@@ -233,6 +234,11 @@ class Arena {
     std::vector<int32_t> rows(pl.count * (size_t)R);
     check(ws_index_get_graph(idx_, node, &R, deg.data(), rows.data()), "ws_index_get_graph");
     std::string path = graph_filename(bp, pl.min_label, pl.max_label, pl.count);
+    {
+      std::error_code ec;
+      auto dir = std::filesystem::path(path).parent_path();
+      if (!dir.empty()) std::filesystem::create_directories(dir, ec);
+    }
     std::string tmp = path + ".tmp";
     {
       std::ofstream out(tmp, std::ios::binary);

@@ -70,6 +70,41 @@ __device__ __forceinline__ float ws_team_dist(const float4* __restrict__ row, co
   return METRIC == 0 ? acc : -acc;
 }
 
+// Predicate-free variant for the hot loops: `rowtl` already points at this lane's first
+// float4 (row + tl) of a row that is always safe to read (callers clamp the candidate
+// index instead of predicating the loads).  EXACT = the padded row is exactly 8*KQ float4s,
+// so no column check is needed either.  Same accumulation order as ws_team_dist.
+template <int KQ, int METRIC, bool EXACT>
+__device__ __forceinline__ float ws_team_dist_nv(const float4* __restrict__ rowtl, const float4 (&q)[KQ], int tl,
+                                                 int dpad4) {
+  float4 v[KQ];
+#pragma unroll
+  for (int i = 0; i < KQ; i++) {
+    if (EXACT || tl + WS_TEAM * i < dpad4) v[i] = ws_ldg_f4(rowtl + WS_TEAM * i);
+    else v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < KQ; i++) {
+    if (METRIC == 0) {
+      float dx = v[i].x - q[i].x, dy = v[i].y - q[i].y, dz = v[i].z - q[i].z, dw = v[i].w - q[i].w;
+      acc = __fmaf_rn(dx, dx, acc);
+      acc = __fmaf_rn(dy, dy, acc);
+      acc = __fmaf_rn(dz, dz, acc);
+      acc = __fmaf_rn(dw, dw, acc);
+    } else {
+      acc = __fmaf_rn(v[i].x, q[i].x, acc);
+      acc = __fmaf_rn(v[i].y, q[i].y, acc);
+      acc = __fmaf_rn(v[i].z, q[i].z, acc);
+      acc = __fmaf_rn(v[i].w, q[i].w, acc);
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  return METRIC == 0 ? acc : -acc;
+}
+
 // Load this lane's share of the (zero-padded, smem-staged) query.
 template <int KQ>
 __device__ __forceinline__ void ws_load_query(const float* qs, float4 (&q)[KQ], int tl, int dpad4) {

@@ -615,6 +615,16 @@ __device__ __forceinline__ bool ws_seen_warp(volatile int* table, uint32_t mask,
   return false;
 }
 
+__device__ __forceinline__ uint64_t ws_shfl_up_u64(uint64_t v, int d) {
+  uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)v, d);
+  uint32_t hi = __shfl_up_sync(0xffffffffu, (uint32_t)(v >> 32), d);
+  return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ uint64_t ws_shfl_idx_u64(uint64_t v, int src) {
+  uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
+  uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+  return ((uint64_t)hi << 32) | lo;
+}
 __device__ __forceinline__ uint64_t ws_shfl_xor_u64(uint64_t v, int m) {
   uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m);
   uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
@@ -643,26 +653,44 @@ __device__ __forceinline__ void ws_warp_sort64(uint64_t& k0, uint64_t& k1, int l
   }
 }
 
-template <int KQ, int METRIC>
-__global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32) ws_beam_warp_kernel(WsBeamArgs A) {
+// ascending bitonic sort of 32 keys, one per lane
+__device__ __forceinline__ void ws_warp_sort32(uint64_t& k0, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint64_t o = ws_shfl_xor_u64(k0, j);
+      const bool lower = (lane & j) == 0;
+      const bool up = (lane & k) == 0 || k == 32;
+      k0 = (up == lower) ? (k0 < o ? k0 : o) : (k0 < o ? o : k0);
+    }
+  }
+}
+
+// shared memory one warp needs (bytes)
+__host__ __device__ inline size_t ws_warp_smem_bytes(uint32_t cap, uint32_t hash_entries) {
+  return (size_t)cap * 8 + 64 * 8 * 2 + 64 * 4 * 2 + (size_t)hash_entries * 4;
+}
+
+template <int KQ, int METRIC, bool EXACT>
+__global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, 5) ws_beam_warp_kernel(WsBeamArgs A) {
   extern __shared__ __align__(16) unsigned char ws_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tl = lane & (WS_TEAM - 1), team = lane / WS_TEAM;  // 4 teams per warp
   const uint32_t CAP = A.beam_cap;
-  const size_t per_warp = (size_t)2 * CAP * 8 + 64 * 8 * 2 + 64 * 4 * 2 + (size_t)(A.hash_mask + 1) * 4;
-  unsigned char* base = ws_smem + per_warp * warp;
-  uint64_t* fr = reinterpret_cast<uint64_t*>(base);
-  uint64_t* fo = fr + CAP;
-  uint64_t* ck = fo + CAP;        // [64]
-  uint64_t* ck2 = ck + 64;        // [64]
-  int* cpos = reinterpret_cast<int*>(ck2 + 64);  // [64]
-  int* cid = cpos + 64;           // [64]
-  volatile int* hash = cid + 64;  // [hash_mask + 1]
+  unsigned char* base = ws_smem + ws_warp_smem_bytes(CAP, A.hash_mask + 1) * warp;
+  uint64_t* fr = reinterpret_cast<uint64_t*>(base);  // [CAP] frontier, updated in place
+  uint64_t* sk = fr + CAP;                           // [64] candidates under the cutoff
+  uint64_t* sk2 = sk + 64;                           // [64] sorted, de-duplicated
+  int* cpos = reinterpret_cast<int*>(sk2 + 64);      // [64] insertion ranks
+  int* cid = cpos + 64;                              // [64] kept neighbour ids
+  volatile int* hash = cid + 64;                     // [hash_mask + 1]
 
   const int dpad4 = A.dpad >> 2;
   const int K = (int)A.k;
   const int R = (int)A.R;
   const unsigned lt = (1u << lane) - 1u;
+  const bool leader = tl == 0;
 
   for (;;) {
     uint32_t t = 0;
@@ -684,7 +712,7 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32) ws_beam_warp_kernel(WsB
         q[i].w = (c + 3 < (int)A.dim) ? __ldg(qrow + c + 3) : 0.f;
       }
     }
-    const float4* vbase = reinterpret_cast<const float4*>(A.vecs + (size_t)node.start * A.dpad);
+    const float4* vbase_tl = reinterpret_cast<const float4*>(A.vecs + (size_t)node.start * A.dpad) + tl;
     const int skip_id = A.skip_query_id ? (int)task.query : -1;
 
     long long beam = task.beam;
@@ -708,8 +736,7 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32) ws_beam_warp_kernel(WsB
       // ---- beam_search (beamSearch.h:51-184), QP.beamSize = QP.k = B, start = local id 0
       for (int i = lane; i <= (int)A.hash_mask; i += 32) hash[i] = -1;
       {
-        float d0 = ws_team_dist<KQ, METRIC>(vbase, q, tl, dpad4, team == 0);
-        d0 = __shfl_sync(0xffffffffu, d0, 0);
+        const float d0 = ws_team_dist_nv<KQ, METRIC, EXACT>(vbase_tl, q, tl, dpad4);
         if (lane == 0) fr[0] = ws_key(d0, 0u);
       }
       __syncwarp();
@@ -717,8 +744,6 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32) ws_beam_warp_kernel(WsB
       __syncwarp();
       int n = 1, scan_from = 0;
       unsigned long long nvis = 0, ncmp = 1;
-      uint64_t* cur = fr;
-      uint64_t* oth = fo;
 
       for (;;) {
         if ((long long)nvis >= A.limit) break;
@@ -726,21 +751,24 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32) ws_beam_warp_kernel(WsB
         int pick = -1;
         for (int b0 = scan_from; b0 < n; b0 += 32) {
           const int i = b0 + lane;
-          const bool unv = i < n && !(cur[i] & 1ull);
+          const bool unv = i < n && !(fr[i] & 1ull);
           const unsigned bal = __ballot_sync(0xffffffffu, unv);
           if (bal) { pick = b0 + __ffs(bal) - 1; break; }
         }
         if (pick < 0) break;
-        const uint64_t pkey = cur[pick];
+        const uint64_t pkey = fr[pick];
         const uint32_t cur_id = (uint32_t)(pkey & 0xFFFFFFFFull) >> 1;
         __syncwarp();
-        if (lane == 0) cur[pick] = pkey | 1ull;  // visited (beamSearch.h:114-117)
+        if (lane == 0) fr[pick] = pkey | 1ull;  // visited (beamSearch.h:114-117)
         nvis++;
 
         // neighbours not seen before (beamSearch.h:123-131); two per lane
         int nb0 = -1, nb1 = -1;
-        if (lane < R && (long long)lane < A.degree_limit) nb0 = __ldg(node.adj + (size_t)cur_id * R + lane);
-        if (lane + 32 < R && (long long)(lane + 32) < A.degree_limit) nb1 = __ldg(node.adj + (size_t)cur_id * R + lane + 32);
+        {
+          const int* arow = node.adj + (size_t)cur_id * R;
+          if (lane < R && (long long)lane < A.degree_limit) nb0 = __ldg(arow + lane);
+          if (lane + 32 < R && (long long)(lane + 32) < A.degree_limit) nb1 = __ldg(arow + lane + 32);
+        }
         bool keep0 = nb0 >= 0 && nb0 != skip_id;
         bool keep1 = nb1 >= 0 && nb1 != skip_id;
         if (keep0) keep0 = !ws_seen_warp(hash, A.hash_mask, nb0);
@@ -751,61 +779,83 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32) ws_beam_warp_kernel(WsB
         if (m == 0) { scan_from = pick + 1; continue; }
         if (keep0) cid[__popc(bal0 & lt)] = nb0;
         if (keep1) cid[m0 + __popc(bal1 & lt)] = nb1;
-        ck[lane] = WS_KEY_MAX;
-        ck[lane + 32] = WS_KEY_MAX;
         __syncwarp();
         ncmp += (unsigned long long)m;
 
-        // distances; keep those under the cutoff (beamSearch.h:135-145); 4 teams x 2 rows in flight
-        const float cutoff = (n < B) ? (float)2147483647 : ws_unord((uint32_t)(cur[n - 1] >> 32));
+        // distances (4 teams x 2 rows in flight); keep those under the cutoff (beamSearch.h:135-145)
+        const float cutoff = (n < B) ? (float)2147483647 : ws_unord((uint32_t)(fr[n - 1] >> 32));
+        int s = 0;
         for (int jb = 0; jb < m; jb += 8) {
           const int ja = jb + team, jc = jb + 4 + team;
-          const bool va = ja < m, vc = jc < m;
-          const int ida = va ? cid[ja] : 0, idc = vc ? cid[jc] : 0;
-          const float da = ws_team_dist<KQ, METRIC>(vbase + (size_t)ida * dpad4, q, tl, dpad4, va);
-          const float dc = ws_team_dist<KQ, METRIC>(vbase + (size_t)idc * dpad4, q, tl, dpad4, vc);
-          if (tl == 0) {
-            if (va && da < cutoff) ck[ja] = ws_key(da, (uint32_t)ida << 1);
-            if (vc && dc < cutoff) ck[jc] = ws_key(dc, (uint32_t)idc << 1);
-          }
+          const int ida = cid[min(ja, m - 1)], idc = cid[min(jc, m - 1)];
+          const float da = ws_team_dist_nv<KQ, METRIC, EXACT>(vbase_tl + (size_t)ida * dpad4, q, tl, dpad4);
+          const float dc = ws_team_dist_nv<KQ, METRIC, EXACT>(vbase_tl + (size_t)idc * dpad4, q, tl, dpad4);
+          const bool pa = leader && ja < m && da < cutoff;
+          const bool pc = leader && jc < m && dc < cutoff;
+          const unsigned ba = __ballot_sync(0xffffffffu, pa), bc = __ballot_sync(0xffffffffu, pc);
+          if (pa) sk[s + __popc(ba & lt)] = ws_key(da, (uint32_t)ida << 1);
+          s += __popc(ba);
+          if (pc) sk[s + __popc(bc & lt)] = ws_key(dc, (uint32_t)idc << 1);
+          s += __popc(bc);
         }
+        if (s == 0) { scan_from = pick + 1; continue; }
         __syncwarp();
-        uint64_t k0 = ck[lane], k1 = ck[lane + 32];
-        ws_warp_sort64(k0, k1, lane);  // beamSearch.h:148
-        // rank candidates against the frontier, dropping ones already in it (set_union, :151-154)
+
+        // sort the survivors (beamSearch.h:148), then rank them against the frontier, dropping
+        // ones already in it (the reference's set_union de-duplicates the same way, :151-154)
+        uint64_t k0 = lane < s ? sk[lane] : WS_KEY_MAX, k1 = WS_KEY_MAX;
+        if (s > 32) {
+          k1 = lane + 32 < s ? sk[lane + 32] : WS_KEY_MAX;
+          ws_warp_sort64(k0, k1, lane);
+        } else {
+          ws_warp_sort32(k0, lane);
+        }
         bool ok0 = k0 != WS_KEY_MAX, ok1 = k1 != WS_KEY_MAX;
         {  // a row can list a neighbour twice (graph.h:85-95 appends without de-duplication) and
            // the racy visited table may let both copies through: equal keys are adjacent now
-          const uint64_t up0 = __shfl_up_sync(0xffffffffu, k0, 1);
-          uint64_t up1 = __shfl_up_sync(0xffffffffu, k1, 1);
-          const uint64_t last0 = __shfl_sync(0xffffffffu, k0, 31);
-          if (lane == 0) up1 = last0;
+          const uint64_t up0 = ws_shfl_up_u64(k0, 1);
           if (lane > 0 && up0 == k0) ok0 = false;
-          if (up1 == k1) ok1 = false;
+          if (s > 32) {
+            uint64_t up1 = ws_shfl_up_u64(k1, 1);
+            const uint64_t last0 = ws_shfl_idx_u64(k0, 31);
+            if (lane == 0) up1 = last0;
+            if (up1 == k1) ok1 = false;
+          }
         }
         int p0 = 0, p1 = 0;
-        if (ok0) { p0 = ws_lb_shift1(cur, n, k0 >> 1); ok0 = !(p0 < n && (cur[p0] >> 1) == (k0 >> 1)); }
-        if (ok1) { p1 = ws_lb_shift1(cur, n, k1 >> 1); ok1 = !(p1 < n && (cur[p1] >> 1) == (k1 >> 1)); }
-        const unsigned ba = __ballot_sync(0xffffffffu, ok0), bb = __ballot_sync(0xffffffffu, ok1);
-        const int ca = __popc(ba), mc2 = ca + __popc(bb);
+        if (ok0) { p0 = ws_lb_shift1(fr, n, k0 >> 1); ok0 = !(p0 < n && (fr[p0] >> 1) == (k0 >> 1)); }
+        if (ok1) { p1 = ws_lb_shift1(fr, n, k1 >> 1); ok1 = !(p1 < n && (fr[p1] >> 1) == (k1 >> 1)); }
+        const unsigned bka = __ballot_sync(0xffffffffu, ok0), bkb = __ballot_sync(0xffffffffu, ok1);
+        const int ca = __popc(bka), mc2 = ca + __popc(bkb);
         if (mc2 == 0) { scan_from = pick + 1; continue; }
-        if (ok0) { const int r = __popc(ba & lt); ck2[r] = k0; cpos[r] = p0; }
-        if (ok1) { const int r = ca + __popc(bb & lt); ck2[r] = k1; cpos[r] = p1; }
+        if (ok0) { const int r = __popc(bka & lt); sk2[r] = k0; cpos[r] = p0; }
+        if (ok1) { const int r = ca + __popc(bkb & lt); sk2[r] = k1; cpos[r] = p1; }
         __syncwarp();
-        // merge into the other buffer, trim to the beam (beamSearch.h:151-172)
-        for (int i = lane; i < n; i += 32) {
-          const uint64_t key = cur[i];
-          const int pos = i + ws_lb_shift1(ck2, mc2, key >> 1);
-          if (pos < B) oth[pos] = key;
+
+        // merge in place, trim to the beam (beamSearch.h:151-172): entries before the first
+        // insertion point stay where they are
+        const int first_new = cpos[0];
+        uint64_t e[4];
+        int np[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const int i = lane + 32 * r;
+          np[r] = -1;
+          if (i >= first_new && i < n) {
+            e[r] = fr[i];
+            np[r] = i + ws_lb_shift1(sk2, mc2, e[r] >> 1);
+          }
         }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+          if (np[r] >= 0 && np[r] < B) fr[np[r]] = e[r];
         for (int j = lane; j < mc2; j += 32) {
           const int pos = cpos[j] + j;
-          if (pos < B) oth[pos] = ck2[j];
+          if (pos < B) fr[pos] = sk2[j];
         }
-        const int first_new = cpos[0];
         n = min(n + mc2, B);
         scan_from = min(pick + 1, first_new);
-        uint64_t* tmp = cur; cur = oth; oth = tmp;
         __syncwarp();
       }
 
@@ -817,7 +867,7 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32) ws_beam_warp_kernel(WsB
         uint64_t key = 0;
         uint32_t rank = 0;
         if (i < n) {
-          key = cur[i];
+          key = fr[i];
           rank = node.start + ((uint32_t)(key & 0xFFFFFFFFull) >> 1);
           const float lab = __ldg(A.labels + rank);
           in = (lab >= task.lo) && (lab <= task.hi);

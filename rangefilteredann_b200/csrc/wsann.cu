@@ -523,17 +523,30 @@ static cudaError_t ws_beam_occupancy_t(bool global_seen, size_t smem, int* block
 }
 
 template <int KQ, int METRIC>
-static cudaError_t ws_launch_beam_warp_t(int grid, size_t smem, cudaStream_t s, const WsBeamArgs& a) {
-  cudaError_t e = cudaFuncSetAttribute(ws_beam_warp_kernel<KQ, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  ws_beam_warp_kernel<KQ, METRIC><<<grid, WS_WARPS_PER_CTA * 32, smem, s>>>(a);
+static cudaError_t ws_launch_beam_warp_t(bool exact, int grid, size_t smem, cudaStream_t s, const WsBeamArgs& a) {
+  cudaError_t e;
+  if (exact) {
+    e = cudaFuncSetAttribute(ws_beam_warp_kernel<KQ, METRIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ws_beam_warp_kernel<KQ, METRIC, true><<<grid, WS_WARPS_PER_CTA * 32, smem, s>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(ws_beam_warp_kernel<KQ, METRIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ws_beam_warp_kernel<KQ, METRIC, false><<<grid, WS_WARPS_PER_CTA * 32, smem, s>>>(a);
+  }
   return cudaGetLastError();
 }
 template <int KQ, int METRIC>
-static cudaError_t ws_beam_warp_occupancy_t(size_t smem, int* blocks) {
-  cudaError_t e = cudaFuncSetAttribute(ws_beam_warp_kernel<KQ, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+static cudaError_t ws_beam_warp_occupancy_t(bool exact, size_t smem, int* blocks) {
+  cudaError_t e;
+  if (exact) {
+    e = cudaFuncSetAttribute(ws_beam_warp_kernel<KQ, METRIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_beam_warp_kernel<KQ, METRIC, true>, WS_WARPS_PER_CTA * 32, smem);
+  }
+  e = cudaFuncSetAttribute(ws_beam_warp_kernel<KQ, METRIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_beam_warp_kernel<KQ, METRIC>, WS_WARPS_PER_CTA * 32, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_beam_warp_kernel<KQ, METRIC, false>, WS_WARPS_PER_CTA * 32, smem);
 }
 
 template <int KQ, int METRIC>
@@ -651,6 +664,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
   // ---- tiers: which launch takes fresh graph tasks
   const int kq = ws_pick_kq(idx->dpad);
   const int lowest_tier = (idx->R <= 64 && idx->opt_warp_tiers) ? 0 : 2;
+  const bool exact_rows = (uint32_t)kq * WS_TEAM * 4 == idx->dpad;  // padded row = 8*KQ float4s: no column predicate
   int first_tier = WS_NUM_TIERS - 1;
   if (needs_graph) {
     for (int t = lowest_tier; t < WS_NUM_TIERS - 1; t++)
@@ -703,12 +717,12 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
       }
       size_t smem;
       if (warp_tier)
-        smem = (size_t)WS_WARPS_PER_CTA * ((size_t)2 * beam_cap * 8 + 64 * 8 * 2 + 64 * 4 * 2 + (size_t)hash_entries * 4);
+        smem = (size_t)WS_WARPS_PER_CTA * ws_warp_smem_bytes(beam_cap, hash_entries);
       else
         smem = (size_t)2 * beam_cap * 8 + (size_t)cand_cap * 24 + (size_t)idx->dpad * 4 + (size_t)hash_entries * 4;
       if (smem > idx->smem_optin) return ws_fail(WS_ERR_BADARG, "beam tier %d needs %zu B of shared memory (> %zu)", t, smem, idx->smem_optin);
       int occ = 0;
-#define WS_OCC(KQ_, M_) { cudaError_t _e = warp_tier ? ws_beam_warp_occupancy_t<KQ_, M_>(smem, &occ) : ws_beam_occupancy_t<KQ_, M_>(large, smem, &occ); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(_e)); }
+#define WS_OCC(KQ_, M_) { cudaError_t _e = warp_tier ? ws_beam_warp_occupancy_t<KQ_, M_>(exact_rows, smem, &occ) : ws_beam_occupancy_t<KQ_, M_>(large, smem, &occ); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(_e)); }
       WS_DISPATCH_KQ(kq, idx->metric, WS_OCC);
 #undef WS_OCC
       if (occ < 1) return ws_fail(WS_ERR_CUDA, "beam kernel does not fit on an SM (smem %zu)", smem);
@@ -734,7 +748,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
         ba.bitmap = (uint32_t*)idx->bitmap.p;
       }
       ba.stats = idx->d_stats;
-#define WS_LB(KQ_, M_) { cudaError_t _e = warp_tier ? ws_launch_beam_warp_t<KQ_, M_>(grid, smem, st, ba) : ws_launch_beam_t<KQ_, M_>(large, grid, smem, st, ba); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "beam kernel launch (tier %d): %s", t, cudaGetErrorString(_e)); }
+#define WS_LB(KQ_, M_) { cudaError_t _e = warp_tier ? ws_launch_beam_warp_t<KQ_, M_>(exact_rows, grid, smem, st, ba) : ws_launch_beam_t<KQ_, M_>(large, grid, smem, st, ba); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "beam kernel launch (tier %d): %s", t, cudaGetErrorString(_e)); }
       {
         WsKernelScope ks(idx, 1 + t);
         WS_DISPATCH_KQ(kq, idx->metric, WS_LB);
