@@ -653,6 +653,55 @@ __device__ __forceinline__ void ws_warp_sort64(uint64_t& k0, uint64_t& k1, int l
   }
 }
 
+// Branch-free lower bound: number of keys in a[0..n) whose (key >> 1) is < v.  STEPS = log2 of
+// the capacity (7 -> n <= 128, 6 -> n <= 64); fixed trip count, predicated loads only, so the
+// warp never diverges on it.
+template <int STEPS>
+__device__ __forceinline__ int ws_lb_fixed(const uint64_t* a, int n, uint64_t v) {
+  int lo = 0;
+#pragma unroll
+  for (int step = 1 << (STEPS - 1); step > 0; step >>= 1) {
+    const int mid = lo + step;
+    const uint64_t x = (mid <= n) ? a[mid - 1] : WS_KEY_MAX;
+    lo = (mid <= n && (x >> 1) < v) ? mid : lo;
+  }
+  // capacity itself (n == 1 << STEPS) needs one more probe
+  if ((1 << STEPS) <= n) {
+    const uint64_t x = a[(1 << STEPS) - 1];
+    lo = (lo == (1 << STEPS) - 1 && (x >> 1) < v) ? (1 << STEPS) : lo;
+  }
+  return lo;
+}
+
+// Visited-set probe for two ids per lane with warp-uniform control flow: every lane walks
+// the probe sequence together (votes decide when to stop), loads and stores are predicated.
+// Same guarantees as ws_seen_warp: never reports an unseen id as seen; a lost insertion or
+// an eviction can only cause a recomputation.
+__device__ __forceinline__ void ws_seen_warp2(volatile int* table, uint32_t mask, int id0, bool& keep0, int id1,
+                                              bool& keep1) {
+  const uint32_t h0 = ws_hash32((uint32_t)id0) & mask, h1 = ws_hash32((uint32_t)id1) & mask;
+  bool pend0 = keep0, pend1 = keep1;
+#pragma unroll 1
+  for (int p = 0; p < WS_HASH_PROBES; p++) {
+    if (!__any_sync(0xffffffffu, pend0 || pend1)) break;
+    const uint32_t s0 = (h0 + p) & mask, s1 = (h1 + p) & mask;
+    const int v0 = pend0 ? table[s0] : 0;
+    const bool hit0 = pend0 && v0 == id0, empty0 = pend0 && v0 == -1;
+    if (empty0) table[s0] = id0;
+    keep0 = keep0 && !hit0;
+    pend0 = pend0 && !hit0 && !empty0;
+    __syncwarp();
+    const int v1 = pend1 ? table[s1] : 0;
+    const bool hit1 = pend1 && v1 == id1, empty1 = pend1 && v1 == -1;
+    if (empty1) table[s1] = id1;
+    keep1 = keep1 && !hit1;
+    pend1 = pend1 && !hit1 && !empty1;
+    __syncwarp();
+  }
+  if (pend0) table[h0] = id0;  // probe window full: evict
+  if (pend1) table[h1] = id1;
+}
+
 // ascending bitonic sort of 32 keys, one per lane
 __device__ __forceinline__ void ws_warp_sort32(uint64_t& k0, int lane) {
 #pragma unroll
@@ -771,9 +820,7 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, 5) ws_beam_warp_kernel(
         }
         bool keep0 = nb0 >= 0 && nb0 != skip_id;
         bool keep1 = nb1 >= 0 && nb1 != skip_id;
-        if (keep0) keep0 = !ws_seen_warp(hash, A.hash_mask, nb0);
-        __syncwarp();
-        if (keep1) keep1 = !ws_seen_warp(hash, A.hash_mask, nb1);
+        ws_seen_warp2(hash, A.hash_mask, nb0, keep0, nb1, keep1);
         const unsigned bal0 = __ballot_sync(0xffffffffu, keep0), bal1 = __ballot_sync(0xffffffffu, keep1);
         const int m0 = __popc(bal0), m = m0 + __popc(bal1);
         if (m == 0) { scan_from = pick + 1; continue; }
@@ -810,21 +857,16 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, 5) ws_beam_warp_kernel(
         } else {
           ws_warp_sort32(k0, lane);
         }
-        bool ok0 = k0 != WS_KEY_MAX, ok1 = k1 != WS_KEY_MAX;
-        {  // a row can list a neighbour twice (graph.h:85-95 appends without de-duplication) and
-           // the racy visited table may let both copies through: equal keys are adjacent now
-          const uint64_t up0 = ws_shfl_up_u64(k0, 1);
-          if (lane > 0 && up0 == k0) ok0 = false;
-          if (s > 32) {
-            uint64_t up1 = ws_shfl_up_u64(k1, 1);
-            const uint64_t last0 = ws_shfl_idx_u64(k0, 31);
-            if (lane == 0) up1 = last0;
-            if (up1 == k1) ok1 = false;
-          }
-        }
-        int p0 = 0, p1 = 0;
-        if (ok0) { p0 = ws_lb_shift1(fr, n, k0 >> 1); ok0 = !(p0 < n && (fr[p0] >> 1) == (k0 >> 1)); }
-        if (ok1) { p1 = ws_lb_shift1(fr, n, k1 >> 1); ok1 = !(p1 < n && (fr[p1] >> 1) == (k1 >> 1)); }
+        // a row can list a neighbour twice (graph.h:85-95 appends without de-duplication) and
+        // the racy visited table may let both copies through: equal keys are adjacent now
+        const uint64_t up0 = ws_shfl_up_u64(k0, 1);
+        uint64_t up1 = ws_shfl_up_u64(k1, 1);
+        const uint64_t last0 = ws_shfl_idx_u64(k0, 31);
+        up1 = lane == 0 ? last0 : up1;
+        const int p0 = ws_lb_fixed<7>(fr, n, k0 >> 1), p1 = ws_lb_fixed<7>(fr, n, k1 >> 1);
+        const uint64_t f0 = fr[min(p0, n - 1)], f1 = fr[min(p1, n - 1)];
+        const bool ok0 = k0 != WS_KEY_MAX && !(lane > 0 && up0 == k0) && !(p0 < n && (f0 >> 1) == (k0 >> 1));
+        const bool ok1 = k1 != WS_KEY_MAX && up1 != k1 && !(p1 < n && (f1 >> 1) == (k1 >> 1));
         const unsigned bka = __ballot_sync(0xffffffffu, ok0), bkb = __ballot_sync(0xffffffffu, ok1);
         const int ca = __popc(bka), mc2 = ca + __popc(bkb);
         if (mc2 == 0) { scan_from = pick + 1; continue; }
@@ -840,20 +882,20 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, 5) ws_beam_warp_kernel(
 #pragma unroll
         for (int r = 0; r < 4; r++) {
           const int i = lane + 32 * r;
-          np[r] = -1;
-          if (i >= first_new && i < n) {
-            e[r] = fr[i];
-            np[r] = i + ws_lb_shift1(sk2, mc2, e[r] >> 1);
-          }
+          const bool mv = i >= first_new && i < n;
+          e[r] = fr[min(i, (int)CAP - 1)];
+          const int c = ws_lb_fixed<6>(sk2, mc2, e[r] >> 1);
+          np[r] = mv ? i + c : B;
         }
+        const int j1 = lane + 32;
+        const uint64_t c0 = sk2[lane], c1 = sk2[j1];
+        const int q0 = lane < mc2 ? cpos[lane] + lane : B, q1 = j1 < mc2 ? cpos[j1] + j1 : B;
         __syncwarp();
 #pragma unroll
         for (int r = 0; r < 4; r++)
-          if (np[r] >= 0 && np[r] < B) fr[np[r]] = e[r];
-        for (int j = lane; j < mc2; j += 32) {
-          const int pos = cpos[j] + j;
-          if (pos < B) fr[pos] = sk2[j];
-        }
+          if (np[r] < B) fr[np[r]] = e[r];
+        if (q0 < B) fr[q0] = c0;
+        if (q1 < B) fr[q1] = c1;
         n = min(n + mc2, B);
         scan_from = min(pick + 1, first_new);
         __syncwarp();
