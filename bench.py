@@ -481,6 +481,7 @@ def cpu_baseline(args, cfg, data, queries, labels, windows, gts, table, ops):
     ref = load_ref()
     if ref is None:
         return {"value": None, "unit": "queries/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+    assert not hasattr(ref, "__engine__"), "the reference module resolved to this engine"
     cores = int(os.environ.get("PARLAY_NUM_THREADS", os.cpu_count()))
     tree, pre = ref_indices(ref, cfg, cache_dir(args.config), data, labels)
     total_q, total_t, detail = 0, 0.0, {}
@@ -489,9 +490,9 @@ def cpu_baseline(args, cfg, data, queries, labels, windows, gts, table, ops):
         best = None
         for method, v in table[p].items():
             ns = min(args.cpu_sample, cfg["nq"])
-            t_probe, _ = ref_time(ref, tree, pre, queries, windows[p], v["op"], min(32, ns))
-            per_q = t_probe / min(32, ns)
-            ns = int(max(32, min(ns, args.cpu_budget_s / len(POWERS) / 3 / max(per_q, 1e-7))))
+            t_probe, _ = ref_time(ref, tree, pre, queries, windows[p], v["op"], min(64, ns))
+            per_q = t_probe / min(64, ns)
+            ns = int(max(64, min(ns, args.cpu_budget_s / len(POWERS) / 3 / max(per_q, 1e-7))))
             t, ids = ref_time(ref, tree, pre, queries, windows[p], v["op"], ns)
             r = recall_at_k(ids, gts[p][:ns])
             if r >= RECALL_TARGET - 0.02 and (best is None or t / ns < best[0]):  # sample recall is noisier
@@ -524,7 +525,7 @@ def run_reference(args, rank, world):
     ns = args.ref_sample
     gts = {p: synth.ground_truth(data, queries[:ns], labels, windows[p][:ns]) for p in POWERS}
     # operating points: smallest beam reaching the recall target per method (CPU sweep on the sample)
-    ops = {}
+    ops, est_qps = {}, {}
     for p in POWERS:
         cands = [("prefilter", 0, 0)]
         for method in ("fenwick", "optimized_postfilter"):
@@ -535,30 +536,42 @@ def run_reference(args, rank, world):
                     break
         timed = [(ref_time(ref, tree, pre, queries, windows[p], op, ns)[0], op) for op in cands]
         ops[p] = min(timed)[1]
+        est_qps[p] = ns / min(timed)[0]
         log(f"reference 2^{p}: " + ", ".join(f"{op[0]} b{op[1]} {ns / t:.0f} qps" for t, op in timed))
 
+    # per-fraction batch sizes: large enough for parlay's fork-join to amortise on the fast
+    # fractions, bounded (~0.25 s) on the slow ones
+    ns_p = {p: int(min(cfg["nq"], max(ns, 0.25 * est_qps[p]))) for p in POWERS}
+
     def step():
+        per_q = 0.0
         for p in POWERS:
-            ref_time(ref, tree, pre, queries, windows[p], ops[p], ns)
+            t, _ = ref_time(ref, tree, pre, queries, windows[p], ops[p], ns_p[p])
+            per_q += t / ns_p[p]
+        return per_q
 
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
+    per_q_sum = 0.0
     for _ in range(args.steps):
-        step()
+        per_q_sum += step()
     dt = time.perf_counter() - t0
-    value = args.steps * ns * len(POWERS) / dt
+    # same definition as the engine arm: equal number of queries from every fraction
+    value = len(POWERS) / (per_q_sum / args.steps)
     cores = int(os.environ.get("PARLAY_NUM_THREADS", os.cpu_count()))
     line = {"impl": "reference", "metric": "QPS at recall@10>=0.95, one pass over filter fractions 2^-16..2^0",
             "value": round(value, 1), "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(dt / args.steps * 1000.0, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{cfg['name']} (same data, windows, graphs as the engine arm); each step = {ns} "
-                                   f"queries per fraction x 17 fractions", "name": args.config},
+            "config": {"workload": f"{cfg['name']} (same data, windows, graphs as the engine arm); each step = one "
+                                   f"batch per fraction x 17 fractions, batch = 0.25 s of work bounded to "
+                                   f"[{ns}, {cfg['nq']}] queries; value = 17 / sum of per-query times", "name": args.config},
             "cpu_baseline": {"value": round(value, 1), "unit": "queries/s", "cores": cores, "kind": "reference",
-                             "sample": f"{ns} queries per fraction per step"},
+                             "sample": "per fraction: " + ", ".join(f"2^{p}:{ns_p[p]}" for p in POWERS)},
             "e2e": {"value": round(value, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "per_fraction": {f"2^{p}": {"method": ops[p][0], "beam": ops[p][1]} for p in POWERS}}
+            "per_fraction": {f"2^{p}": {"method": ops[p][0], "beam": ops[p][1], "qps_estimate": round(est_qps[p])}
+                             for p in POWERS}}
     print(json.dumps(line), flush=True)
 
 
@@ -570,7 +583,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--config", default=os.environ.get("WSANN_BENCH_CONFIG", "auto"))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--cpu-sample", type=int, default=1000)
+    ap.add_argument("--cpu-sample", type=int, default=5000)
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     ap.add_argument("--ref-sample", type=int, default=200)
     ap.add_argument("--ops-file", default=None, help="save / reuse the swept operating points (profiling runs)")

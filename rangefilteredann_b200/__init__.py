@@ -23,7 +23,7 @@ _ENGINE = None
 
 def _ext_path() -> str | None:
     for f in sorted(os.listdir(_HERE)):
-        if f.startswith("window_ann") and f.endswith(".so"):
+        if f.startswith("_window_ann_b200") and f.endswith(".so"):
             return os.path.join(_HERE, f)
     return None
 
@@ -38,11 +38,12 @@ def load_engine():
     lib = os.path.join(_HERE, "libwsann_cuda.so")
     if path is None or not os.path.exists(lib):
         raise ImportError(
-            "rangefilteredann_b200: native extension missing (libwsann_cuda.so / window_ann*.so). "
+            "rangefilteredann_b200: native extension missing (libwsann_cuda.so / _window_ann_b200*.so). "
             "Run `python -m rangefilteredann_b200.build` (needs nvcc); there is no CPU fallback.")
-    spec = importlib.util.spec_from_file_location("window_ann", path)
+    # its own extension name: it must be able to coexist with the reference's `window_ann`
+    # extension in one interpreter (tests and bench load both)
+    spec = importlib.util.spec_from_file_location("_window_ann_b200", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    sys.modules.pop("window_ann", None)
     _ENGINE = mod
     return mod

@@ -1,7 +1,8 @@
 """Builds the two native artefacts of the package, in-tree:
 
   libwsann_cuda.so                 nvcc, sm_100a only  (csrc/wsann.cu: kernels + C ABI)
-  window_ann.cpython-*.so          g++ + pybind11      (csrc/host/python_bindings.cpp)
+  _window_ann_b200.cpython-*.so    g++ + pybind11      (csrc/host/python_bindings.cpp; re-exported as
+                                   `window_ann` by window_ann.py)
 
 Both land next to this file so they travel with the repo snapshot.  nvcc cross-compiles
 without a GPU.
@@ -16,7 +17,7 @@ import sysconfig
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwsann_cuda.so")
-EXT = os.path.join(HERE, "window_ann" + sysconfig.get_config_var("EXT_SUFFIX"))
+EXT = os.path.join(HERE, "_window_ann_b200" + sysconfig.get_config_var("EXT_SUFFIX"))
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -42,7 +43,8 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     if not force and _newer(LIB, srcs):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, os.path.join(CSRC, "wsann.cu")]
+    cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("WSANN_NVCC_EXTRA", "").split(), "-o", os.environ.get("WSANN_LIB_OUT", LIB),
+           os.path.join(CSRC, "wsann.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True)

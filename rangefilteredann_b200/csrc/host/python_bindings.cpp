@@ -136,7 +136,10 @@ static void add_variant(py::module_& m, const std::string& sfx) {
 
 }
 
-PYBIND11_MODULE(window_ann, m) {
+// The extension itself is named _window_ann_b200 so that it can live in one interpreter next to
+// the reference's `window_ann` extension (CPython caches extension modules by name); the
+// drop-in name is provided by rangefilteredann_b200/window_ann.py, which re-exports it.
+PYBIND11_MODULE(_window_ann_b200, m) {
   m.doc() = "WindowANN Python bindings — B200-native window-search engine (drop-in for the reference module)";
   m.attr("__version__") = "b200-dev";
   m.attr("__engine__") = "wsann_cuda";

@@ -599,6 +599,9 @@ __global__ void ws_fill_kernel(uint4* p, size_t n16) {
 // memory), which is what hides the two dependent HBM latencies of every expansion.
 // ------------------------------------------------------------------------------------------
 #define WS_WARPS_PER_CTA 4
+#ifndef WS_WARP_MINBLOCKS
+#define WS_WARP_MINBLOCKS 5  // resident CTAs per SM the warp kernels are register-budgeted for
+#endif
 
 __device__ __forceinline__ bool ws_seen_warp(volatile int* table, uint32_t mask, int id) {
   // plain loads/stores: lanes of one warp may race on a slot, which can only lose an
@@ -722,7 +725,7 @@ __host__ __device__ inline size_t ws_warp_smem_bytes(uint32_t cap, uint32_t hash
 }
 
 template <int KQ, int METRIC, bool EXACT>
-__global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, 5) ws_beam_warp_kernel(WsBeamArgs A) {
+__global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_WARP_MINBLOCKS) ws_beam_warp_kernel(WsBeamArgs A) {
   extern __shared__ __align__(16) unsigned char ws_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tl = lane & (WS_TEAM - 1), team = lane / WS_TEAM;  // 4 teams per warp
@@ -752,13 +755,19 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, 5) ws_beam_warp_kernel(
     float4 q[KQ];
     {
       const float* qrow = A.queries + (size_t)task.query * A.dim;
+      if (EXACT && A.dim == A.dpad) {  // rows of the query batch are 16-byte aligned and unpadded
+        const float4* q4 = reinterpret_cast<const float4*>(qrow) + tl;
 #pragma unroll
-      for (int i = 0; i < KQ; i++) {
-        const int c = (tl + WS_TEAM * i) * 4;
-        q[i].x = (c + 0 < (int)A.dim) ? __ldg(qrow + c + 0) : 0.f;
-        q[i].y = (c + 1 < (int)A.dim) ? __ldg(qrow + c + 1) : 0.f;
-        q[i].z = (c + 2 < (int)A.dim) ? __ldg(qrow + c + 2) : 0.f;
-        q[i].w = (c + 3 < (int)A.dim) ? __ldg(qrow + c + 3) : 0.f;
+        for (int i = 0; i < KQ; i++) q[i] = __ldg(q4 + WS_TEAM * i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < KQ; i++) {
+          const int c = (tl + WS_TEAM * i) * 4;
+          q[i].x = (c + 0 < (int)A.dim) ? __ldg(qrow + c + 0) : 0.f;
+          q[i].y = (c + 1 < (int)A.dim) ? __ldg(qrow + c + 1) : 0.f;
+          q[i].z = (c + 2 < (int)A.dim) ? __ldg(qrow + c + 2) : 0.f;
+          q[i].w = (c + 3 < (int)A.dim) ? __ldg(qrow + c + 3) : 0.f;
+        }
       }
     }
     const float4* vbase_tl = reinterpret_cast<const float4*>(A.vecs + (size_t)node.start * A.dpad) + tl;
