@@ -55,6 +55,10 @@ def main():
         print(f"rep {r}: {ms:.3f} ms  {a.nq / ms * 1000:.0f} qps", flush=True)
     st = h.stats()
     print({k: v // a.reps for k, v in st.items()})
+    try:
+        print({k: round(v["ms"] / a.reps, 3) for k, v in h.kernel_times().items()})
+    except Exception:
+        pass
 
 
 if __name__ == "__main__":

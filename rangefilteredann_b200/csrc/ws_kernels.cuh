@@ -599,6 +599,9 @@ __global__ void ws_fill_kernel(uint4* p, size_t n16) {
 // memory), which is what hides the two dependent HBM latencies of every expansion.
 // ------------------------------------------------------------------------------------------
 #define WS_WARPS_PER_CTA 4
+#ifndef WS_BEAM_ROWS
+#define WS_BEAM_ROWS 2  // candidate rows each team of 8 lanes keeps in flight (x4 teams per warp)
+#endif
 #ifndef WS_WARP_MINBLOCKS
 #define WS_WARP_MINBLOCKS 5  // resident CTAs per SM the warp kernels are register-budgeted for
 #endif
@@ -841,18 +844,21 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_WARP_MINBLOCKS) ws_b
         // distances (4 teams x 2 rows in flight); keep those under the cutoff (beamSearch.h:135-145)
         const float cutoff = (n < B) ? (float)2147483647 : ws_unord((uint32_t)(fr[n - 1] >> 32));
         int s = 0;
-        for (int jb = 0; jb < m; jb += 8) {
-          const int ja = jb + team, jc = jb + 4 + team;
-          const int ida = cid[min(ja, m - 1)], idc = cid[min(jc, m - 1)];
-          const float da = ws_team_dist_nv<KQ, METRIC, EXACT>(vbase_tl + (size_t)ida * dpad4, q, tl, dpad4);
-          const float dc = ws_team_dist_nv<KQ, METRIC, EXACT>(vbase_tl + (size_t)idc * dpad4, q, tl, dpad4);
-          const bool pa = leader && ja < m && da < cutoff;
-          const bool pc = leader && jc < m && dc < cutoff;
-          const unsigned ba = __ballot_sync(0xffffffffu, pa), bc = __ballot_sync(0xffffffffu, pc);
-          if (pa) sk[s + __popc(ba & lt)] = ws_key(da, (uint32_t)ida << 1);
-          s += __popc(ba);
-          if (pc) sk[s + __popc(bc & lt)] = ws_key(dc, (uint32_t)idc << 1);
-          s += __popc(bc);
+        for (int jb = 0; jb < m; jb += 4 * WS_BEAM_ROWS) {
+          int idu[WS_BEAM_ROWS];
+          float du[WS_BEAM_ROWS];
+#pragma unroll
+          for (int u = 0; u < WS_BEAM_ROWS; u++) {
+            idu[u] = cid[min(jb + 4 * u + team, m - 1)];
+            du[u] = ws_team_dist_nv<KQ, METRIC, EXACT>(vbase_tl + (size_t)idu[u] * dpad4, q, tl, dpad4);
+          }
+#pragma unroll
+          for (int u = 0; u < WS_BEAM_ROWS; u++) {
+            const bool pu = leader && jb + 4 * u + team < m && du[u] < cutoff;
+            const unsigned bu = __ballot_sync(0xffffffffu, pu);
+            if (pu) sk[s + __popc(bu & lt)] = ws_key(du[u], (uint32_t)idu[u] << 1);
+            s += __popc(bu);
+          }
         }
         if (s == 0) { scan_from = pick + 1; continue; }
         __syncwarp();
@@ -947,5 +953,148 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_WARP_MINBLOCKS) ws_b
       A.q_out[pos] = slot;
       atomicAdd(A.stats + WS_ST_ESCALATED, 1ull);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1w: warp-per-task brute-force scan (k <= 128)
+//
+// Streams a contiguous slice with 16 rows (8 KB) in flight per warp and keeps the running
+// top-k in shared memory with the same machinery as the beam kernel: rows whose key is under
+// the current k-th key are ballot-compacted, sorted in registers and merged in place.
+// No CTA barriers; ~2.5 KB of shared memory per warp.
+// ------------------------------------------------------------------------------------------
+#ifndef WS_SCAN_MINBLOCKS
+#define WS_SCAN_MINBLOCKS 6
+#endif
+
+template <int STEPS>
+__device__ __forceinline__ int ws_lb_fixed_raw(const uint64_t* a, int n, uint64_t v) {
+  int lo = 0;
+#pragma unroll
+  for (int step = 1 << (STEPS - 1); step > 0; step >>= 1) {
+    const int mid = lo + step;
+    const uint64_t x = (mid <= n) ? a[mid - 1] : WS_KEY_MAX;
+    lo = (mid <= n && x < v) ? mid : lo;
+  }
+  if ((1 << STEPS) <= n) {
+    const uint64_t x = a[(1 << STEPS) - 1];
+    lo = (lo == (1 << STEPS) - 1 && x < v) ? (1 << STEPS) : lo;
+  }
+  return lo;
+}
+
+template <int KQ, int METRIC, bool EXACT>
+__global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_SCAN_MINBLOCKS) ws_scan_warp_kernel(WsScanArgs A) {
+  __shared__ uint64_t s_fr[WS_WARPS_PER_CTA][128];
+  __shared__ uint64_t s_sk[WS_WARPS_PER_CTA][64];
+  __shared__ uint64_t s_sk2[WS_WARPS_PER_CTA][64];
+  __shared__ int s_cpos[WS_WARPS_PER_CTA][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tl = lane & (WS_TEAM - 1), team = lane / WS_TEAM;
+  uint64_t* fr = s_fr[warp];
+  uint64_t* sk = s_sk[warp];
+  uint64_t* sk2 = s_sk2[warp];
+  int* cpos = s_cpos[warp];
+  const int dpad4 = A.dpad >> 2;
+  const int B = (int)A.k;
+  const unsigned lt = (1u << lane) - 1u;
+  const bool leader = tl == 0;
+
+  for (;;) {
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(A.q_head, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= *A.q_in_count) break;
+    const uint32_t slot = A.q_in[t];
+    const WsTask task = A.tasks[slot];
+    float4 q[KQ];
+    {
+      const float* qrow = A.queries + (size_t)task.query * A.dim;
+      if (EXACT && A.dim == A.dpad) {
+        const float4* q4 = reinterpret_cast<const float4*>(qrow) + tl;
+#pragma unroll
+        for (int i = 0; i < KQ; i++) q[i] = __ldg(q4 + WS_TEAM * i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < KQ; i++) {
+          const int c = (tl + WS_TEAM * i) * 4;
+          q[i].x = (c + 0 < (int)A.dim) ? __ldg(qrow + c + 0) : 0.f;
+          q[i].y = (c + 1 < (int)A.dim) ? __ldg(qrow + c + 1) : 0.f;
+          q[i].z = (c + 2 < (int)A.dim) ? __ldg(qrow + c + 2) : 0.f;
+          q[i].w = (c + 3 < (int)A.dim) ? __ldg(qrow + c + 3) : 0.f;
+        }
+      }
+    }
+    const float4* vtl = reinterpret_cast<const float4*>(A.vecs) + tl;
+    int n = 0, s = 0;
+    uint64_t cutoff = WS_KEY_MAX;  // k-th best key once the list is full
+    const uint32_t a = task.a, b = task.b;
+    for (uint32_t r0 = a; r0 < b; r0 += 16) {
+      uint32_t r[4];
+      float d[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        r[u] = r0 + 4 * u + team;
+        const uint32_t rc = r[u] < b ? r[u] : b - 1;
+        d[u] = ws_team_dist_nv<KQ, METRIC, EXACT>(vtl + (size_t)rc * dpad4, q, tl, dpad4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint64_t key = ws_key(d[u], r[u]);
+        const bool pass = leader && r[u] < b && key < cutoff;
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (pass) sk[s + __popc(bal & lt)] = key;
+        s += __popc(bal);
+      }
+      if (s <= 48 && r0 + 16 < b) continue;
+      if (s == 0) continue;
+      // ---- fold the survivors into the running top-k
+      __syncwarp();
+      uint64_t k0 = lane < s ? sk[lane] : WS_KEY_MAX, k1 = WS_KEY_MAX;
+      if (s > 32) {
+        k1 = lane + 32 < s ? sk[lane + 32] : WS_KEY_MAX;
+        ws_warp_sort64(k0, k1, lane);
+      } else {
+        ws_warp_sort32(k0, lane);
+      }
+      const int p0 = ws_lb_fixed_raw<7>(fr, n, k0), p1 = ws_lb_fixed_raw<7>(fr, n, k1);
+      const bool ok0 = k0 != WS_KEY_MAX, ok1 = k1 != WS_KEY_MAX;
+      const int mc2 = s;  // survivors are distinct rows: nothing to de-duplicate
+      if (ok0) { sk2[lane] = k0; cpos[lane] = p0; }
+      if (ok1) { sk2[lane + 32] = k1; cpos[lane + 32] = p1; }
+      __syncwarp();
+      const int first_new = cpos[0];
+      uint64_t e[4];
+      int np[4];
+#pragma unroll
+      for (int rr = 0; rr < 4; rr++) {
+        const int i = lane + 32 * rr;
+        const bool mv = i >= first_new && i < n;
+        e[rr] = fr[i];
+        const int c = ws_lb_fixed_raw<6>(sk2, mc2, e[rr]);
+        np[rr] = mv ? i + c : B;
+      }
+      const int j1 = lane + 32;
+      const uint64_t c0 = sk2[lane], c1 = sk2[j1];
+      const int q0 = lane < mc2 ? cpos[lane] + lane : B, q1 = j1 < mc2 ? cpos[j1] + j1 : B;
+      __syncwarp();
+#pragma unroll
+      for (int rr = 0; rr < 4; rr++)
+        if (np[rr] < B) fr[np[rr]] = e[rr];
+      if (q0 < B) fr[q0] = c0;
+      if (q1 < B) fr[q1] = c1;
+      n = min(n + mc2, B);
+      s = 0;
+      __syncwarp();
+      cutoff = (n == B) ? fr[B - 1] : WS_KEY_MAX;
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) A.res_keys[(size_t)slot * B + i] = fr[i];
+    if (lane == 0) {
+      A.res_cnt[slot] = (uint32_t)n;
+      atomicAdd(A.stats + WS_ST_SCANPTS, (unsigned long long)(b - a));
+    }
+    __syncwarp();
   }
 }

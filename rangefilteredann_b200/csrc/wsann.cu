@@ -114,7 +114,8 @@ struct ws_index {
   int64_t opt_scan_chunk = 8192;
   int64_t opt_hash_factor = 32;
   int64_t opt_warp_tiers = 1;    // use the warp-per-task kernels for beams <= 128
-  int64_t opt_warp_hash = 2048;  // visited-table entries per warp in those kernels
+  int64_t opt_warp_hash = 2048;
+  int64_t opt_warp_scan = 1;     // warp-per-task scan kernel for k <= 128  // visited-table entries per warp in those kernels
   int64_t opt_build_expand = 1;  // nodes expanded per step while BUILDING graphs
   uint64_t build_stats[4] = {0, 0, 0, 0};  // inserts, visited, dist_cmps, overflow re-prunes  // smem visited-table entries per unit of beam capacity
 
@@ -557,6 +558,18 @@ static cudaError_t ws_launch_scan_t(int grid, size_t smem, cudaStream_t s, const
   return cudaGetLastError();
 }
 
+template <int KQ, int METRIC>
+static cudaError_t ws_launch_scan_warp_t(bool exact, int grid, cudaStream_t s, const WsScanArgs& a) {
+  if (exact) ws_scan_warp_kernel<KQ, METRIC, true><<<grid, WS_WARPS_PER_CTA * 32, 0, s>>>(a);
+  else ws_scan_warp_kernel<KQ, METRIC, false><<<grid, WS_WARPS_PER_CTA * 32, 0, s>>>(a);
+  return cudaGetLastError();
+}
+template <int KQ, int METRIC>
+static cudaError_t ws_scan_warp_occupancy_t(bool exact, int* blocks) {
+  if (exact) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_scan_warp_kernel<KQ, METRIC, true>, WS_WARPS_PER_CTA * 32, 0);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_scan_warp_kernel<KQ, METRIC, false>, WS_WARPS_PER_CTA * 32, 0);
+}
+
 #define WS_DISPATCH_KQ(KQV, METRICV, CALL)                                    \
   do {                                                                        \
     if ((METRICV) == 0) {                                                     \
@@ -765,14 +778,29 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
     sa.k = k;
     sa.q_in = queues + (size_t)WS_NUM_TIERS * slots; sa.q_in_count = ctrl + WS_NUM_TIERS; sa.q_head = ctrl + 8 + WS_NUM_TIERS;
     sa.stats = idx->d_stats;
-    size_t smem = (size_t)WS_TOPK_BUF * 8 + (size_t)idx->dpad * 4;
-    int grid = idx->num_sms * 8;
+    if (k <= 128 && idx->opt_warp_scan) {  // warp-per-task streaming scan
+      int occ = 0;
+#define WS_OCS(KQ_, M_) { cudaError_t _e = ws_scan_warp_occupancy_t<KQ_, M_>(exact_rows, &occ); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(_e)); }
+      WS_DISPATCH_KQ(kq, idx->metric, WS_OCS);
+#undef WS_OCS
+      if (occ < 1) return ws_fail(WS_ERR_CUDA, "scan kernel does not fit on an SM");
+      int grid = idx->num_sms * occ;
+#define WS_LSW(KQ_, M_) { cudaError_t _e = ws_launch_scan_warp_t<KQ_, M_>(exact_rows, grid, st, sa); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "scan kernel launch: %s", cudaGetErrorString(_e)); }
+      {
+        WsKernelScope ks(idx, 6);
+        WS_DISPATCH_KQ(kq, idx->metric, WS_LSW);
+      }
+#undef WS_LSW
+    } else {
+      size_t smem = (size_t)WS_TOPK_BUF * 8 + (size_t)idx->dpad * 4;
+      int grid = idx->num_sms * 8;
 #define WS_LS(KQ_, M_) { cudaError_t _e = ws_launch_scan_t<KQ_, M_>(grid, smem, st, sa); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "scan kernel launch: %s", cudaGetErrorString(_e)); }
-    {
-      WsKernelScope ks(idx, 6);
-      WS_DISPATCH_KQ(kq, idx->metric, WS_LS);
-    }
+      {
+        WsKernelScope ks(idx, 6);
+        WS_DISPATCH_KQ(kq, idx->metric, WS_LS);
+      }
 #undef WS_LS
+    }
   }
 
   // ---- K4 merge + decode
@@ -1213,6 +1241,8 @@ int ws_index_set_option(ws_index* idx, const char* name, int64_t value) {
     idx->opt_scan_chunk = value;
   } else if (s == "warp_tiers") {
     idx->opt_warp_tiers = value != 0;
+  } else if (s == "warp_scan") {
+    idx->opt_warp_scan = value != 0;
   } else if (s == "warp_hash") {
     if (value < 256 || value > 16384 || (value & (value - 1))) return ws_fail(WS_ERR_BADARG, "warp_hash must be a power of two in 256..16384");
     idx->opt_warp_hash = value;

@@ -110,7 +110,7 @@ def test_beam_tiers(tiny, beam, mult, max_beam):
         tiny.assert_identical(method, q, w, beam=beam, mult=mult, max_beam=max_beam)
 
 
-@pytest.mark.parametrize("k", [1, 3, 10, 37, 100])
+@pytest.mark.parametrize("k", [1, 3, 10, 37, 100, 150])
 def test_k_sweep(tiny, k):
     w = synth.make_windows(tiny.labels, -2, 16, seed=k)
     q = tiny.queries[:16]
@@ -187,6 +187,16 @@ def test_cta_tiers_match_warp_tiers(tiny):
                 tiny.assert_identical(method, q, w, beam=beam, mult=mult)
     finally:
         h.set_option("warp_tiers", 1)
+    try:
+        h.set_option("warp_scan", 0)  # CTA-per-task scan kernel instead of the warp-per-task one
+        for method in ("fenwick", "three_split"):
+            tiny.assert_identical(method, q, w, beam=10, mult=1)
+        hp = capi.Handle.borrow(tiny.eng["prefilter"])
+        hp.set_option("warp_scan", 0)
+        tiny.assert_identical("prefilter", q, w)
+        hp.set_option("warp_scan", 1)
+    finally:
+        h.set_option("warp_scan", 1)
     try:
         h.set_option("warp_hash", 256)  # a saturated visited table may only cost recomputation
         tiny.assert_identical("optimized_postfilter", q, w, beam=60, mult=2)
