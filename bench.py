@@ -256,7 +256,10 @@ def choose_operating_points(runner: EngineRunner, gts, rank):
                         ms = runner.time_dev(p, op)
                         if best is None or ms < best["ms"]:
                             best = dict(op=op, recall=r, ms=ms)
-                        break
+                        # fenwick gets slower with the beam; optimized postfilter need not (a
+                        # larger start beam can save doubling rounds), so keep looking there
+                        if method == "fenwick" or (best is not None and ms > 2.0 * best["ms"]):
+                            break
             if best is not None:
                 per_method[method] = best
         table[p] = per_method

@@ -30,6 +30,7 @@
 #define WS_TF_MULT1 1u     // final_beam_multiply forced to 1 (three_split centre buckets, range_filter_tree.h:490-498)
 #define WS_TF_FINAL 2u     // (resumed task) the pending search is the final-multiply search
 #define WS_TF_RESUMED 4u   // task was escalated from a smaller beam tier
+#define WS_TF_SOLO 8u      // the query's only task: the search kernel writes the final ids/dists itself
 
 struct WsTask {            // 32 bytes
   uint32_t query;          // index into the batch

@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(128) ws_decompose_kernel(WsDecompArgs A) {
     case WS_MODE_POSTFILTER: em.graph(A.node, lo, hi, 0); break;
   }
   A.counts[q] = em.count;
+  if (em.count == 1) em.slots[0].flags |= WS_TF_SOLO;  // no merge needed: K1/K2 write the result rows
   if (em.overflow) atomicExch(A.overflow, 1u);
   uint32_t ng = 0, ns = 0;
   for (uint32_t i = 0; i < em.count; i++) (em.slots[i].node >= 0) ? ng++ : ns++;
@@ -107,6 +108,11 @@ struct WsBeamArgs {
   uint32_t* bitmap;        // GLOBAL_SEEN: [gridDim.x][bitmap_words]
   uint64_t bitmap_words;
   unsigned long long* stats;
+  // final result rows (written directly for WS_TF_SOLO tasks; K4 handles the rest)
+  uint32_t* out_ids;
+  float* out_dists;
+  const uint32_t* decode;
+  uint32_t pad_id;
 };
 
 __device__ __forceinline__ int ws_lb_shift1(const uint64_t* a, int n, uint64_t v) {
@@ -131,6 +137,18 @@ __device__ __forceinline__ int ws_cta_rank(bool flag, int* s_wc, int lane, int w
   for (int w = 0; w < WS_CTA_THREADS / 32; w++) pre += (w < warp) ? s_wc[w] : 0;
   *total = s_wc[0] + s_wc[1] + s_wc[2] + s_wc[3];
   return pre + __popc(bal & ((1u << lane) - 1u));
+}
+
+// final result slot j of query q (range_filter_tree.h:84-92 / postfilter_vamana.h:207-215)
+__device__ __forceinline__ void ws_write_result(uint32_t* ids, float* dists, const uint32_t* decode, size_t q, int K,
+                                                int j, uint64_t key) {
+  const uint32_t rank = (uint32_t)(key & 0xFFFFFFFFull);
+  ids[q * K + j] = decode ? decode[rank] : rank;
+  dists[q * K + j] = ws_unord((uint32_t)(key >> 32));
+}
+__device__ __forceinline__ void ws_write_pad(uint32_t* ids, float* dists, uint32_t pad_id, size_t q, int K, int j) {
+  ids[q * K + j] = pad_id;
+  dists[q * K + j] = 3.402823466e+38f;
 }
 
 // Shared-memory working set of one beam search (pointers into the CTA's dynamic smem)
@@ -403,7 +421,11 @@ __global__ void __launch_bounds__(WS_CTA_THREADS) ws_beam_kernel(WsBeamArgs A) {
         int tot;
         int prev = s_have;
         int r = prev + ws_cta_rank(in, s_wc, lane, warp, &tot);
-        if (in && r < K) A.res_keys[(size_t)slot * K + r] = (key & 0xFFFFFFFF00000000ull) | rank;
+        if (in && r < K) {
+          const uint64_t okey = (key & 0xFFFFFFFF00000000ull) | rank;
+          A.res_keys[(size_t)slot * K + r] = okey;
+          if (task.flags & WS_TF_SOLO) ws_write_result(A.out_ids, A.out_dists, A.decode, task.query, K, r, okey);
+        }
         __syncthreads();
         if (tid == 0) s_have = prev + tot;
         __syncthreads();
@@ -421,6 +443,8 @@ __global__ void __launch_bounds__(WS_CTA_THREADS) ws_beam_kernel(WsBeamArgs A) {
       if (have < K) beam *= 2;
     }
 
+    if (!escalate && (task.flags & WS_TF_SOLO))
+      for (int j = min(have, K) + tid; j < K; j += WS_CTA_THREADS) ws_write_pad(A.out_ids, A.out_dists, A.pad_id, task.query, K, j);
     if (escalate && tid == 0) {
       if (A.q_out != nullptr) {
         A.tasks[slot].beam = (uint32_t)beam;
@@ -449,6 +473,10 @@ struct WsScanArgs {
   const uint32_t* q_in_count;
   uint32_t* q_head;
   unsigned long long* stats;
+  uint32_t* out_ids;
+  float* out_dists;
+  const uint32_t* decode;
+  uint32_t pad_id;
 };
 
 #define WS_SCAN_UNROLL 2
@@ -513,6 +541,11 @@ __global__ void __launch_bounds__(WS_CTA_THREADS) ws_scan_kernel(WsScanArgs A) {
     ws_topk_compact(tk, K, tid);
     const int nb = s_nbest;
     for (int i = tid; i < nb; i += WS_CTA_THREADS) A.res_keys[(size_t)slot * K + i] = buf[i];
+    if (task.flags & WS_TF_SOLO)
+      for (int j = tid; j < K; j += WS_CTA_THREADS) {
+        if (j < nb) ws_write_result(A.out_ids, A.out_dists, A.decode, task.query, K, j, buf[j]);
+        else ws_write_pad(A.out_ids, A.out_dists, A.pad_id, task.query, K, j);
+      }
     if (tid == 0) {
       A.res_cnt[slot] = (uint32_t)nb;
       atomicAdd(A.stats + WS_ST_SCANPTS, (unsigned long long)(task.b - task.a));
@@ -550,6 +583,7 @@ __global__ void __launch_bounds__(WS_CTA_THREADS) ws_merge_kernel(WsMergeArgs A)
     ws_topk_init(tk, tid);
     __syncthreads();
     const uint32_t nt = A.counts[q];
+    if (nt == 1) continue;  // WS_TF_SOLO: the search kernel already wrote this row
     int appended = 0;
     int nbest = 0;
     for (uint32_t t = 0; t < nt; t++) {
@@ -931,7 +965,11 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_WARP_MINBLOCKS) ws_b
         }
         const unsigned bal = __ballot_sync(0xffffffffu, in);
         const int r = have + __popc(bal & lt);
-        if (in && r < K) A.res_keys[(size_t)slot * K + r] = (key & 0xFFFFFFFF00000000ull) | rank;
+        if (in && r < K) {
+          const uint64_t okey = (key & 0xFFFFFFFF00000000ull) | rank;
+          A.res_keys[(size_t)slot * K + r] = okey;
+          if (task.flags & WS_TF_SOLO) ws_write_result(A.out_ids, A.out_dists, A.decode, task.query, K, r, okey);
+        }
         have += __popc(bal);
       }
       if (lane == 0) {
@@ -946,6 +984,8 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_WARP_MINBLOCKS) ws_b
       if (have < K) beam *= 2;
     }
 
+    if (!escalate && (task.flags & WS_TF_SOLO))
+      for (int j = min(have, K) + lane; j < K; j += 32) ws_write_pad(A.out_ids, A.out_dists, A.pad_id, task.query, K, j);
     if (escalate && lane == 0 && A.q_out != nullptr) {
       A.tasks[slot].beam = (uint32_t)beam;
       A.tasks[slot].flags = task.flags | WS_TF_RESUMED | (phase ? WS_TF_FINAL : 0u);
@@ -1091,6 +1131,11 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_SCAN_MINBLOCKS) ws_s
     }
     __syncwarp();
     for (int i = lane; i < n; i += 32) A.res_keys[(size_t)slot * B + i] = fr[i];
+    if (task.flags & WS_TF_SOLO)
+      for (int j = lane; j < B; j += 32) {
+        if (j < n) ws_write_result(A.out_ids, A.out_dists, A.decode, task.query, B, j, fr[j]);
+        else ws_write_pad(A.out_ids, A.out_dists, A.pad_id, task.query, B, j);
+      }
     if (lane == 0) {
       A.res_cnt[slot] = (uint32_t)n;
       atomicAdd(A.stats + WS_ST_SCANPTS, (unsigned long long)(b - a));

@@ -761,6 +761,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
         ba.bitmap = (uint32_t*)idx->bitmap.p;
       }
       ba.stats = idx->d_stats;
+      ba.out_ids = dids; ba.out_dists = ddists; ba.decode = plan.use_decode ? idx->d_decode : nullptr; ba.pad_id = plan.pad_id;
 #define WS_LB(KQ_, M_) { cudaError_t _e = warp_tier ? ws_launch_beam_warp_t<KQ_, M_>(exact_rows, grid, smem, st, ba) : ws_launch_beam_t<KQ_, M_>(large, grid, smem, st, ba); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "beam kernel launch (tier %d): %s", t, cudaGetErrorString(_e)); }
       {
         WsKernelScope ks(idx, 1 + t);
@@ -778,6 +779,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
     sa.k = k;
     sa.q_in = queues + (size_t)WS_NUM_TIERS * slots; sa.q_in_count = ctrl + WS_NUM_TIERS; sa.q_head = ctrl + 8 + WS_NUM_TIERS;
     sa.stats = idx->d_stats;
+    sa.out_ids = dids; sa.out_dists = ddists; sa.decode = plan.use_decode ? idx->d_decode : nullptr; sa.pad_id = plan.pad_id;
     if (k <= 128 && idx->opt_warp_scan) {  // warp-per-task streaming scan
       int occ = 0;
 #define WS_OCS(KQ_, M_) { cudaError_t _e = ws_scan_warp_occupancy_t<KQ_, M_>(exact_rows, &occ); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(_e)); }
