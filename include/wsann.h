@@ -197,8 +197,8 @@ int ws_index_set_option(ws_index* idx, const char* name, int64_t value);
 int ws_index_hbm_bytes(const ws_index* idx, uint64_t* out);
 /* With option "profile_kernels" = 1 every kernel launch is bracketed by CUDA events on the
  * index stream.  Returns accumulated milliseconds / launch counts per kernel kind:
- * 0 decompose, 1..2 beam search warp-per-task tiers (beam <= 64 / 128), 3..4 beam search
- * CTA-per-task tiers (256 / 1024), 5 beam search large tier, 6 scan, 7 merge.
+ * 0 decompose, 1..3 beam search warp-per-task tiers (beam <= 64 / 128 / 256), 4 beam search
+ * CTA-per-task tier (1024), 5 beam search large tier, 6 scan, 7 merge.
  * ms_out / launches_out are [8]. */
 int ws_index_kernel_times(ws_index* idx, double* ms_out, uint64_t* launches_out, int reset);
 

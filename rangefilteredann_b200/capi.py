@@ -155,7 +155,7 @@ class Handle:
     def set_option(self, name: str, value: int):
         check(lib().ws_index_set_option(self.raw, name.encode(), int(value)), "ws_index_set_option")
 
-    KERNEL_KINDS = ("decompose", "beam_warp64", "beam_warp128", "beam256", "beam1024", "beam_large", "scan", "merge")
+    KERNEL_KINDS = ("decompose", "beam_warp64", "beam_warp128", "beam_warp256", "beam1024", "beam_large", "scan", "merge")
 
     def kernel_times(self, reset=True) -> dict:
         ms = np.zeros(8, np.float64)

@@ -636,6 +636,9 @@ __global__ void ws_fill_kernel(uint4* p, size_t n16) {
 #ifndef WS_BEAM_ROWS
 #define WS_BEAM_ROWS 2  // candidate rows each team of 8 lanes keeps in flight (x4 teams per warp)
 #endif
+#ifndef WS_BEAM_PREFETCH
+#define WS_BEAM_PREFETCH 1  // L2-prefetch the candidate rows that do not fit the first register batch
+#endif
 #ifndef WS_WARP_MINBLOCKS
 #define WS_WARP_MINBLOCKS 5  // resident CTAs per SM the warp kernels are register-budgeted for
 #endif
@@ -761,8 +764,9 @@ __host__ __device__ inline size_t ws_warp_smem_bytes(uint32_t cap, uint32_t hash
   return (size_t)cap * 8 + 64 * 8 * 2 + 64 * 4 * 2 + (size_t)hash_entries * 4;
 }
 
-template <int KQ, int METRIC, bool EXACT>
-__global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_WARP_MINBLOCKS) ws_beam_warp_kernel(WsBeamArgs A) {
+// CS = log2 of the largest beam the instantiation can hold (7 -> 128, 8 -> 256)
+template <int KQ, int METRIC, bool EXACT, int CS>
+__global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, (CS <= 7 ? WS_WARP_MINBLOCKS : 2)) ws_beam_warp_kernel(WsBeamArgs A) {
   extern __shared__ __align__(16) unsigned char ws_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tl = lane & (WS_TEAM - 1), team = lane / WS_TEAM;  // 4 teams per warp
@@ -875,6 +879,17 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_WARP_MINBLOCKS) ws_b
         __syncwarp();
         ncmp += (unsigned long long)m;
 
+        // Only 4*WS_BEAM_ROWS candidate rows fit in registers at a time; pull the later ones
+        // towards L2 now so that their loads find them there (4 x 128 B lines per 512 B row,
+        // one line per lane; costs no registers and no extra DRAM traffic).
+        if (WS_BEAM_PREFETCH) {
+          const int lines = ((int)A.dpad * 4 + 127) >> 7;  // 128 B lines per row
+          for (int j = 4 * WS_BEAM_ROWS + (lane >> 2); j < m; j += 8) {
+            const char* rowp = reinterpret_cast<const char*>(vbase_tl - tl + (size_t)cid[j] * dpad4);
+            for (int l = lane & 3; l < lines; l += 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + 128 * l));
+          }
+        }
+
         // distances (4 teams x 2 rows in flight); keep those under the cutoff (beamSearch.h:135-145)
         const float cutoff = (n < B) ? (float)2147483647 : ws_unord((uint32_t)(fr[n - 1] >> 32));
         int s = 0;
@@ -890,7 +905,14 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_WARP_MINBLOCKS) ws_b
           for (int u = 0; u < WS_BEAM_ROWS; u++) {
             const bool pu = leader && jb + 4 * u + team < m && du[u] < cutoff;
             const unsigned bu = __ballot_sync(0xffffffffu, pu);
-            if (pu) sk[s + __popc(bu & lt)] = ws_key(du[u], (uint32_t)idu[u] << 1);
+            if (pu) {
+              sk[s + __popc(bu & lt)] = ws_key(du[u], (uint32_t)idu[u] << 1);
+              if (WS_BEAM_PREFETCH) {  // a candidate that enters the beam is likely to be expanded: warm its adjacency row
+                const char* ar = reinterpret_cast<const char*>(node.adj + (size_t)idu[u] * R);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ar));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ar + 128));
+              }
+            }
             s += __popc(bu);
           }
         }
@@ -912,7 +934,7 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_WARP_MINBLOCKS) ws_b
         uint64_t up1 = ws_shfl_up_u64(k1, 1);
         const uint64_t last0 = ws_shfl_idx_u64(k0, 31);
         up1 = lane == 0 ? last0 : up1;
-        const int p0 = ws_lb_fixed<7>(fr, n, k0 >> 1), p1 = ws_lb_fixed<7>(fr, n, k1 >> 1);
+        const int p0 = ws_lb_fixed<CS>(fr, n, k0 >> 1), p1 = ws_lb_fixed<CS>(fr, n, k1 >> 1);
         const uint64_t f0 = fr[min(p0, n - 1)], f1 = fr[min(p1, n - 1)];
         const bool ok0 = k0 != WS_KEY_MAX && !(lane > 0 && up0 == k0) && !(p0 < n && (f0 >> 1) == (k0 >> 1));
         const bool ok1 = k1 != WS_KEY_MAX && up1 != k1 && !(p1 < n && (f1 >> 1) == (k1 >> 1));
@@ -926,10 +948,11 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_WARP_MINBLOCKS) ws_b
         // merge in place, trim to the beam (beamSearch.h:151-172): entries before the first
         // insertion point stay where they are
         const int first_new = cpos[0];
-        uint64_t e[4];
-        int np[4];
+        constexpr int NE = (1 << CS) / 32;  // frontier entries per lane
+        uint64_t e[NE];
+        int np[NE];
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
+        for (int r = 0; r < NE; r++) {
           const int i = lane + 32 * r;
           const bool mv = i >= first_new && i < n;
           e[r] = fr[min(i, (int)CAP - 1)];
@@ -941,7 +964,7 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_WARP_MINBLOCKS) ws_b
         const int q0 = lane < mc2 ? cpos[lane] + lane : B, q1 = j1 < mc2 ? cpos[j1] + j1 : B;
         __syncwarp();
 #pragma unroll
-        for (int r = 0; r < 4; r++)
+        for (int r = 0; r < NE; r++)
           if (np[r] < B) fr[np[r]] = e[r];
         if (q0 < B) fr[q0] = c0;
         if (q1 < B) fr[q1] = c1;

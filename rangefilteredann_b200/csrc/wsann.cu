@@ -51,14 +51,15 @@ static int ws_fail(int code, const char* fmt, ...) {
 // ------------------------------------------------------------------------------------------
 // index object
 // ------------------------------------------------------------------------------------------
-// beam tiers: 0,1 = warp-per-task kernels (cap 64 / 128), 2,3 = CTA-per-task with a shared-memory
-// visited table (cap 256 / 1024), 4 = CTA-per-task with a global visited bitmap
+// beam tiers: 0,1,2 = warp-per-task kernels (cap 64 / 128 / 256), 3 = CTA-per-task with a
+// shared-memory visited table (cap 1024), 4 = CTA-per-task with a global visited bitmap
 static const uint32_t kBeamTierCaps[4] = {64, 128, 256, 1024};
+#define WS_NUM_WARP_TIERS 3
 #define WS_NUM_TIERS 5
 static const uint32_t kBeamCapLarge = 12288;                // global-bitmap tier
 static const uint32_t kMaxK = WS_TOPK_BUF / 2;
 static const size_t kAdjSlabBytes = 256ull << 20;
-#define WS_NUM_KERNEL_KINDS 8  // 0 decompose, 1-2 warp beam tiers 64/128, 3-4 CTA beam tiers 256/1024, 5 beam large, 6 scan, 7 merge
+#define WS_NUM_KERNEL_KINDS 8  // 0 decompose, 1-3 warp beam tiers 64/128/256, 4 CTA beam tier 1024, 5 beam large, 6 scan, 7 merge
 
 struct WsDevBuf {
   void* p = nullptr;
@@ -523,31 +524,28 @@ static cudaError_t ws_beam_occupancy_t(bool global_seen, size_t smem, int* block
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_beam_kernel<KQ, METRIC, false>, WS_CTA_THREADS, smem);
 }
 
-template <int KQ, int METRIC>
-static cudaError_t ws_launch_beam_warp_t(bool exact, int grid, size_t smem, cudaStream_t s, const WsBeamArgs& a) {
-  cudaError_t e;
-  if (exact) {
-    e = cudaFuncSetAttribute(ws_beam_warp_kernel<KQ, METRIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    ws_beam_warp_kernel<KQ, METRIC, true><<<grid, WS_WARPS_PER_CTA * 32, smem, s>>>(a);
-  } else {
-    e = cudaFuncSetAttribute(ws_beam_warp_kernel<KQ, METRIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    ws_beam_warp_kernel<KQ, METRIC, false><<<grid, WS_WARPS_PER_CTA * 32, smem, s>>>(a);
-  }
+template <int KQ, int METRIC, bool EXACT, int CS>
+static cudaError_t ws_launch_beam_warp_tt(int grid, size_t smem, cudaStream_t s, const WsBeamArgs& a) {
+  cudaError_t e = cudaFuncSetAttribute(ws_beam_warp_kernel<KQ, METRIC, EXACT, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  ws_beam_warp_kernel<KQ, METRIC, EXACT, CS><<<grid, WS_WARPS_PER_CTA * 32, smem, s>>>(a);
   return cudaGetLastError();
 }
 template <int KQ, int METRIC>
-static cudaError_t ws_beam_warp_occupancy_t(bool exact, size_t smem, int* blocks) {
-  cudaError_t e;
-  if (exact) {
-    e = cudaFuncSetAttribute(ws_beam_warp_kernel<KQ, METRIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_beam_warp_kernel<KQ, METRIC, true>, WS_WARPS_PER_CTA * 32, smem);
-  }
-  e = cudaFuncSetAttribute(ws_beam_warp_kernel<KQ, METRIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+static cudaError_t ws_launch_beam_warp_t(bool exact, bool wide, int grid, size_t smem, cudaStream_t s, const WsBeamArgs& a) {
+  if (exact) return wide ? ws_launch_beam_warp_tt<KQ, METRIC, true, 8>(grid, smem, s, a) : ws_launch_beam_warp_tt<KQ, METRIC, true, 7>(grid, smem, s, a);
+  return wide ? ws_launch_beam_warp_tt<KQ, METRIC, false, 8>(grid, smem, s, a) : ws_launch_beam_warp_tt<KQ, METRIC, false, 7>(grid, smem, s, a);
+}
+template <int KQ, int METRIC, bool EXACT, int CS>
+static cudaError_t ws_beam_warp_occupancy_tt(size_t smem, int* blocks) {
+  cudaError_t e = cudaFuncSetAttribute(ws_beam_warp_kernel<KQ, METRIC, EXACT, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_beam_warp_kernel<KQ, METRIC, false>, WS_WARPS_PER_CTA * 32, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_beam_warp_kernel<KQ, METRIC, EXACT, CS>, WS_WARPS_PER_CTA * 32, smem);
+}
+template <int KQ, int METRIC>
+static cudaError_t ws_beam_warp_occupancy_t(bool exact, bool wide, size_t smem, int* blocks) {
+  if (exact) return wide ? ws_beam_warp_occupancy_tt<KQ, METRIC, true, 8>(smem, blocks) : ws_beam_warp_occupancy_tt<KQ, METRIC, true, 7>(smem, blocks);
+  return wide ? ws_beam_warp_occupancy_tt<KQ, METRIC, false, 8>(smem, blocks) : ws_beam_warp_occupancy_tt<KQ, METRIC, false, 7>(smem, blocks);
 }
 
 template <int KQ, int METRIC>
@@ -676,7 +674,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
 
   // ---- tiers: which launch takes fresh graph tasks
   const int kq = ws_pick_kq(idx->dpad);
-  const int lowest_tier = (idx->R <= 64 && idx->opt_warp_tiers) ? 0 : 2;
+  const int lowest_tier = (idx->R <= 64 && idx->opt_warp_tiers) ? 0 : WS_NUM_WARP_TIERS;
   const bool exact_rows = (uint32_t)kq * WS_TEAM * 4 == idx->dpad;  // padded row = 8*KQ float4s: no column predicate
   int first_tier = WS_NUM_TIERS - 1;
   if (needs_graph) {
@@ -717,13 +715,14 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
     while (cand_cap < E * idx->R) cand_cap <<= 1;
     for (int t = first_tier; t < WS_NUM_TIERS; t++) {
       const bool large = (t == WS_NUM_TIERS - 1);
-      const bool warp_tier = t < 2;
+      const bool warp_tier = t < WS_NUM_WARP_TIERS;
+      const bool wide = t == 2;  // the 256-beam instantiation of the warp kernel
       const uint32_t beam_cap = large ? kBeamCapLarge : kBeamTierCaps[t];
       if (t > first_tier && (int64_t)kBeamTierCaps[t - 1] >= qp.postfiltering_max_beam)
         break;  // no task can need a beam this large
       uint32_t hash_entries = 0;
       if (warp_tier) {
-        hash_entries = (uint32_t)idx->opt_warp_hash;
+        hash_entries = (uint32_t)idx->opt_warp_hash * (wide ? 2 : 1);
       } else if (!large) {
         hash_entries = 1024;
         while (hash_entries < (uint64_t)idx->opt_hash_factor * beam_cap) hash_entries <<= 1;
@@ -735,7 +734,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
         smem = (size_t)2 * beam_cap * 8 + (size_t)cand_cap * 24 + (size_t)idx->dpad * 4 + (size_t)hash_entries * 4;
       if (smem > idx->smem_optin) return ws_fail(WS_ERR_BADARG, "beam tier %d needs %zu B of shared memory (> %zu)", t, smem, idx->smem_optin);
       int occ = 0;
-#define WS_OCC(KQ_, M_) { cudaError_t _e = warp_tier ? ws_beam_warp_occupancy_t<KQ_, M_>(exact_rows, smem, &occ) : ws_beam_occupancy_t<KQ_, M_>(large, smem, &occ); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(_e)); }
+#define WS_OCC(KQ_, M_) { cudaError_t _e = warp_tier ? ws_beam_warp_occupancy_t<KQ_, M_>(exact_rows, wide, smem, &occ) : ws_beam_occupancy_t<KQ_, M_>(large, smem, &occ); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(_e)); }
       WS_DISPATCH_KQ(kq, idx->metric, WS_OCC);
 #undef WS_OCC
       if (occ < 1) return ws_fail(WS_ERR_CUDA, "beam kernel does not fit on an SM (smem %zu)", smem);
@@ -762,7 +761,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
       }
       ba.stats = idx->d_stats;
       ba.out_ids = dids; ba.out_dists = ddists; ba.decode = plan.use_decode ? idx->d_decode : nullptr; ba.pad_id = plan.pad_id;
-#define WS_LB(KQ_, M_) { cudaError_t _e = warp_tier ? ws_launch_beam_warp_t<KQ_, M_>(exact_rows, grid, smem, st, ba) : ws_launch_beam_t<KQ_, M_>(large, grid, smem, st, ba); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "beam kernel launch (tier %d): %s", t, cudaGetErrorString(_e)); }
+#define WS_LB(KQ_, M_) { cudaError_t _e = warp_tier ? ws_launch_beam_warp_t<KQ_, M_>(exact_rows, wide, grid, smem, st, ba) : ws_launch_beam_t<KQ_, M_>(large, grid, smem, st, ba); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "beam kernel launch (tier %d): %s", t, cudaGetErrorString(_e)); }
       {
         WsKernelScope ks(idx, 1 + t);
         WS_DISPATCH_KQ(kq, idx->metric, WS_LB);

@@ -101,9 +101,10 @@ def test_mips_golden_and_oracle(tiny_mips, method):
 
 
 @pytest.mark.parametrize("beam,mult,max_beam", [(64, 1, 10000), (65, 1, 10000), (100, 4, 10000), (300, 2, 10000),
+                                                (200, 1, 10000), (120, 2, 10000), (256, 1, 10000),
                                                 (1100, 1, 10000), (10, 32, 10000), (700, 8, 4000), (10, 1, 12288)])
 def test_beam_tiers(tiny, beam, mult, max_beam):
-    """Every shared-memory tier (64/256/1024) and the global-bitmap tier, fresh and escalated."""
+    """Every tier (warp 64/128/256, CTA 1024, global-bitmap 12288), fresh and escalated."""
     w = synth.make_windows(tiny.labels, -4, 24, seed=beam)
     q = tiny.queries[:24]
     for method in ("optimized_postfilter", "flat", "super", "fenwick"):
