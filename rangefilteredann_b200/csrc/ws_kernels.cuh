@@ -637,7 +637,7 @@ __global__ void ws_fill_kernel(uint4* p, size_t n16) {
 #define WS_BEAM_ROWS 2  // candidate rows each team of 8 lanes keeps in flight (x4 teams per warp)
 #endif
 #ifndef WS_BEAM_PREFETCH
-#define WS_BEAM_PREFETCH 1  // L2-prefetch the candidate rows that do not fit the first register batch
+#define WS_BEAM_PREFETCH 1  // 1: L2-prefetch the candidate rows beyond the first register batch; 2: also survivors' adjacency rows
 #endif
 #ifndef WS_WARP_MINBLOCKS
 #define WS_WARP_MINBLOCKS 5  // resident CTAs per SM the warp kernels are register-budgeted for
@@ -907,7 +907,7 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, (CS <= 7 ? WS_WARP_MINB
             const unsigned bu = __ballot_sync(0xffffffffu, pu);
             if (pu) {
               sk[s + __popc(bu & lt)] = ws_key(du[u], (uint32_t)idu[u] << 1);
-              if (WS_BEAM_PREFETCH) {  // a candidate that enters the beam is likely to be expanded: warm its adjacency row
+              if (WS_BEAM_PREFETCH >= 2) {  // a candidate that enters the beam is likely to be expanded: warm its adjacency row
                 const char* ar = reinterpret_cast<const char*>(node.adj + (size_t)idu[u] * R);
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ar));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ar + 128));
