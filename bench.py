@@ -278,7 +278,8 @@ def run_engine(args, rank, world, local_rank):
     os.environ["WSANN_DEVICE"] = str(local_rank)
     t_setup = time.time()
     data, queries_all, labels = synth.make_dataset(cfg["n"], cfg["d"], cfg["nq"] * world, cfg["seed"])
-    queries = np.ascontiguousarray(queries_all[rank * cfg["nq"]:(rank + 1) * cfg["nq"]])
+    from rangefilteredann_b200 import sharding
+    queries = sharding.weak_batch(queries_all, cfg["nq"], rank)
     windows = {p: synth.make_windows(labels, p, cfg["nq"], seed=1000 + 17 * rank + p) for p in POWERS}
     cdir = cache_dir(args.config)
     os.makedirs(cdir, exist_ok=True)
@@ -373,14 +374,7 @@ def run_engine(args, rank, world, local_rank):
     barrier()
 
     # ---- reduce over ranks (max time)
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        t = torch.tensor([ms_total, e2e_s * 1000.0], device=f"cuda:{local_rank}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_ms = float(t[0]), float(t[1])
-    else:
-        e2e_ms = e2e_s * 1000.0
+    ms_total, e2e_ms = sharding.reduce_max([ms_total, e2e_s * 1000.0], device=f"cuda:{local_rank}" if world > 1 else None)
     if rank != 0:
         return
 

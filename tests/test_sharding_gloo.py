@@ -1,0 +1,64 @@
+"""CPU, world_size 2, gloo: the host-side logic of the query-sharded multi-GPU path
+(shard bounds, per-rank batches, max-over-ranks timing, host gather of result rows)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from rangefilteredann_b200 import sharding
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(0)
+        queries = rng.standard_normal((1001, 8)).astype(np.float32)
+        windows = rng.uniform(size=(1001, 2)).astype(np.float32)
+        q, w = sharding.shard_queries(queries, windows, rank, world)
+        lo, hi = sharding.shard_bounds(1001, rank, world)
+        assert len(q) == hi - lo and np.array_equal(q, queries[lo:hi]) and np.array_equal(w, windows[lo:hi])
+        # every rank "answers" its shard: fake ids = global row index
+        local = np.arange(lo, hi, dtype=np.uint32)[:, None].repeat(10, axis=1)
+        allrows = sharding.gather_rows(local, world)
+        t = sharding.reduce_max([1.0 + rank, 5.0 - rank])
+        dist.barrier()
+        if rank == 0:
+            ok = allrows.shape == (1001, 10) and np.array_equal(allrows[:, 0], np.arange(1001))
+            out.put(("ok" if ok and t == [float(world), 5.0] else f"bad {t} {allrows.shape}"))
+        wb = sharding.weak_batch(np.arange(40).reshape(20, 2), 10, rank)
+        assert wb[0, 0] == rank * 20
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out.get(timeout=10) == "ok"
+
+
+@pytest.mark.parametrize("n,world", [(10, 3), (7, 8), (10000, 8), (0, 2)])
+def test_shard_bounds_cover(n, world):
+    spans = [sharding.shard_bounds(n, r, world) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+    sizes = [b - a for a, b in spans]
+    assert max(sizes) - min(sizes) <= 1
