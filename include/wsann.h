@@ -170,6 +170,15 @@ int ws_tree_batch(ws_index* idx, int method, const float* queries, const float* 
                   uint64_t nq, const ws_query_params* qp, uint32_t* ids, float* dists,
                   uint32_t flags);
 
+/* Label-range sharded mode (datasets larger than one GPU's HBM): every rank
+ * owns a contiguous label range with its own sub-tree, answers the whole batch locally, the
+ * per-rank [nq][k] rows are all-gathered (NCCL over NVLink, done by the host plumbing) and this
+ * kernel merges the `parts` lists per query — sort_and_truncate (range_filter_tree.h:542-549)
+ * across shards.  All pointers are DEVICE pointers; rows with dist == FLT_MAX are pads.
+ * Enqueues on the index stream. */
+int ws_merge_partial_topk(ws_index* idx, const uint32_t* ids, const float* dists, uint32_t parts, uint64_t nq,
+                          uint32_t k, uint32_t pad_id, uint32_t* out_ids, float* out_dists);
+
 /* ---- device plumbing for callers that keep batches resident in HBM (bench `value`) --- */
 int ws_index_device(const ws_index* idx, int* device);
 int ws_index_sync(ws_index* idx);

@@ -56,6 +56,7 @@ def lib() -> C.CDLL:
         L.ws_prefilter_batch.argtypes = [vp, vp, vp, u64, u32, vp, vp, u32]
         L.ws_postfilter_batch.argtypes = [vp, i32, vp, vp, u64, C.POINTER(QueryParamsC), C.c_int, vp, vp, u32]
         L.ws_tree_batch.argtypes = [vp, C.c_int, vp, vp, u64, C.POINTER(QueryParamsC), vp, vp, u32]
+        L.ws_merge_partial_topk.argtypes = [vp, vp, vp, u32, u64, u32, u32, vp, vp]
         L.ws_index_sync.argtypes = [vp]
         L.ws_device_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
         L.ws_device_free.argtypes = [vp, vp]
@@ -178,6 +179,10 @@ class Handle:
         f = WS_FLAG_DEVICE_PTRS if device_ptrs else 0
         a = [x if isinstance(x, C.c_void_p) else ptr(x) for x in (queries, windows, ids, dists)]
         check(lib().ws_prefilter_batch(self.raw, a[0], a[1], nq, k, a[2], a[3], f), "ws_prefilter_batch")
+
+    def merge_partial_topk(self, ids_dev, dists_dev, parts: int, nq: int, k: int, pad_id: int, out_ids_dev, out_dists_dev):
+        check(lib().ws_merge_partial_topk(self.raw, ids_dev, dists_dev, parts, nq, k, pad_id, out_ids_dev, out_dists_dev),
+              "ws_merge_partial_topk")
 
     def postfilter_batch(self, node: int, queries, windows, nq: int, qp: QueryParamsC, pad: int, ids, dists,
                          device_ptrs=False):

@@ -1166,3 +1166,61 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_SCAN_MINBLOCKS) ws_s
     __syncwarp();
   }
 }
+
+
+// ------------------------------------------------------------------------------------------
+// K4b: merge of per-shard partial top-k lists after the all-gather of the label-sharded mode
+//      (SURVEY.md §8e-2): parts x [nq][k] (id, dist) rows -> [nq][k], ascending (dist, id);
+//      pad rows (dist == FLT_MAX) are ignored and re-created at the tail.
+// ------------------------------------------------------------------------------------------
+struct WsMergePartsArgs {
+  const uint32_t* ids;    // [parts][nq][k]
+  const float* dists;     // [parts][nq][k]
+  uint32_t parts, k, nq, pad_id;
+  uint32_t* out_ids;      // [nq][k]
+  float* out_dists;
+};
+
+__global__ void __launch_bounds__(WS_CTA_THREADS) ws_merge_parts_kernel(WsMergePartsArgs A) {
+  __shared__ uint64_t buf[WS_TOPK_BUF];
+  __shared__ int s_cnt, s_nbest;
+  __shared__ uint64_t s_tau;
+  WsTopk tk;
+  tk.buf = buf; tk.cnt = &s_cnt; tk.nbest = &s_nbest; tk.tau = &s_tau;
+  const int tid = threadIdx.x;
+  const int K = (int)A.k;
+  for (uint32_t q = blockIdx.x; q < A.nq; q += gridDim.x) {
+    __syncthreads();
+    ws_topk_init(tk, tid);
+    __syncthreads();
+    int nbest = 0, appended = 0;
+    for (uint32_t p = 0; p < A.parts; p++) {
+      if (nbest + appended + K > WS_TOPK_BUF) {
+        if (tid == 0) s_cnt = appended;
+        ws_topk_compact(tk, K, tid);
+        nbest = s_nbest;
+        appended = 0;
+      }
+      const size_t base = ((size_t)p * A.nq + q) * K;
+      for (int i = tid; i < K; i += WS_CTA_THREADS) {
+        const float d = A.dists[base + i];
+        buf[nbest + appended + i] = (d == 3.402823466e+38f) ? WS_KEY_MAX : ws_key(d, A.ids[base + i]);
+      }
+      appended += K;
+    }
+    __syncthreads();
+    if (tid == 0) s_cnt = appended;
+    ws_topk_compact(tk, K, tid);
+    nbest = s_nbest;
+    for (int j = tid; j < K; j += WS_CTA_THREADS) {
+      const uint64_t key = j < nbest ? buf[j] : WS_KEY_MAX;
+      if (key != WS_KEY_MAX) {
+        A.out_ids[(size_t)q * K + j] = (uint32_t)(key & 0xFFFFFFFFull);
+        A.out_dists[(size_t)q * K + j] = ws_unord((uint32_t)(key >> 32));
+      } else {
+        A.out_ids[(size_t)q * K + j] = A.pad_id;
+        A.out_dists[(size_t)q * K + j] = 3.402823466e+38f;
+      }
+    }
+  }
+}

@@ -1202,6 +1202,22 @@ int ws_index_build_stats(ws_index* idx, uint64_t* out4) {
   return WS_OK;
 }
 
+int ws_merge_partial_topk(ws_index* idx, const uint32_t* ids, const float* dists, uint32_t parts, uint64_t nq,
+                          uint32_t k, uint32_t pad_id, uint32_t* out_ids, float* out_dists) {
+  WS_NEED_DEVICE(idx);
+  if (!ids || !dists || !out_ids || !out_dists) return ws_fail(WS_ERR_BADARG, "null buffer");
+  if (k == 0 || k > kMaxK || parts == 0) return ws_fail(WS_ERR_BADARG, "k=%u parts=%u", k, parts);
+  if (nq == 0) return WS_OK;
+  WsMergePartsArgs a;
+  a.ids = ids; a.dists = dists; a.parts = parts; a.k = k; a.nq = (uint32_t)nq; a.pad_id = pad_id;
+  a.out_ids = out_ids; a.out_dists = out_dists;
+  int grid = (int)std::min<uint64_t>(nq, (uint64_t)idx->num_sms * 16);
+  ws_merge_parts_kernel<<<grid, WS_CTA_THREADS, 0, idx->stream>>>(a);
+  WS_CUDA(cudaGetLastError());
+  idx->launches++;
+  return WS_OK;
+}
+
 int ws_index_get_stats(ws_index* idx, ws_stats* out) {
   WS_NEED_DEVICE(idx);
   if (!out) return ws_fail(WS_ERR_BADARG, "null out");

@@ -8,7 +8,7 @@ import pytest
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from rangefilteredann_b200 import sharding
+from rangefilteredann_b200 import label_shard, sharding
 
 
 def _free_port():
@@ -38,6 +38,26 @@ def _worker(rank, world, port, out):
             out.put(("ok" if ok and t == [float(world), 5.0] else f"bad {t} {allrows.shape}"))
         wb = sharding.weak_batch(np.arange(40).reshape(20, 2), 10, rank)
         assert wb[0, 0] == rank * 20
+        # label-sharded mode: all-gather of per-rank partial top-k rows + per-query merge
+        nq, k = 37, 10
+        prng = np.random.default_rng(100 + rank)
+        gids = (prng.integers(0, 1000, size=(nq, k)) * world + rank).astype(np.uint32)  # disjoint id sets per rank
+        d = np.sort(prng.uniform(size=(nq, k)).astype(np.float32), axis=1)
+        d[rank::5, 6:] = label_shard.FLT_MAX  # some short rows
+        gids[d == label_shard.FLT_MAX] = 0
+        mi, md = label_shard.allgather_merge(gids, d, k, world)
+        # every rank must hold the same merged rows, equal to a direct merge of both inputs
+        parts_i, parts_d = [], []
+        for r in range(world):
+            g = np.random.default_rng(100 + r)
+            gi = (g.integers(0, 1000, size=(nq, k)) * world + r).astype(np.uint32)
+            dd = np.sort(g.uniform(size=(nq, k)).astype(np.float32), axis=1)
+            dd[r::5, 6:] = label_shard.FLT_MAX
+            gi[dd == label_shard.FLT_MAX] = 0
+            parts_i.append(gi); parts_d.append(dd)
+        ei, ed = label_shard.merge_partial_topk_numpy(np.stack(parts_i), np.stack(parts_d), k)
+        assert np.array_equal(mi, ei) and np.array_equal(md, ed)
+        assert (np.diff(md, axis=1) >= 0).all()
     finally:
         dist.destroy_process_group()
 
@@ -62,3 +82,12 @@ def test_shard_bounds_cover(n, world):
     assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
     sizes = [b - a for a, b in spans]
     assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_of_sorted_labels_partition():
+    rng = np.random.default_rng(3)
+    labels = rng.permutation(1000).astype(np.float32)
+    owned = [label_shard.shard_of_sorted_labels(labels, r, 4) for r in range(4)]
+    assert sorted(np.concatenate(owned).tolist()) == list(range(1000))
+    for r in range(3):  # contiguous in label order
+        assert labels[owned[r]].max() < labels[owned[r + 1]].min()
