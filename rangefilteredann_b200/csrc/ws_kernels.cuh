@@ -108,6 +108,11 @@ struct WsBeamArgs {
   uint32_t* bitmap;        // GLOBAL_SEEN: [gridDim.x][bitmap_words]
   uint64_t bitmap_words;
   unsigned long long* stats;
+  // optional: brute-force scan tasks of the same batch, drained by the same warps once the graph
+  // queue is empty (warp tiers only; null otherwise)
+  const uint32_t* sq_in;
+  const uint32_t* sq_count;
+  uint32_t* sq_head;
   // final result rows (written directly for WS_TF_SOLO tasks; K4 handles the rest)
   uint32_t* out_ids;
   float* out_dists;
@@ -764,6 +769,144 @@ __host__ __device__ inline size_t ws_warp_smem_bytes(uint32_t cap, uint32_t hash
   return (size_t)cap * 8 + 64 * 8 * 2 + 64 * 4 * 2 + (size_t)hash_entries * 4;
 }
 
+template <int STEPS>
+__device__ __forceinline__ int ws_lb_fixed_raw(const uint64_t* a, int n, uint64_t v) {
+  int lo = 0;
+#pragma unroll
+  for (int step = 1 << (STEPS - 1); step > 0; step >>= 1) {
+    const int mid = lo + step;
+    const uint64_t x = (mid <= n) ? a[mid - 1] : WS_KEY_MAX;
+    lo = (mid <= n && x < v) ? mid : lo;
+  }
+  if ((1 << STEPS) <= n) {
+    const uint64_t x = a[(1 << STEPS) - 1];
+    lo = (lo == (1 << STEPS) - 1 && x < v) ? (1 << STEPS) : lo;
+  }
+  return lo;
+}
+
+// this lane's share of query `qi` (rows of the batch are unpadded [nq][dim])
+template <int KQ, bool EXACT>
+__device__ __forceinline__ void ws_load_query_global(const float* queries, uint32_t dim, uint32_t dpad, uint32_t qi, int tl,
+                                                     float4 (&q)[KQ]) {
+  const float* qrow = queries + (size_t)qi * dim;
+  if (EXACT && dim == dpad) {  // 16-byte aligned, unpadded rows
+    const float4* q4 = reinterpret_cast<const float4*>(qrow) + tl;
+#pragma unroll
+    for (int i = 0; i < KQ; i++) q[i] = __ldg(q4 + WS_TEAM * i);
+  } else {
+#pragma unroll
+    for (int i = 0; i < KQ; i++) {
+      const int c = (tl + WS_TEAM * i) * 4;
+      q[i].x = (c + 0 < (int)dim) ? __ldg(qrow + c + 0) : 0.f;
+      q[i].y = (c + 1 < (int)dim) ? __ldg(qrow + c + 1) : 0.f;
+      q[i].z = (c + 2 < (int)dim) ? __ldg(qrow + c + 2) : 0.f;
+      q[i].w = (c + 3 < (int)dim) ? __ldg(qrow + c + 3) : 0.f;
+    }
+  }
+}
+
+// One brute-force scan task (query, rows [a,b)) by one warp: streams the slice with 16 rows in
+// flight, keeps the running top-B in `fr` (in-place merges of cutoff survivors) and writes the
+// partial (or, for WS_TF_SOLO tasks, final) result.  Shared by the scan kernel and by the beam
+// warp kernel, which drains the scan queue with the same warps once the graph queue is empty.
+struct WsScanOut {
+  const float* vecs;
+  uint32_t dpad;
+  uint64_t* res_keys;
+  uint32_t* res_cnt;
+  unsigned long long* stats;
+  uint32_t* out_ids;
+  float* out_dists;
+  const uint32_t* decode;
+  uint32_t pad_id;
+};
+
+template <int KQ, int METRIC, bool EXACT>
+__device__ __forceinline__ void ws_scan_task(const WsScanOut& A, const WsTask& task, uint32_t slot, const float4 (&q)[KQ],
+                                             int B, uint64_t* fr, uint64_t* sk, uint64_t* sk2, int* cpos) {
+  const int lane = threadIdx.x & 31;
+  const int tl = lane & (WS_TEAM - 1), team = lane / WS_TEAM;
+  const int dpad4 = A.dpad >> 2;
+  const unsigned lt = (1u << lane) - 1u;
+  const bool leader = tl == 0;
+  const float4* vtl = reinterpret_cast<const float4*>(A.vecs) + tl;
+  int n = 0, s = 0;
+  uint64_t cutoff = WS_KEY_MAX;  // k-th best key once the list is full
+  const uint32_t a = task.a, b = task.b;
+  for (uint32_t r0 = a; r0 < b; r0 += 16) {
+    uint32_t r[4];
+    float d[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      r[u] = r0 + 4 * u + team;
+      const uint32_t rc = r[u] < b ? r[u] : b - 1;
+      d[u] = ws_team_dist_nv<KQ, METRIC, EXACT>(vtl + (size_t)rc * dpad4, q, tl, dpad4);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const uint64_t key = ws_key(d[u], r[u]);
+      const bool pass = leader && r[u] < b && key < cutoff;
+      const unsigned bal = __ballot_sync(0xffffffffu, pass);
+      if (pass) sk[s + __popc(bal & lt)] = key;
+      s += __popc(bal);
+    }
+    if (s <= 48 && r0 + 16 < b) continue;
+    if (s == 0) continue;
+    // ---- fold the survivors into the running top-k
+    __syncwarp();
+    uint64_t k0 = lane < s ? sk[lane] : WS_KEY_MAX, k1 = WS_KEY_MAX;
+    if (s > 32) {
+      k1 = lane + 32 < s ? sk[lane + 32] : WS_KEY_MAX;
+      ws_warp_sort64(k0, k1, lane);
+    } else {
+      ws_warp_sort32(k0, lane);
+    }
+    const int p0 = ws_lb_fixed_raw<7>(fr, n, k0), p1 = ws_lb_fixed_raw<7>(fr, n, k1);
+    const bool ok0 = k0 != WS_KEY_MAX, ok1 = k1 != WS_KEY_MAX;
+    const int mc2 = s;  // survivors are distinct rows: nothing to de-duplicate
+    if (ok0) { sk2[lane] = k0; cpos[lane] = p0; }
+    if (ok1) { sk2[lane + 32] = k1; cpos[lane + 32] = p1; }
+    __syncwarp();
+    const int first_new = cpos[0];
+    uint64_t e[4];
+    int np[4];
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) {
+      const int i = lane + 32 * rr;
+      const bool mv = i >= first_new && i < n;
+      e[rr] = fr[i];
+      const int c = ws_lb_fixed_raw<6>(sk2, mc2, e[rr]);
+      np[rr] = mv ? i + c : B;
+    }
+    const int j1 = lane + 32;
+    const uint64_t c0 = sk2[lane], c1 = sk2[j1];
+    const int q0 = lane < mc2 ? cpos[lane] + lane : B, q1 = j1 < mc2 ? cpos[j1] + j1 : B;
+    __syncwarp();
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++)
+      if (np[rr] < B) fr[np[rr]] = e[rr];
+    if (q0 < B) fr[q0] = c0;
+    if (q1 < B) fr[q1] = c1;
+    n = min(n + mc2, B);
+    s = 0;
+    __syncwarp();
+    cutoff = (n == B) ? fr[B - 1] : WS_KEY_MAX;
+  }
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) A.res_keys[(size_t)slot * B + i] = fr[i];
+  if (task.flags & WS_TF_SOLO)
+    for (int j = lane; j < B; j += 32) {
+      if (j < n) ws_write_result(A.out_ids, A.out_dists, A.decode, task.query, B, j, fr[j]);
+      else ws_write_pad(A.out_ids, A.out_dists, A.pad_id, task.query, B, j);
+    }
+  if (lane == 0) {
+    A.res_cnt[slot] = (uint32_t)n;
+    atomicAdd(A.stats + WS_ST_SCANPTS, (unsigned long long)(b - a));
+  }
+  __syncwarp();
+}
+
 // CS = log2 of the largest beam the instantiation can hold (7 -> 128, 8 -> 256)
 template <int KQ, int METRIC, bool EXACT, int CS>
 __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, (CS <= 7 ? WS_WARP_MINBLOCKS : 2)) ws_beam_warp_kernel(WsBeamArgs A) {
@@ -794,23 +937,7 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, (CS <= 7 ? WS_WARP_MINB
     const WsTask task = A.tasks[slot];
     const WsNode node = A.nodes[task.node];
     float4 q[KQ];
-    {
-      const float* qrow = A.queries + (size_t)task.query * A.dim;
-      if (EXACT && A.dim == A.dpad) {  // rows of the query batch are 16-byte aligned and unpadded
-        const float4* q4 = reinterpret_cast<const float4*>(qrow) + tl;
-#pragma unroll
-        for (int i = 0; i < KQ; i++) q[i] = __ldg(q4 + WS_TEAM * i);
-      } else {
-#pragma unroll
-        for (int i = 0; i < KQ; i++) {
-          const int c = (tl + WS_TEAM * i) * 4;
-          q[i].x = (c + 0 < (int)A.dim) ? __ldg(qrow + c + 0) : 0.f;
-          q[i].y = (c + 1 < (int)A.dim) ? __ldg(qrow + c + 1) : 0.f;
-          q[i].z = (c + 2 < (int)A.dim) ? __ldg(qrow + c + 2) : 0.f;
-          q[i].w = (c + 3 < (int)A.dim) ? __ldg(qrow + c + 3) : 0.f;
-        }
-      }
-    }
+    ws_load_query_global<KQ, EXACT>(A.queries, A.dim, A.dpad, task.query, tl, q);
     const float4* vbase_tl = reinterpret_cast<const float4*>(A.vecs + (size_t)node.start * A.dpad) + tl;
     const int skip_id = A.skip_query_id ? (int)task.query : -1;
 
@@ -1017,6 +1144,25 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, (CS <= 7 ? WS_WARP_MINB
       atomicAdd(A.stats + WS_ST_ESCALATED, 1ull);
     }
   }
+
+  // ---- graph queue empty: the same warps drain the batch's brute-force scan tasks (fenwick
+  //      edges), so the short scans fill the tail of the graph searches instead of a launch of their own
+  if (A.sq_in != nullptr) {
+    WsScanOut so;
+    so.vecs = A.vecs; so.dpad = A.dpad; so.res_keys = A.res_keys; so.res_cnt = A.res_cnt; so.stats = A.stats;
+    so.out_ids = A.out_ids; so.out_dists = A.out_dists; so.decode = A.decode; so.pad_id = A.pad_id;
+    for (;;) {
+      uint32_t t = 0;
+      if (lane == 0) t = atomicAdd(A.sq_head, 1u);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= *A.sq_count) break;
+      const uint32_t slot = A.sq_in[t];
+      const WsTask task = A.tasks[slot];
+      float4 q[KQ];
+      ws_load_query_global<KQ, EXACT>(A.queries, A.dim, A.dpad, task.query, tl, q);
+      ws_scan_task<KQ, METRIC, EXACT>(so, task, slot, q, K, fr, sk, sk2, cpos);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1030,22 +1176,6 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, (CS <= 7 ? WS_WARP_MINB
 #ifndef WS_SCAN_MINBLOCKS
 #define WS_SCAN_MINBLOCKS 6
 #endif
-
-template <int STEPS>
-__device__ __forceinline__ int ws_lb_fixed_raw(const uint64_t* a, int n, uint64_t v) {
-  int lo = 0;
-#pragma unroll
-  for (int step = 1 << (STEPS - 1); step > 0; step >>= 1) {
-    const int mid = lo + step;
-    const uint64_t x = (mid <= n) ? a[mid - 1] : WS_KEY_MAX;
-    lo = (mid <= n && x < v) ? mid : lo;
-  }
-  if ((1 << STEPS) <= n) {
-    const uint64_t x = a[(1 << STEPS) - 1];
-    lo = (lo == (1 << STEPS) - 1 && x < v) ? (1 << STEPS) : lo;
-  }
-  return lo;
-}
 
 template <int KQ, int METRIC, bool EXACT>
 __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_SCAN_MINBLOCKS) ws_scan_warp_kernel(WsScanArgs A) {
@@ -1072,98 +1202,11 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_SCAN_MINBLOCKS) ws_s
     const uint32_t slot = A.q_in[t];
     const WsTask task = A.tasks[slot];
     float4 q[KQ];
-    {
-      const float* qrow = A.queries + (size_t)task.query * A.dim;
-      if (EXACT && A.dim == A.dpad) {
-        const float4* q4 = reinterpret_cast<const float4*>(qrow) + tl;
-#pragma unroll
-        for (int i = 0; i < KQ; i++) q[i] = __ldg(q4 + WS_TEAM * i);
-      } else {
-#pragma unroll
-        for (int i = 0; i < KQ; i++) {
-          const int c = (tl + WS_TEAM * i) * 4;
-          q[i].x = (c + 0 < (int)A.dim) ? __ldg(qrow + c + 0) : 0.f;
-          q[i].y = (c + 1 < (int)A.dim) ? __ldg(qrow + c + 1) : 0.f;
-          q[i].z = (c + 2 < (int)A.dim) ? __ldg(qrow + c + 2) : 0.f;
-          q[i].w = (c + 3 < (int)A.dim) ? __ldg(qrow + c + 3) : 0.f;
-        }
-      }
-    }
-    const float4* vtl = reinterpret_cast<const float4*>(A.vecs) + tl;
-    int n = 0, s = 0;
-    uint64_t cutoff = WS_KEY_MAX;  // k-th best key once the list is full
-    const uint32_t a = task.a, b = task.b;
-    for (uint32_t r0 = a; r0 < b; r0 += 16) {
-      uint32_t r[4];
-      float d[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        r[u] = r0 + 4 * u + team;
-        const uint32_t rc = r[u] < b ? r[u] : b - 1;
-        d[u] = ws_team_dist_nv<KQ, METRIC, EXACT>(vtl + (size_t)rc * dpad4, q, tl, dpad4);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const uint64_t key = ws_key(d[u], r[u]);
-        const bool pass = leader && r[u] < b && key < cutoff;
-        const unsigned bal = __ballot_sync(0xffffffffu, pass);
-        if (pass) sk[s + __popc(bal & lt)] = key;
-        s += __popc(bal);
-      }
-      if (s <= 48 && r0 + 16 < b) continue;
-      if (s == 0) continue;
-      // ---- fold the survivors into the running top-k
-      __syncwarp();
-      uint64_t k0 = lane < s ? sk[lane] : WS_KEY_MAX, k1 = WS_KEY_MAX;
-      if (s > 32) {
-        k1 = lane + 32 < s ? sk[lane + 32] : WS_KEY_MAX;
-        ws_warp_sort64(k0, k1, lane);
-      } else {
-        ws_warp_sort32(k0, lane);
-      }
-      const int p0 = ws_lb_fixed_raw<7>(fr, n, k0), p1 = ws_lb_fixed_raw<7>(fr, n, k1);
-      const bool ok0 = k0 != WS_KEY_MAX, ok1 = k1 != WS_KEY_MAX;
-      const int mc2 = s;  // survivors are distinct rows: nothing to de-duplicate
-      if (ok0) { sk2[lane] = k0; cpos[lane] = p0; }
-      if (ok1) { sk2[lane + 32] = k1; cpos[lane + 32] = p1; }
-      __syncwarp();
-      const int first_new = cpos[0];
-      uint64_t e[4];
-      int np[4];
-#pragma unroll
-      for (int rr = 0; rr < 4; rr++) {
-        const int i = lane + 32 * rr;
-        const bool mv = i >= first_new && i < n;
-        e[rr] = fr[i];
-        const int c = ws_lb_fixed_raw<6>(sk2, mc2, e[rr]);
-        np[rr] = mv ? i + c : B;
-      }
-      const int j1 = lane + 32;
-      const uint64_t c0 = sk2[lane], c1 = sk2[j1];
-      const int q0 = lane < mc2 ? cpos[lane] + lane : B, q1 = j1 < mc2 ? cpos[j1] + j1 : B;
-      __syncwarp();
-#pragma unroll
-      for (int rr = 0; rr < 4; rr++)
-        if (np[rr] < B) fr[np[rr]] = e[rr];
-      if (q0 < B) fr[q0] = c0;
-      if (q1 < B) fr[q1] = c1;
-      n = min(n + mc2, B);
-      s = 0;
-      __syncwarp();
-      cutoff = (n == B) ? fr[B - 1] : WS_KEY_MAX;
-    }
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) A.res_keys[(size_t)slot * B + i] = fr[i];
-    if (task.flags & WS_TF_SOLO)
-      for (int j = lane; j < B; j += 32) {
-        if (j < n) ws_write_result(A.out_ids, A.out_dists, A.decode, task.query, B, j, fr[j]);
-        else ws_write_pad(A.out_ids, A.out_dists, A.pad_id, task.query, B, j);
-      }
-    if (lane == 0) {
-      A.res_cnt[slot] = (uint32_t)n;
-      atomicAdd(A.stats + WS_ST_SCANPTS, (unsigned long long)(b - a));
-    }
-    __syncwarp();
+    ws_load_query_global<KQ, EXACT>(A.queries, A.dim, A.dpad, task.query, tl, q);
+    WsScanOut so;
+    so.vecs = A.vecs; so.dpad = A.dpad; so.res_keys = A.res_keys; so.res_cnt = A.res_cnt; so.stats = A.stats;
+    so.out_ids = A.out_ids; so.out_dists = A.out_dists; so.decode = A.decode; so.pad_id = A.pad_id;
+    ws_scan_task<KQ, METRIC, EXACT>(so, task, slot, q, B, fr, sk, sk2, cpos);
   }
 }
 

@@ -116,7 +116,8 @@ struct ws_index {
   int64_t opt_hash_factor = 32;
   int64_t opt_warp_tiers = 1;    // use the warp-per-task kernels for beams <= 128
   int64_t opt_warp_hash = 2048;
-  int64_t opt_warp_scan = 1;     // warp-per-task scan kernel for k <= 128  // visited-table entries per warp in those kernels
+  int64_t opt_warp_scan = 1;     // warp-per-task scan kernel for k <= 128
+  int64_t opt_fuse_scan = 1;     // let the first warp-tier beam launch drain the scan queue too  // visited-table entries per warp in those kernels
   int64_t opt_build_expand = 1;  // nodes expanded per step while BUILDING graphs
   uint64_t build_stats[4] = {0, 0, 0, 0};  // inserts, visited, dist_cmps, overflow re-prunes  // smem visited-table entries per unit of beam capacity
 
@@ -708,6 +709,11 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
   }
   WS_CUDA(cudaGetLastError());
 
+  // the first warp-tier launch can also take the batch's scan tasks (same warps, same smem)
+  const bool has_scans = plan.mode != WS_MODE_POSTFILTER && plan.mode != WS_METHOD_SUPER_POSTFILTER;
+  const bool fuse_scan = needs_graph && has_scans && idx->opt_fuse_scan && first_tier < WS_NUM_WARP_TIERS &&
+                         k <= std::min<uint32_t>(128u, kBeamTierCaps[first_tier]);
+
   // ---- K2 beam search, one persistent launch per tier
   if (needs_graph) {
     const uint32_t E = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(8, idx->opt_expand));
@@ -760,6 +766,10 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
         ba.bitmap = (uint32_t*)idx->bitmap.p;
       }
       ba.stats = idx->d_stats;
+      ba.sq_in = nullptr; ba.sq_count = nullptr; ba.sq_head = nullptr;
+      if (fuse_scan && t == first_tier) {  // this launch also drains the scan queue
+        ba.sq_in = queues + (size_t)WS_NUM_TIERS * slots; ba.sq_count = ctrl + WS_NUM_TIERS; ba.sq_head = ctrl + 8 + WS_NUM_TIERS;
+      }
       ba.out_ids = dids; ba.out_dists = ddists; ba.decode = plan.use_decode ? idx->d_decode : nullptr; ba.pad_id = plan.pad_id;
 #define WS_LB(KQ_, M_) { cudaError_t _e = warp_tier ? ws_launch_beam_warp_t<KQ_, M_>(exact_rows, wide, grid, smem, st, ba) : ws_launch_beam_t<KQ_, M_>(large, grid, smem, st, ba); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "beam kernel launch (tier %d): %s", t, cudaGetErrorString(_e)); }
       {
@@ -771,7 +781,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
   }
 
   // ---- K1 scans
-  if (plan.mode != WS_MODE_POSTFILTER && plan.mode != WS_METHOD_SUPER_POSTFILTER) {
+  if (has_scans && !fuse_scan) {
     WsScanArgs sa;
     sa.vecs = idx->d_vecs; sa.queries = dq; sa.dim = idx->dim; sa.dpad = idx->dpad;
     sa.tasks = (const WsTask*)idx->tasks.p; sa.res_keys = (uint64_t*)idx->res_keys.p; sa.res_cnt = (uint32_t*)idx->res_cnt.p;
@@ -1258,6 +1268,8 @@ int ws_index_set_option(ws_index* idx, const char* name, int64_t value) {
     idx->opt_scan_chunk = value;
   } else if (s == "warp_tiers") {
     idx->opt_warp_tiers = value != 0;
+  } else if (s == "fuse_scan") {
+    idx->opt_fuse_scan = value != 0;
   } else if (s == "warp_scan") {
     idx->opt_warp_scan = value != 0;
   } else if (s == "warp_hash") {
