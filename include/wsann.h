@@ -199,9 +199,11 @@ int ws_index_get_stats(ws_index* idx, ws_stats* out);
 int ws_index_reset_stats(ws_index* idx);
 /* number of kernels launched by this index since creation (bench `gpu_launches`) */
 int ws_index_launch_count(const ws_index* idx, uint64_t* out);
-/* tuning knobs: "expand_width" (nodes expanded per beam-search step, default 1 = reference
- * order), "emulate_query_id_skip" (beamSearch.h:128 `a == p.id()`, default 1),
- * "scan_chunk" (rows per brute-force task), "profile_kernels", "hash_factor" */
+/* tuning knobs: "emulate_query_id_skip" (beamSearch.h:128 `a == p.id()`, default 1),
+ * "scan_chunk" (rows per brute-force task), "profile_kernels", "warp_tiers", "warp_hash",
+ * "warp_scan", "fuse_scan", "hash_factor", "build_expand_width" (nodes expanded per step by
+ * the device-side graph BUILDER; the query kernels always expand one node per step, as the
+ * reference does) */
 int ws_index_set_option(ws_index* idx, const char* name, int64_t value);
 int ws_index_hbm_bytes(const ws_index* idx, uint64_t* out);
 /* With option "profile_kernels" = 1 every kernel launch is bracketed by CUDA events on the

@@ -1267,3 +1267,262 @@ __global__ void __launch_bounds__(WS_CTA_THREADS) ws_merge_parts_kernel(WsMergeP
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------
+// K2c: CTA-per-task beam search for the large-beam tail (beams up to 1024 in shared memory,
+//      up to 12288 with a global visited bitmap).
+//
+// Tail tasks are few and long (the doubling loop of postfilter_vamana.h:161-172 has driven
+// them to beams in the hundreds or thousands), so what matters is the latency of ONE
+// expansion, not occupancy: warp 0 is the control warp (pick, adjacency, visited filter,
+// survivor sort, ranks) and all 8 warps gather distances together, so every candidate row of
+// an expansion is in flight at once; the frontier is one array updated in place by all
+// threads.  Same algorithm and same results as the warp kernel / ws_beam_kernel.
+// ------------------------------------------------------------------------------------------
+#define WS_CTA2_THREADS 256
+
+template <int KQ, int METRIC, bool EXACT, bool GLOBAL_SEEN, int CS>
+__global__ void __launch_bounds__(WS_CTA2_THREADS, 1) ws_beam_cta2_kernel(WsBeamArgs A) {
+  extern __shared__ __align__(16) unsigned char ws_smem[];
+  const uint32_t CAP = A.beam_cap;
+  uint64_t* fr = reinterpret_cast<uint64_t*>(ws_smem);   // [CAP]
+  uint64_t* sk = fr + CAP;                                // [64]
+  uint64_t* sk2 = sk + 64;                                // [64]
+  int* cpos = reinterpret_cast<int*>(sk2 + 64);           // [64]
+  int* cid = cpos + 64;                                   // [64]
+  volatile int* hash = cid + 64;                          // [hash_mask + 1] (!GLOBAL_SEEN)
+  __shared__ uint32_t s_task;
+  __shared__ int s_m, s_cnt, s_mc2, s_first_new, s_pick, s_have;
+  __shared__ float s_cutoff;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tl = lane & (WS_TEAM - 1), team = lane / WS_TEAM;
+  const int dpad4 = A.dpad >> 2;
+  const int K = (int)A.k;
+  const int R = (int)A.R;
+  const unsigned lt = (1u << lane) - 1u;
+  const bool leader = tl == 0;
+  uint32_t* bitmap = GLOBAL_SEEN ? A.bitmap + (size_t)blockIdx.x * A.bitmap_words : nullptr;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_task = atomicAdd(A.q_head, 1u);
+    __syncthreads();
+    const uint32_t t = s_task;
+    if (t >= *A.q_in_count) break;
+    const uint32_t slot = A.q_in[t];
+    const WsTask task = A.tasks[slot];
+    const WsNode node = A.nodes[task.node];
+    float4 q[KQ];
+    ws_load_query_global<KQ, EXACT>(A.queries, A.dim, A.dpad, task.query, tl, q);
+    const float4* vbase_tl = reinterpret_cast<const float4*>(A.vecs + (size_t)node.start * A.dpad) + tl;
+    const int skip_id = A.skip_query_id ? (int)task.query : -1;
+
+    long long beam = task.beam;
+    int phase = (task.flags & WS_TF_FINAL) ? 1 : 0;
+    const long long mult = (task.flags & WS_TF_MULT1) ? 1 : A.final_mult;
+    int have = 0;
+    bool escalate = false;
+    if (!(task.flags & WS_TF_RESUMED) && tid == 0) A.res_cnt[slot] = 0;
+
+    for (;;) {  // PostfilterVamanaIndex::query (postfilter_vamana.h:141-188)
+      if (phase == 0) {
+        if (!(have < K && beam < A.max_beam)) {
+          long long fin = beam * mult;
+          if (fin > A.max_beam) fin = A.max_beam;
+          if (fin > beam) { beam = fin; phase = 1; } else break;
+        }
+      }
+      if (beam > (long long)CAP) { escalate = true; break; }
+      const int B = (int)beam;
+
+      // ---- beam_search (beamSearch.h:51-184)
+      if (!GLOBAL_SEEN) {
+        for (int i = tid; i <= (int)A.hash_mask; i += WS_CTA2_THREADS) hash[i] = -1;
+      } else {
+        const int words = (int)((node.count + 31u) >> 5);
+        for (int i = tid; i < words; i += WS_CTA2_THREADS) bitmap[i] = 0u;
+      }
+      if (warp == 0) {
+        const float d0 = ws_team_dist_nv<KQ, METRIC, EXACT>(vbase_tl, q, tl, dpad4);
+        if (lane == 0) fr[0] = ws_key(d0, 0u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        if (!GLOBAL_SEEN) ws_seen_warp(hash, A.hash_mask, 0); else ws_seen_bitmap(bitmap, 0);
+      }
+      int n = 1, scan_from = 0;
+      unsigned long long nvis = 0, ncmp = 1;
+
+      for (;;) {
+        if ((long long)nvis >= A.limit) break;
+        __syncthreads();
+        // ---- A: control warp — pick, adjacency, visited filter (beamSearch.h:111-131)
+        if (warp == 0) {
+          int pick = -1;
+          for (int b0 = scan_from; b0 < n; b0 += 32) {
+            const int i = b0 + lane;
+            const bool unv = i < n && !(fr[i] & 1ull);
+            const unsigned bal = __ballot_sync(0xffffffffu, unv);
+            if (bal) { pick = b0 + __ffs(bal) - 1; break; }
+          }
+          int m = 0;
+          if (pick >= 0) {
+            const uint64_t pkey = fr[pick];
+            const uint32_t cur_id = (uint32_t)(pkey & 0xFFFFFFFFull) >> 1;
+            __syncwarp();
+            if (lane == 0) fr[pick] = pkey | 1ull;
+            int nb0 = -1, nb1 = -1;
+            const int* arow = node.adj + (size_t)cur_id * R;
+            if (lane < R && (long long)lane < A.degree_limit) nb0 = __ldg(arow + lane);
+            if (lane + 32 < R && (long long)(lane + 32) < A.degree_limit) nb1 = __ldg(arow + lane + 32);
+            bool keep0 = nb0 >= 0 && nb0 != skip_id;
+            bool keep1 = nb1 >= 0 && nb1 != skip_id;
+            if (!GLOBAL_SEEN) {
+              ws_seen_warp2(hash, A.hash_mask, nb0, keep0, nb1, keep1);
+            } else {
+              if (keep0) keep0 = !ws_seen_bitmap(bitmap, nb0);
+              if (keep1) keep1 = !ws_seen_bitmap(bitmap, nb1);
+            }
+            const unsigned bal0 = __ballot_sync(0xffffffffu, keep0), bal1 = __ballot_sync(0xffffffffu, keep1);
+            const int m0 = __popc(bal0);
+            m = m0 + __popc(bal1);
+            if (keep0) cid[__popc(bal0 & lt)] = nb0;
+            if (keep1) cid[m0 + __popc(bal1 & lt)] = nb1;
+          }
+          if (lane == 0) {
+            s_pick = pick;
+            s_m = m;
+            s_cnt = 0;
+            s_cutoff = (n < B) ? (float)2147483647 : ws_unord((uint32_t)(fr[n - 1] >> 32));
+          }
+        }
+        __syncthreads();
+        const int pick = s_pick;
+        if (pick < 0) break;
+        nvis++;
+        const int m = s_m;
+        if (m == 0) { scan_from = pick + 1; continue; }
+        ncmp += (unsigned long long)m;
+
+        // ---- B: every warp gathers its share of the candidate rows (beamSearch.h:135-145)
+        {
+          const float cutoff = s_cutoff;
+          for (int jb = 0; jb < m; jb += (WS_CTA2_THREADS / WS_TEAM)) {
+            const int j = jb + warp * 4 + team;
+            const int id = cid[min(j, m - 1)];
+            const float d = ws_team_dist_nv<KQ, METRIC, EXACT>(vbase_tl + (size_t)id * dpad4, q, tl, dpad4);
+            const bool pu = leader && j < m && d < cutoff;
+            const unsigned bu = __ballot_sync(0xffffffffu, pu);
+            int wbase = 0;
+            if (lane == 0 && bu) wbase = atomicAdd(&s_cnt, __popc(bu));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (pu) sk[wbase + __popc(bu & lt)] = ws_key(d, (uint32_t)id << 1);
+          }
+        }
+        __syncthreads();
+        const int s = s_cnt;
+        if (s == 0) { scan_from = pick + 1; continue; }
+
+        // ---- C: control warp — sort survivors, drop duplicates, rank against the frontier
+        if (warp == 0) {
+          uint64_t k0 = lane < s ? sk[lane] : WS_KEY_MAX, k1 = WS_KEY_MAX;
+          if (s > 32) {
+            k1 = lane + 32 < s ? sk[lane + 32] : WS_KEY_MAX;
+            ws_warp_sort64(k0, k1, lane);
+          } else {
+            ws_warp_sort32(k0, lane);
+          }
+          const uint64_t up0 = ws_shfl_up_u64(k0, 1);
+          uint64_t up1 = ws_shfl_up_u64(k1, 1);
+          const uint64_t last0 = ws_shfl_idx_u64(k0, 31);
+          up1 = lane == 0 ? last0 : up1;
+          const int p0 = ws_lb_fixed<CS>(fr, n, k0 >> 1), p1 = ws_lb_fixed<CS>(fr, n, k1 >> 1);
+          const uint64_t f0 = fr[min(p0, n - 1)], f1 = fr[min(p1, n - 1)];
+          const bool ok0 = k0 != WS_KEY_MAX && !(lane > 0 && up0 == k0) && !(p0 < n && (f0 >> 1) == (k0 >> 1));
+          const bool ok1 = k1 != WS_KEY_MAX && up1 != k1 && !(p1 < n && (f1 >> 1) == (k1 >> 1));
+          const unsigned bka = __ballot_sync(0xffffffffu, ok0), bkb = __ballot_sync(0xffffffffu, ok1);
+          const int ca = __popc(bka);
+          if (ok0) { const int r = __popc(bka & lt); sk2[r] = k0; cpos[r] = p0; }
+          if (ok1) { const int r = ca + __popc(bkb & lt); sk2[r] = k1; cpos[r] = p1; }
+          __syncwarp();
+          if (lane == 0) { s_mc2 = ca + __popc(bkb); s_first_new = (ca + __popc(bkb)) ? cpos[0] : n; }
+        }
+        __syncthreads();
+        const int mc2 = s_mc2;
+        if (mc2 == 0) { scan_from = pick + 1; continue; }
+        const int first_new = s_first_new;
+
+        // ---- D: all threads shift the tail of the frontier right, from the end, one chunk of
+        //         256 entries at a time (a chunk's targets never fall below its own start)
+        for (int hi = n; hi > first_new; hi -= WS_CTA2_THREADS) {
+          const int i = hi - 1 - tid;
+          const bool valid = i >= first_new;
+          uint64_t key = 0;
+          int c = 0;
+          if (valid) {
+            key = fr[i];
+            c = ws_lb_fixed<6>(sk2, mc2, key >> 1);
+          }
+          __syncthreads();
+          if (valid && i + c < B) fr[i + c] = key;
+        }
+        __syncthreads();
+        if (tid < mc2) {
+          const int pos = cpos[tid] + tid;
+          if (pos < B) fr[pos] = sk2[tid];
+        }
+        n = min(n + mc2, B);
+        scan_from = min(pick + 1, first_new);
+      }
+
+      // ---- raw_query's label predicate by the control warp (postfilter_vamana.h:234-251)
+      __syncthreads();
+      if (warp == 0) {
+        int hv = 0;
+        for (int b0 = 0; b0 < n && hv < K; b0 += 32) {
+          const int i = b0 + lane;
+          bool in = false;
+          uint64_t key = 0;
+          uint32_t rank = 0;
+          if (i < n) {
+            key = fr[i];
+            rank = node.start + ((uint32_t)(key & 0xFFFFFFFFull) >> 1);
+            const float lab = __ldg(A.labels + rank);
+            in = (lab >= task.lo) && (lab <= task.hi);
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, in);
+          const int r = hv + __popc(bal & lt);
+          if (in && r < K) {
+            const uint64_t okey = (key & 0xFFFFFFFF00000000ull) | rank;
+            A.res_keys[(size_t)slot * K + r] = okey;
+            if (task.flags & WS_TF_SOLO) ws_write_result(A.out_ids, A.out_dists, A.decode, task.query, K, r, okey);
+          }
+          hv += __popc(bal);
+        }
+        if (lane == 0) {
+          s_have = hv;
+          A.res_cnt[slot] = (uint32_t)min(hv, K);
+          atomicAdd(A.stats + WS_ST_SEARCHES, 1ull);
+          atomicAdd(A.stats + WS_ST_VISITED, nvis);
+          atomicAdd(A.stats + WS_ST_DISTCMPS, ncmp);
+          atomicAdd(A.stats + WS_ST_BEAMSUM, (unsigned long long)B);
+        }
+      }
+      __syncthreads();
+      have = s_have;
+      if (phase == 1) break;
+      if (have < K) beam *= 2;
+    }
+
+    if (!escalate && (task.flags & WS_TF_SOLO))
+      for (int j = min(have, K) + tid; j < K; j += WS_CTA2_THREADS) ws_write_pad(A.out_ids, A.out_dists, A.pad_id, task.query, K, j);
+    if (escalate && tid == 0 && A.q_out != nullptr) {
+      A.tasks[slot].beam = (uint32_t)beam;
+      A.tasks[slot].flags = task.flags | WS_TF_RESUMED | (phase ? WS_TF_FINAL : 0u);
+      const uint32_t pos = atomicAdd(A.q_out_count, 1u);
+      A.q_out[pos] = slot;
+      atomicAdd(A.stats + WS_ST_ESCALATED, 1ull);
+    }
+  }
+}

@@ -117,7 +117,7 @@ struct ws_index {
   int64_t opt_warp_tiers = 1;    // use the warp-per-task kernels for beams <= 128
   int64_t opt_warp_hash = 2048;
   int64_t opt_warp_scan = 1;     // warp-per-task scan kernel for k <= 128
-  int64_t opt_fuse_scan = 1;     // let the first warp-tier beam launch drain the scan queue too  // visited-table entries per warp in those kernels
+  int64_t opt_fuse_scan = 0;     // let the first warp-tier beam launch drain the scan queue too (measured neutral)  // visited-table entries per warp in those kernels
   int64_t opt_build_expand = 1;  // nodes expanded per step while BUILDING graphs
   uint64_t build_stats[4] = {0, 0, 0, 0};  // inserts, visited, dist_cmps, overflow re-prunes  // smem visited-table entries per unit of beam capacity
 
@@ -309,7 +309,7 @@ int ws_index_add_graph(ws_index* idx, uint64_t start, uint64_t count, uint32_t m
   if (!idx || !node_out) return ws_fail(WS_ERR_BADARG, "null argument");
   if (idx->finalized) return ws_fail(WS_ERR_STATE, "index already finalized");
   if (count == 0 || start + count > idx->n) return ws_fail(WS_ERR_BADARG, "graph range [%llu,+%llu) outside the arena", (unsigned long long)start, (unsigned long long)count);
-  if (max_degree == 0 || max_degree > 128) return ws_fail(WS_ERR_BADARG, "max_degree %u unsupported (1..128)", max_degree);
+  if (max_degree == 0 || max_degree > 64) return ws_fail(WS_ERR_BADARG, "max_degree %u unsupported (1..64)", max_degree);
   uint32_t R = (max_degree + 3u) & ~3u;
   if (idx->R == 0) idx->R = R;
   if (idx->R != R) return ws_fail(WS_ERR_BADARG, "all graphs of one index must share max_degree (%u vs %u)", idx->R, R);
@@ -497,32 +497,30 @@ static uint32_t ws_task_capacity(const ws_index* idx, int mode) {
   return (uint32_t)fen;
 }
 
-template <int KQ, int METRIC>
-static cudaError_t ws_launch_beam_t(bool global_seen, int grid, size_t smem, cudaStream_t s, const WsBeamArgs& a) {
-  cudaError_t e;
-  if (global_seen) {
-    e = cudaFuncSetAttribute(ws_beam_kernel<KQ, METRIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    ws_beam_kernel<KQ, METRIC, true><<<grid, WS_CTA_THREADS, smem, s>>>(a);
-  } else {
-    e = cudaFuncSetAttribute(ws_beam_kernel<KQ, METRIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    ws_beam_kernel<KQ, METRIC, false><<<grid, WS_CTA_THREADS, smem, s>>>(a);
-  }
+// CTA-per-task tiers (beams > 256): ws_beam_cta2_kernel, shared-memory visited table (cap 1024)
+// or global bitmap (cap 12288)
+template <int KQ, int METRIC, bool EXACT, bool GS, int CS>
+static cudaError_t ws_launch_beam_cta_tt(int grid, size_t smem, cudaStream_t s, const WsBeamArgs& a) {
+  cudaError_t e = cudaFuncSetAttribute(ws_beam_cta2_kernel<KQ, METRIC, EXACT, GS, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  ws_beam_cta2_kernel<KQ, METRIC, EXACT, GS, CS><<<grid, WS_CTA2_THREADS, smem, s>>>(a);
   return cudaGetLastError();
 }
-
 template <int KQ, int METRIC>
-static cudaError_t ws_beam_occupancy_t(bool global_seen, size_t smem, int* blocks) {
-  cudaError_t e;
-  if (global_seen) {
-    e = cudaFuncSetAttribute(ws_beam_kernel<KQ, METRIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_beam_kernel<KQ, METRIC, true>, WS_CTA_THREADS, smem);
-  }
-  e = cudaFuncSetAttribute(ws_beam_kernel<KQ, METRIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+static cudaError_t ws_launch_beam_t(bool exact, bool global_seen, int grid, size_t smem, cudaStream_t s, const WsBeamArgs& a) {
+  if (global_seen) return exact ? ws_launch_beam_cta_tt<KQ, METRIC, true, true, 14>(grid, smem, s, a) : ws_launch_beam_cta_tt<KQ, METRIC, false, true, 14>(grid, smem, s, a);
+  return exact ? ws_launch_beam_cta_tt<KQ, METRIC, true, false, 10>(grid, smem, s, a) : ws_launch_beam_cta_tt<KQ, METRIC, false, false, 10>(grid, smem, s, a);
+}
+template <int KQ, int METRIC, bool EXACT, bool GS, int CS>
+static cudaError_t ws_beam_cta_occupancy_tt(size_t smem, int* blocks) {
+  cudaError_t e = cudaFuncSetAttribute(ws_beam_cta2_kernel<KQ, METRIC, EXACT, GS, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_beam_kernel<KQ, METRIC, false>, WS_CTA_THREADS, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_beam_cta2_kernel<KQ, METRIC, EXACT, GS, CS>, WS_CTA2_THREADS, smem);
+}
+template <int KQ, int METRIC>
+static cudaError_t ws_beam_occupancy_t(bool exact, bool global_seen, size_t smem, int* blocks) {
+  if (global_seen) return exact ? ws_beam_cta_occupancy_tt<KQ, METRIC, true, true, 14>(smem, blocks) : ws_beam_cta_occupancy_tt<KQ, METRIC, false, true, 14>(smem, blocks);
+  return exact ? ws_beam_cta_occupancy_tt<KQ, METRIC, true, false, 10>(smem, blocks) : ws_beam_cta_occupancy_tt<KQ, METRIC, false, false, 10>(smem, blocks);
 }
 
 template <int KQ, int METRIC, bool EXACT, int CS>
@@ -675,7 +673,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
 
   // ---- tiers: which launch takes fresh graph tasks
   const int kq = ws_pick_kq(idx->dpad);
-  const int lowest_tier = (idx->R <= 64 && idx->opt_warp_tiers) ? 0 : WS_NUM_WARP_TIERS;
+  const int lowest_tier = idx->opt_warp_tiers ? 0 : WS_NUM_WARP_TIERS;
   const bool exact_rows = (uint32_t)kq * WS_TEAM * 4 == idx->dpad;  // padded row = 8*KQ float4s: no column predicate
   int first_tier = WS_NUM_TIERS - 1;
   if (needs_graph) {
@@ -733,14 +731,15 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
         hash_entries = 1024;
         while (hash_entries < (uint64_t)idx->opt_hash_factor * beam_cap) hash_entries <<= 1;
       }
+      if (!warp_tier && idx->R > 64) return ws_fail(WS_ERR_BADARG, "graphs with max_degree > 64 are not supported by the query kernels");
       size_t smem;
       if (warp_tier)
         smem = (size_t)WS_WARPS_PER_CTA * ws_warp_smem_bytes(beam_cap, hash_entries);
       else
-        smem = (size_t)2 * beam_cap * 8 + (size_t)cand_cap * 24 + (size_t)idx->dpad * 4 + (size_t)hash_entries * 4;
+        smem = (size_t)beam_cap * 8 + 64 * 8 * 2 + 64 * 4 * 2 + (size_t)hash_entries * 4;
       if (smem > idx->smem_optin) return ws_fail(WS_ERR_BADARG, "beam tier %d needs %zu B of shared memory (> %zu)", t, smem, idx->smem_optin);
       int occ = 0;
-#define WS_OCC(KQ_, M_) { cudaError_t _e = warp_tier ? ws_beam_warp_occupancy_t<KQ_, M_>(exact_rows, wide, smem, &occ) : ws_beam_occupancy_t<KQ_, M_>(large, smem, &occ); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(_e)); }
+#define WS_OCC(KQ_, M_) { cudaError_t _e = warp_tier ? ws_beam_warp_occupancy_t<KQ_, M_>(exact_rows, wide, smem, &occ) : ws_beam_occupancy_t<KQ_, M_>(exact_rows, large, smem, &occ); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(_e)); }
       WS_DISPATCH_KQ(kq, idx->metric, WS_OCC);
 #undef WS_OCC
       if (occ < 1) return ws_fail(WS_ERR_CUDA, "beam kernel does not fit on an SM (smem %zu)", smem);
@@ -771,7 +770,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
         ba.sq_in = queues + (size_t)WS_NUM_TIERS * slots; ba.sq_count = ctrl + WS_NUM_TIERS; ba.sq_head = ctrl + 8 + WS_NUM_TIERS;
       }
       ba.out_ids = dids; ba.out_dists = ddists; ba.decode = plan.use_decode ? idx->d_decode : nullptr; ba.pad_id = plan.pad_id;
-#define WS_LB(KQ_, M_) { cudaError_t _e = warp_tier ? ws_launch_beam_warp_t<KQ_, M_>(exact_rows, wide, grid, smem, st, ba) : ws_launch_beam_t<KQ_, M_>(large, grid, smem, st, ba); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "beam kernel launch (tier %d): %s", t, cudaGetErrorString(_e)); }
+#define WS_LB(KQ_, M_) { cudaError_t _e = warp_tier ? ws_launch_beam_warp_t<KQ_, M_>(exact_rows, wide, grid, smem, st, ba) : ws_launch_beam_t<KQ_, M_>(exact_rows, large, grid, smem, st, ba); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "beam kernel launch (tier %d): %s", t, cudaGetErrorString(_e)); }
       {
         WsKernelScope ks(idx, 1 + t);
         WS_DISPATCH_KQ(kq, idx->metric, WS_LB);
@@ -1019,7 +1018,7 @@ int ws_build_graphs(ws_index* idx, uint32_t ngraphs, const uint64_t* starts, con
   WS_NEED_DEVICE(idx);
   if (idx->finalized) return ws_fail(WS_ERR_STATE, "index already finalized");
   if (!starts || !counts || !nodes_out || ngraphs == 0) return ws_fail(WS_ERR_BADARG, "null/empty argument");
-  if (max_degree == 0 || max_degree > 128) return ws_fail(WS_ERR_BADARG, "max_degree %u unsupported (1..128)", max_degree);
+  if (max_degree == 0 || max_degree > 64) return ws_fail(WS_ERR_BADARG, "max_degree %u unsupported (1..64)", max_degree);
   if (beam_l < 1 || beam_l > 1024) return ws_fail(WS_ERR_BADARG, "build beam L=%u outside 1..1024", beam_l);
   const uint32_t R = (max_degree + 3u) & ~3u;
   if (idx->R == 0) idx->R = R;
