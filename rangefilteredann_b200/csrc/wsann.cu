@@ -117,6 +117,7 @@ struct ws_index {
   int64_t opt_warp_tiers = 1;    // use the warp-per-task kernels for beams <= 128
   int64_t opt_warp_hash = 2048;
   int64_t opt_warp_scan = 1;     // warp-per-task scan kernel for k <= 128
+  int64_t opt_warp256 = 0;       // keep escalated beams 129..256 on the warp kernel (else: CTA tier)
   int64_t opt_fuse_scan = 0;     // let the first warp-tier beam launch drain the scan queue too (measured neutral)  // visited-table entries per warp in those kernels
   int64_t opt_build_expand = 1;  // nodes expanded per step while BUILDING graphs
   uint64_t build_stats[4] = {0, 0, 0, 0};  // inserts, visited, dist_cmps, overflow re-prunes  // smem visited-table entries per unit of beam capacity
@@ -717,13 +718,21 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
     const uint32_t E = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(8, idx->opt_expand));
     uint32_t cand_cap = 64;
     while (cand_cap < E * idx->R) cand_cap <<= 1;
+    // active tiers, in order; a task that outgrows tier i re-queues itself for tier i+1 of this list
+    int tiers[WS_NUM_TIERS];
+    int ntiers = 0;
     for (int t = first_tier; t < WS_NUM_TIERS; t++) {
+      if (t == 2 && t != first_tier && !idx->opt_warp256) continue;  // escalate 128 -> CTA tier directly
+      if (ntiers > 0 && (int64_t)kBeamTierCaps[tiers[ntiers - 1]] >= qp.postfiltering_max_beam) break;  // nothing can need more
+      tiers[ntiers++] = t;
+    }
+    for (int ti = 0; ti < ntiers; ti++) {
+      const int t = tiers[ti];
+      const int t_next = ti + 1 < ntiers ? tiers[ti + 1] : -1;
       const bool large = (t == WS_NUM_TIERS - 1);
       const bool warp_tier = t < WS_NUM_WARP_TIERS;
       const bool wide = t == 2;  // the 256-beam instantiation of the warp kernel
       const uint32_t beam_cap = large ? kBeamCapLarge : kBeamTierCaps[t];
-      if (t > first_tier && (int64_t)kBeamTierCaps[t - 1] >= qp.postfiltering_max_beam)
-        break;  // no task can need a beam this large
       uint32_t hash_entries = 0;
       if (warp_tier) {
         hash_entries = (uint32_t)idx->opt_warp_hash * (wide ? 2 : 1);
@@ -750,8 +759,8 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
       ba.tasks = (WsTask*)idx->tasks.p; ba.res_keys = (uint64_t*)idx->res_keys.p; ba.res_cnt = (uint32_t*)idx->res_cnt.p;
       ba.k = k;
       ba.q_in = queues + (size_t)t * slots; ba.q_in_count = ctrl + t; ba.q_head = ctrl + 8 + t;
-      ba.q_out = !large ? queues + (size_t)(t + 1) * slots : nullptr;
-      ba.q_out_count = !large ? ctrl + t + 1 : nullptr;
+      ba.q_out = t_next >= 0 ? queues + (size_t)t_next * slots : nullptr;
+      ba.q_out_count = t_next >= 0 ? ctrl + t_next : nullptr;
       ba.beam_cap = beam_cap; ba.hash_mask = hash_entries ? hash_entries - 1 : 0; ba.cand_cap = cand_cap;
       ba.expand = E; ba.skip_query_id = (int32_t)idx->opt_skip_query_id;
       ba.max_beam = qp.postfiltering_max_beam; ba.final_mult = qp.final_beam_multiply;
@@ -1267,6 +1276,8 @@ int ws_index_set_option(ws_index* idx, const char* name, int64_t value) {
     idx->opt_scan_chunk = value;
   } else if (s == "warp_tiers") {
     idx->opt_warp_tiers = value != 0;
+  } else if (s == "warp256") {
+    idx->opt_warp256 = value != 0;
   } else if (s == "fuse_scan") {
     idx->opt_fuse_scan = value != 0;
   } else if (s == "warp_scan") {
