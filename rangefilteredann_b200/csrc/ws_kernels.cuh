@@ -108,6 +108,7 @@ struct WsBeamArgs {
   uint32_t* bitmap;        // GLOBAL_SEEN: [gridDim.x][bitmap_words]
   uint64_t bitmap_words;
   unsigned long long* stats;
+  uint32_t min_tasks;      // warp tiers fed by escalation: below this many queued tasks, hand them all to q_out
   // optional: brute-force scan tasks of the same batch, drained by the same warps once the graph
   // queue is empty (warp tiers only; null otherwise)
   const uint32_t* sq_in;
@@ -927,6 +928,16 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, (CS <= 7 ? WS_WARP_MINB
   const int R = (int)A.R;
   const unsigned lt = (1u << lane) - 1u;
   const bool leader = tl == 0;
+
+  // A handful of escalated (long) tasks is better served by the CTA-per-task tier, where eight
+  // warps share one expansion; a warp per task only pays off when there are enough of them.
+  if (A.min_tasks != 0 && A.q_out != nullptr && *A.q_in_count < A.min_tasks) {
+    if (blockIdx.x == 0) {
+      const uint32_t cnt = *A.q_in_count;
+      for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) A.q_out[atomicAdd(A.q_out_count, 1u)] = A.q_in[i];
+    }
+    return;
+  }
 
   for (;;) {
     uint32_t t = 0;

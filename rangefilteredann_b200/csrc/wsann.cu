@@ -117,7 +117,8 @@ struct ws_index {
   int64_t opt_warp_tiers = 1;    // use the warp-per-task kernels for beams <= 128
   int64_t opt_warp_hash = 2048;
   int64_t opt_warp_scan = 1;     // warp-per-task scan kernel for k <= 128
-  int64_t opt_warp256 = 0;       // keep escalated beams 129..256 on the warp kernel (else: CTA tier)
+  int64_t opt_warp256 = 1;       // escalated beams 129..256: warp kernel when many tasks are queued, CTA tier otherwise
+  int64_t opt_warp256_min = 384; // ... threshold on the number of queued tasks
   int64_t opt_fuse_scan = 0;     // let the first warp-tier beam launch drain the scan queue too (measured neutral)  // visited-table entries per warp in those kernels
   int64_t opt_build_expand = 1;  // nodes expanded per step while BUILDING graphs
   uint64_t build_stats[4] = {0, 0, 0, 0};  // inserts, visited, dist_cmps, overflow re-prunes  // smem visited-table entries per unit of beam capacity
@@ -774,6 +775,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
         ba.bitmap = (uint32_t*)idx->bitmap.p;
       }
       ba.stats = idx->d_stats;
+      ba.min_tasks = (wide && t != first_tier) ? (uint32_t)idx->opt_warp256_min : 0u;
       ba.sq_in = nullptr; ba.sq_count = nullptr; ba.sq_head = nullptr;
       if (fuse_scan && t == first_tier) {  // this launch also drains the scan queue
         ba.sq_in = queues + (size_t)WS_NUM_TIERS * slots; ba.sq_count = ctrl + WS_NUM_TIERS; ba.sq_head = ctrl + 8 + WS_NUM_TIERS;
@@ -1278,6 +1280,8 @@ int ws_index_set_option(ws_index* idx, const char* name, int64_t value) {
     idx->opt_warp_tiers = value != 0;
   } else if (s == "warp256") {
     idx->opt_warp256 = value != 0;
+  } else if (s == "warp256_min") {
+    idx->opt_warp256_min = value < 0 ? 0 : value;
   } else if (s == "fuse_scan") {
     idx->opt_fuse_scan = value != 0;
   } else if (s == "warp_scan") {
