@@ -108,6 +108,7 @@ struct WsBeamArgs {
   uint32_t* bitmap;        // GLOBAL_SEEN: [gridDim.x][bitmap_words]
   uint64_t bitmap_words;
   unsigned long long* stats;
+  uint32_t hash16;         // warp tiers: visited table holds 16-bit tags (ws_seen_warp2_h16)
   uint32_t min_tasks;      // warp tiers fed by escalation: below this many queued tasks, hand them all to q_out
   // optional: brute-force scan tasks of the same batch, drained by the same warps once the graph
   // queue is empty (warp tiers only; null otherwise)
@@ -646,7 +647,7 @@ __global__ void ws_fill_kernel(uint4* p, size_t n16) {
 #define WS_BEAM_PREFETCH 1  // 1: L2-prefetch the candidate rows beyond the first register batch; 2: also survivors' adjacency rows
 #endif
 #ifndef WS_WARP_MINBLOCKS
-#define WS_WARP_MINBLOCKS 5  // resident CTAs per SM the warp kernels are register-budgeted for
+#define WS_WARP_MINBLOCKS 6  // resident CTAs per SM the warp kernels are register-budgeted for
 #endif
 
 __device__ __forceinline__ bool ws_seen_warp(volatile int* table, uint32_t mask, int id) {
@@ -751,6 +752,36 @@ __device__ __forceinline__ void ws_seen_warp2(volatile int* table, uint32_t mask
   if (pend1) table[h1] = id1;
 }
 
+// 16-bit variant: the table is indexed by the id's low bits (identity hash), so a slot only has
+// to remember the id's high bits plus the probe offset it was stored at — exact membership in
+// half the shared memory.  Valid while id < 2^(bits+12), i.e. nodes of up to 8 M points with
+// 2048 slots; larger nodes use the 32-bit table.
+__device__ __forceinline__ void ws_seen_warp2_h16(volatile unsigned short* table, uint32_t mask, int bits, int id0,
+                                                  bool& keep0, int id1, bool& keep1) {
+  const uint32_t h0 = (uint32_t)id0 & mask, h1 = (uint32_t)id1 & mask;
+  const uint32_t t0 = ((uint32_t)id0 >> bits) << 3, t1 = ((uint32_t)id1 >> bits) << 3;
+  bool pend0 = keep0, pend1 = keep1;
+#pragma unroll 1
+  for (int p = 0; p < WS_HASH_PROBES; p++) {
+    if (!__any_sync(0xffffffffu, pend0 || pend1)) break;
+    const uint32_t s0 = (h0 + p) & mask, s1 = (h1 + p) & mask;
+    const uint32_t v0 = pend0 ? table[s0] : 0u;
+    const bool hit0 = pend0 && v0 == (t0 | p), empty0 = pend0 && v0 == 0xFFFFu;
+    if (empty0) table[s0] = (unsigned short)(t0 | p);
+    keep0 = keep0 && !hit0;
+    pend0 = pend0 && !hit0 && !empty0;
+    __syncwarp();
+    const uint32_t v1 = pend1 ? table[s1] : 0u;
+    const bool hit1 = pend1 && v1 == (t1 | p), empty1 = pend1 && v1 == 0xFFFFu;
+    if (empty1) table[s1] = (unsigned short)(t1 | p);
+    keep1 = keep1 && !hit1;
+    pend1 = pend1 && !hit1 && !empty1;
+    __syncwarp();
+  }
+  if (pend0) table[h0] = (unsigned short)t0;  // probe window full: evict
+  if (pend1) table[h1] = (unsigned short)t1;
+}
+
 // ascending bitonic sort of 32 keys, one per lane
 __device__ __forceinline__ void ws_warp_sort32(uint64_t& k0, int lane) {
 #pragma unroll
@@ -766,8 +797,8 @@ __device__ __forceinline__ void ws_warp_sort32(uint64_t& k0, int lane) {
 }
 
 // shared memory one warp needs (bytes)
-__host__ __device__ inline size_t ws_warp_smem_bytes(uint32_t cap, uint32_t hash_entries) {
-  return (size_t)cap * 8 + 64 * 8 * 2 + 64 * 4 * 2 + (size_t)hash_entries * 4;
+__host__ __device__ inline size_t ws_warp_smem_bytes(uint32_t cap, uint32_t hash_entries, uint32_t hash16) {
+  return (size_t)cap * 8 + 64 * 8 * 2 + 64 * 4 * 2 + (size_t)hash_entries * (hash16 ? 2 : 4);
 }
 
 template <int STEPS>
@@ -915,13 +946,16 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, (CS <= 7 ? WS_WARP_MINB
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tl = lane & (WS_TEAM - 1), team = lane / WS_TEAM;  // 4 teams per warp
   const uint32_t CAP = A.beam_cap;
-  unsigned char* base = ws_smem + ws_warp_smem_bytes(CAP, A.hash_mask + 1) * warp;
+  unsigned char* base = ws_smem + ws_warp_smem_bytes(CAP, A.hash_mask + 1, A.hash16) * warp;
   uint64_t* fr = reinterpret_cast<uint64_t*>(base);  // [CAP] frontier, updated in place
   uint64_t* sk = fr + CAP;                           // [64] candidates under the cutoff
   uint64_t* sk2 = sk + 64;                           // [64] sorted, de-duplicated
   int* cpos = reinterpret_cast<int*>(sk2 + 64);      // [64] insertion ranks
   int* cid = cpos + 64;                              // [64] kept neighbour ids
-  volatile int* hash = cid + 64;                     // [hash_mask + 1]
+  volatile int* hash = cid + 64;                     // [hash_mask + 1] ids, or 16-bit tags (A.hash16)
+  volatile unsigned short* hash16 = reinterpret_cast<volatile unsigned short*>(cid + 64);
+  const bool h16 = A.hash16 != 0;
+  const int hbits = 32 - __clz(A.hash_mask);         // log2(entries)
 
   const int dpad4 = A.dpad >> 2;
   const int K = (int)A.k;
@@ -971,13 +1005,19 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, (CS <= 7 ? WS_WARP_MINB
       const int B = (int)beam;
 
       // ---- beam_search (beamSearch.h:51-184), QP.beamSize = QP.k = B, start = local id 0
-      for (int i = lane; i <= (int)A.hash_mask; i += 32) hash[i] = -1;
+      if (h16) {  // 0xFFFF = empty; cleared two slots per store
+        for (int i = lane; i <= (int)(A.hash_mask >> 1); i += 32) hash[i] = -1;
+      } else {
+        for (int i = lane; i <= (int)A.hash_mask; i += 32) hash[i] = -1;
+      }
       {
         const float d0 = ws_team_dist_nv<KQ, METRIC, EXACT>(vbase_tl, q, tl, dpad4);
         if (lane == 0) fr[0] = ws_key(d0, 0u);
       }
       __syncwarp();
-      if (lane == 0) ws_seen_warp(hash, A.hash_mask, 0);
+      if (lane == 0) {  // the start point counts as seen
+        if (h16) hash16[0] = 0; else hash[ws_hash32(0u) & A.hash_mask] = 0;
+      }
       __syncwarp();
       int n = 1, scan_from = 0;
       unsigned long long nvis = 0, ncmp = 1;
@@ -1008,7 +1048,8 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, (CS <= 7 ? WS_WARP_MINB
         }
         bool keep0 = nb0 >= 0 && nb0 != skip_id;
         bool keep1 = nb1 >= 0 && nb1 != skip_id;
-        ws_seen_warp2(hash, A.hash_mask, nb0, keep0, nb1, keep1);
+        if (h16) ws_seen_warp2_h16(hash16, A.hash_mask, hbits, nb0, keep0, nb1, keep1);
+        else ws_seen_warp2(hash, A.hash_mask, nb0, keep0, nb1, keep1);
         const unsigned bal0 = __ballot_sync(0xffffffffu, keep0), bal1 = __ballot_sync(0xffffffffu, keep1);
         const int m0 = __popc(bal0), m = m0 + __popc(bal1);
         if (m == 0) { scan_from = pick + 1; continue; }

@@ -117,6 +117,7 @@ struct ws_index {
   int64_t opt_warp_tiers = 1;    // use the warp-per-task kernels for beams <= 128
   int64_t opt_warp_hash = 2048;
   int64_t opt_warp_scan = 1;     // warp-per-task scan kernel for k <= 128
+  int64_t opt_hash16 = 1;        // 16-bit visited tags in the warp tiers when node sizes allow
   int64_t opt_warp256 = 1;       // escalated beams 129..256: warp kernel when many tasks are queued, CTA tier otherwise
   int64_t opt_warp256_min = 384; // ... threshold on the number of queued tasks
   int64_t opt_fuse_scan = 0;     // let the first warp-tier beam launch drain the scan queue too (measured neutral)  // visited-table entries per warp in those kernels
@@ -735,8 +736,13 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
       const bool wide = t == 2;  // the 256-beam instantiation of the warp kernel
       const uint32_t beam_cap = large ? kBeamCapLarge : kBeamTierCaps[t];
       uint32_t hash_entries = 0;
+      // 16-bit visited tags need id < 2^(log2(entries) + 12)
+      uint32_t hash16 = 0;
       if (warp_tier) {
         hash_entries = (uint32_t)idx->opt_warp_hash * (wide ? 2 : 1);
+        uint32_t hb = 0;
+        while ((1u << hb) < hash_entries) hb++;
+        hash16 = (idx->opt_hash16 && (uint64_t)idx->max_node_count <= (1ull << (hb + 12))) ? 1u : 0u;
       } else if (!large) {
         hash_entries = 1024;
         while (hash_entries < (uint64_t)idx->opt_hash_factor * beam_cap) hash_entries <<= 1;
@@ -744,7 +750,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
       if (!warp_tier && idx->R > 64) return ws_fail(WS_ERR_BADARG, "graphs with max_degree > 64 are not supported by the query kernels");
       size_t smem;
       if (warp_tier)
-        smem = (size_t)WS_WARPS_PER_CTA * ws_warp_smem_bytes(beam_cap, hash_entries);
+        smem = (size_t)WS_WARPS_PER_CTA * ws_warp_smem_bytes(beam_cap, hash_entries, hash16);
       else
         smem = (size_t)beam_cap * 8 + 64 * 8 * 2 + 64 * 4 * 2 + (size_t)hash_entries * 4;
       if (smem > idx->smem_optin) return ws_fail(WS_ERR_BADARG, "beam tier %d needs %zu B of shared memory (> %zu)", t, smem, idx->smem_optin);
@@ -775,6 +781,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
         ba.bitmap = (uint32_t*)idx->bitmap.p;
       }
       ba.stats = idx->d_stats;
+      ba.hash16 = hash16;
       ba.min_tasks = (wide && t != first_tier) ? (uint32_t)idx->opt_warp256_min : 0u;
       ba.sq_in = nullptr; ba.sq_count = nullptr; ba.sq_head = nullptr;
       if (fuse_scan && t == first_tier) {  // this launch also drains the scan queue
@@ -1278,6 +1285,8 @@ int ws_index_set_option(ws_index* idx, const char* name, int64_t value) {
     idx->opt_scan_chunk = value;
   } else if (s == "warp_tiers") {
     idx->opt_warp_tiers = value != 0;
+  } else if (s == "hash16") {
+    idx->opt_hash16 = value != 0;
   } else if (s == "warp256") {
     idx->opt_warp256 = value != 0;
   } else if (s == "warp256_min") {

@@ -172,11 +172,23 @@ def test_cta_tiers_match_warp_tiers(tiny):
     finally:
         h.set_option("warp_tiers", 1)
     try:
+        h.set_option("hash16", 0)  # 32-bit visited table in the warp tiers
+        for method in ("fenwick", "optimized_postfilter"):
+            tiny.assert_identical(method, q, w, beam=40, mult=2)
+    finally:
+        h.set_option("hash16", 1)
+    try:
+        h.set_option("fuse_scan", 1)
+        for method in ("fenwick", "three_split"):
+            tiny.assert_identical(method, q, w, beam=10, mult=1)
+    finally:
+        h.set_option("fuse_scan", 0)
+    try:
         h.set_option("fuse_scan", 0)  # separate scan launch instead of draining scans in the beam launch
         for method in ("fenwick", "three_split", "optimized_postfilter"):
             tiny.assert_identical(method, q, w, beam=10, mult=1)
     finally:
-        h.set_option("fuse_scan", 1)
+        h.set_option("fuse_scan", 0)
     try:
         h.set_option("warp_scan", 0)  # CTA-per-task scan kernel instead of the warp-per-task one
         h.set_option("fuse_scan", 0)
@@ -188,7 +200,7 @@ def test_cta_tiers_match_warp_tiers(tiny):
         hp.set_option("warp_scan", 1)
     finally:
         h.set_option("warp_scan", 1)
-        h.set_option("fuse_scan", 1)
+        h.set_option("fuse_scan", 0)
     try:
         h.set_option("warp_hash", 256)  # a saturated visited table may only cost recomputation
         tiny.assert_identical("optimized_postfilter", q, w, beam=60, mult=2)
