@@ -647,7 +647,7 @@ __global__ void ws_fill_kernel(uint4* p, size_t n16) {
 #define WS_BEAM_PREFETCH 1  // 1: L2-prefetch the candidate rows beyond the first register batch; 2: also survivors' adjacency rows
 #endif
 #ifndef WS_WARP_MINBLOCKS
-#define WS_WARP_MINBLOCKS 6  // resident CTAs per SM the warp kernels are register-budgeted for
+#define WS_WARP_MINBLOCKS 7  // resident CTAs per SM the warp kernels are register-budgeted for
 #endif
 
 __device__ __forceinline__ bool ws_seen_warp(volatile int* table, uint32_t mask, int id) {
