@@ -333,13 +333,6 @@ def run_engine(args, rank, world, local_rank):
     launches = h.launches() - l0
     clk = clocks.stop()
 
-    # brute-force rows of the fractions answered by the prefilter method (their own scan launches)
-    h.reset_stats()
-    for p in POWERS:
-        if ops[p][0] == "prefilter":
-            runner.launch_dev(p, ops[p])
-    per_step_prefilter_points = h.stats()["scan_points"]
-
     # ---- per-kernel times + counters over the same K steps (roofline)
     h.set_option("profile_kernels", 1)
     h.reset_stats()
@@ -404,14 +397,8 @@ def run_engine(args, rank, world, local_rank):
     # graph search: visited * R*4 + dist_cmps * d_pad*4 + (beam*4 per search)
     beam_bytes = stats["visited"] * 64 * 4 + stats["dist_cmps"] * dpad_bytes + stats["beam_sum"] * 4
     scan_bytes = stats["scan_points"] * dpad_bytes
-    # fenwick edge scans are drained by the beam warp kernel's own warps (same launch), so
-    # their bytes belong to that launch; only the prefilter's scan launches are timed apart
-    pre_scan_points = per_step_prefilter_points * args.steps
-    fused_scan_bytes = max(0, stats["scan_points"] - pre_scan_points) * dpad_bytes
-    beam_bytes += fused_scan_bytes
-    scan_bytes -= fused_scan_bytes
     if beam_ms >= scan_ms:
-        dom, dom_ms, dom_bytes, dom_launches = "ws_beam_warp_kernel (+ CTA tiers)", beam_ms, beam_bytes, beam_launches
+        dom, dom_ms, dom_bytes, dom_launches = "ws_beam_warp_kernel (+ ws_beam_cta2_kernel tail tiers)", beam_ms, beam_bytes, beam_launches
     else:
         dom, dom_ms, dom_bytes = "ws_scan_kernel", scan_ms, scan_bytes
         dom_launches = ktimes["scan"]["launches"]
