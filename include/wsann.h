@@ -201,6 +201,8 @@ int ws_index_reset_stats(ws_index* idx);
 int ws_index_launch_count(const ws_index* idx, uint64_t* out);
 /* tuning knobs: "emulate_query_id_skip" (beamSearch.h:128 `a == p.id()`, default 1),
  * "scan_chunk" (rows per brute-force task), "profile_kernels", "warp_tiers", "warp_hash",
+ * "gemm_prefilter" (tensor-core prefilter: 0 never, 1 whenever eligible, 2 auto = host-sampled mean
+ * window >= "gemm_min_window"), "gemm_items", "gemm_min_tiles",
  * "warp_scan", "fuse_scan", "hash_factor", "build_expand_width" (nodes expanded per step by
  * the device-side graph BUILDER; the query kernels always expand one node per step, as the
  * reference does) */
@@ -209,8 +211,9 @@ int ws_index_hbm_bytes(const ws_index* idx, uint64_t* out);
 /* With option "profile_kernels" = 1 every kernel launch is bracketed by CUDA events on the
  * index stream.  Returns accumulated milliseconds / launch counts per kernel kind:
  * 0 decompose, 1..3 beam search warp-per-task tiers (beam <= 64 / 128 / 256), 4 beam search
- * CTA-per-task tier (1024), 5 beam search large tier, 6 scan, 7 merge.
- * ms_out / launches_out are [8]. */
+ * CTA-per-task tier (1024), 5 beam search large tier, 6 scan, 7 merge, 8 tensor-core prefilter
+ * sweep, 9 its plan + pack kernels, 10 its re-rank kernel, 11 spare.
+ * ms_out / launches_out are [12]. */
 int ws_index_kernel_times(ws_index* idx, double* ms_out, uint64_t* launches_out, int reset);
 
 /* Host-side evaluation of the window→task decomposition, same code the device runs

@@ -1,6 +1,7 @@
 """Builds the two native artefacts of the package, in-tree:
 
-  libwsann_cuda.so                 nvcc, sm_100a only  (csrc/wsann.cu: kernels + C ABI)
+  libwsann_cuda.so                 nvcc, sm_100a only  (csrc/wsann.cu: kernels + C ABI; csrc/ws_gemm.cu: the
+                                   tcgen05 prefilter kernels — separate objects under build/)
   _window_ann_b200.cpython-*.so    g++ + pybind11      (csrc/host/python_bindings.cpp; re-exported as
                                    `window_ann` by window_ann.py)
 
@@ -38,16 +39,34 @@ def _sources(*dirs: str) -> list[str]:
     return out
 
 
+CUDA_UNITS = ("wsann.cu", "ws_gemm.cu")  # one object each, compiled in parallel, linked into LIB
+OBJ_DIR = os.path.join(HERE, "build")
+
+
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
     srcs = _sources(CSRC, os.path.join(os.path.dirname(HERE), "include"))
-    if not force and _newer(LIB, srcs):
-        return LIB
+    headers = [s for s in srcs if not s.endswith(".cu")]
+    lib_out = os.environ.get("WSANN_LIB_OUT", LIB)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("WSANN_NVCC_EXTRA", "").split(), "-o", os.environ.get("WSANN_LIB_OUT", LIB),
-           os.path.join(CSRC, "wsann.cu")]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.run(cmd, check=True)
+    extra = os.environ.get("WSANN_NVCC_EXTRA", "").split()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    procs, objs = [], []
+    for unit in CUDA_UNITS:
+        src = os.path.join(CSRC, unit)
+        obj = os.path.join(OBJ_DIR, unit.replace(".cu", ".o"))
+        objs.append(obj)
+        if not force and not extra and _newer(obj, [src, *headers]):
+            continue
+        cmd = [nvcc, *flags, *extra, "-c", "-o", obj, src]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
+    if procs or force or not _newer(lib_out, objs):
+        subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib_out, *objs], check=True)
     return LIB
 
 

@@ -156,11 +156,12 @@ class Handle:
     def set_option(self, name: str, value: int):
         check(lib().ws_index_set_option(self.raw, name.encode(), int(value)), "ws_index_set_option")
 
-    KERNEL_KINDS = ("decompose", "beam_warp64", "beam_warp128", "beam_warp256", "beam1024", "beam_large", "scan", "merge")
+    KERNEL_KINDS = ("decompose", "beam_warp64", "beam_warp128", "beam_warp256", "beam1024", "beam_large", "scan", "merge",
+                    "gemm_sweep", "gemm_plan_pack", "gemm_rerank", "spare")
 
     def kernel_times(self, reset=True) -> dict:
-        ms = np.zeros(8, np.float64)
-        n = np.zeros(8, np.uint64)
+        ms = np.zeros(len(self.KERNEL_KINDS), np.float64)
+        n = np.zeros(len(self.KERNEL_KINDS), np.uint64)
         check(lib().ws_index_kernel_times(self.raw, ptr(ms), ptr(n), 1 if reset else 0), "ws_index_kernel_times")
         return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(self.KERNEL_KINDS) if n[i]}
 

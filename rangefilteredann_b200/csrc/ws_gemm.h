@@ -1,0 +1,131 @@
+// ws_gemm.h — argument structs and launchers of the tensor-core prefilter (kernels: ws_gemm.cu).
+#pragma once
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define WSG_TILE_M 128       // queries per group = TMEM lanes
+#define WSG_TILE_N 128       // points per tile   = TMEM columns per accumulator stage
+#define WSG_KBLK 32          // fp32 columns per 128-byte swizzle block
+#define WSG_KBLK_BYTES (WSG_TILE_N * 128)  // one operand block: 128 rows x 128 B = 16 KB
+#define WSG_MAX_KB 4         // dpad <= 128
+#define WSG_B_STAGES 8       // ring of point blocks (128 KB)
+#define WSG_ACC_STAGES 4     // 4 x 128 columns = all 512 TMEM columns
+#define WSG_KTOP 16          // k <= 16 on this path
+#define WSG_CAND_CAP 512     // survivors kept per (item, query)
+#define WSG_RING 16          // per-query ring of fresh scores waiting to be folded into the running top-k
+#define WSG_EPI_WARPS 16     // 4 per TMEM lane quarter: each takes 32 of a tile's 128 columns
+#define WSG_THREADS 576      // warp 0: TMA producer, warp 1: MMA issuer, warps 2-17: epilogue
+#define WSG_PLAN_THREADS 1024
+#define WSG_MAX_ROWS 16384   // queries per plan (one CTA sorts them in shared memory)
+#define WSG_MAX_SPLITS 256   // chunks of the label axis
+#define WSG_RR_LIST 1024     // survivors one re-rank warp can hold
+
+struct WsGemmItem {
+  uint32_t row0;    // first sorted row of the query group (multiple of 128)
+  uint32_t p0;      // first point (arena rank) of the item's sweep
+  uint32_t ntiles;  // 128-point tiles
+  uint32_t pend;    // end of the item's slice of the label axis (the last tile may reach past it)
+};
+
+struct WsGemmNormArgs {
+  const float* vecs;
+  uint64_t n;
+  uint32_t dpad;
+  uint32_t npad;      // entries of norms (n rounded up + one tile); the tail is +inf
+  int metric;
+  float* norms;       // L2: |x|^2; MIPS: 0
+  uint32_t* max_sq;   // float bits of max |x|^2 (non-negative floats order like uints)
+};
+
+struct WsGemmPlanArgs {
+  const float* windows;   // [nq][2] of this slice
+  const float* labels;
+  uint64_t n;
+  uint32_t nq;            // <= WSG_MAX_ROWS
+  uint32_t rows_pad;      // nq rounded up to 128
+  uint32_t* perm;         // [rows_pad] sorted row -> query of the slice (0xFFFFFFFF: padding row)
+  uint32_t* row_a;        // [rows_pad]
+  uint32_t* row_b;        // [rows_pad]
+  WsGemmItem* items;
+  uint32_t* nitems;       // out
+  uint32_t max_items;
+  uint32_t* group_items;  // [groups][WSG_MAX_SPLITS] item indices of each group
+  uint32_t* group_cnt;    // [groups]
+  uint32_t target_items;
+  uint32_t min_tiles;
+  uint32_t* overflow;
+};
+
+struct WsGemmPackArgs {
+  const float* queries;   // [nq][dim] of this slice
+  uint32_t dim, dpad, rows_pad;
+  int metric;
+  const uint32_t* perm;
+  const uint32_t* max_sq;
+  float* qpack;           // [rows_pad][dpad]
+  float* slack;           // [rows_pad]  2E
+  float* qnorm;           // [rows_pad]  |q|^2
+};
+
+// seed thresholds: exact distances of a small even sample of each query's window
+struct WsGemmSeedArgs {
+  const float* vecs;
+  const float* queries;
+  uint32_t dim, dpad, rows_pad, k;
+  const uint32_t* perm;
+  const uint32_t* row_a;
+  const uint32_t* row_b;
+  const float* slack;
+  const float* qnorm;
+  float* thr0;            // [rows_pad]
+};
+
+struct WsGemmArgs {
+  const WsGemmItem* items;
+  const uint32_t* nitems;
+  const uint32_t* row_a;
+  const uint32_t* row_b;
+  const float* slack;
+  const float* thr0;    // seed threshold per sorted row (ws_gemm_seed_kernel)
+  const float* norms;
+  uint64_t* cand;       // [max_items][WSG_CAND_CAP][128]  (score~, point) keys
+  uint32_t* cand_cnt;   // [max_items][128]   0xFFFFFFFF: overflow
+  float* cand_thr;      // [max_items][128]   final threshold
+  uint32_t nkb;         // 32-column blocks per row
+  uint32_t k;
+};
+
+struct WsGemmRerankArgs {
+  const float* vecs;
+  const float* queries;    // [nq][dim] of this slice
+  uint32_t dim, dpad;
+  uint32_t rows_pad;
+  const uint32_t* perm;
+  const uint32_t* row_a;
+  const uint32_t* row_b;
+  const uint32_t* group_items;
+  const uint32_t* group_cnt;
+  const uint64_t* cand;
+  const uint32_t* cand_cnt;
+  const float* cand_thr;
+  uint32_t k;
+  uint32_t* out_ids;       // [nq][k] of this slice
+  float* out_dists;
+  const uint32_t* decode;
+  uint32_t pad_id;
+  uint64_t* res_keys;      // scratch [rows_pad][k] (ws_scan_task writes partial rows there)
+  uint32_t* res_cnt;       // scratch [rows_pad]
+  unsigned long long* stats;
+  unsigned long long* gstats;  // [0] survivors re-ranked, [1] queries that fell back to the exact scan
+};
+
+// launchers (defined in ws_gemm.cu, its own translation unit)
+size_t wsg_topk_smem_bytes();
+cudaError_t wsg_init_attributes();
+cudaError_t wsg_launch_norm(int grid, cudaStream_t st, const WsGemmNormArgs& a);
+cudaError_t wsg_launch_plan(uint32_t nsort, cudaStream_t st, const WsGemmPlanArgs& a);
+cudaError_t wsg_launch_pack(cudaStream_t st, const WsGemmPackArgs& a);
+cudaError_t wsg_launch_seed(int kq, int metric, bool exact, cudaStream_t st, const WsGemmSeedArgs& a);
+cudaError_t wsg_launch_topk(int grid, cudaStream_t st, const CUtensorMap& tm_a, const CUtensorMap& tm_b, const WsGemmArgs& a);
+cudaError_t wsg_launch_rerank(int kq, int metric, bool exact, cudaStream_t st, const WsGemmRerankArgs& a);

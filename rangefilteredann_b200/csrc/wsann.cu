@@ -14,6 +14,7 @@
 #include "../../include/wsann.h"
 #include "ws_kernels.cuh"
 #include "ws_build.cuh"
+#include "ws_gemm.h"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <random>
@@ -59,7 +60,8 @@ static const uint32_t kBeamTierCaps[4] = {64, 128, 256, 1024};
 static const uint32_t kBeamCapLarge = 12288;                // global-bitmap tier
 static const uint32_t kMaxK = WS_TOPK_BUF / 2;
 static const size_t kAdjSlabBytes = 256ull << 20;
-#define WS_NUM_KERNEL_KINDS 8  // 0 decompose, 1-3 warp beam tiers 64/128/256, 4 CTA beam tier 1024, 5 beam large, 6 scan, 7 merge
+#define WS_NUM_KERNEL_KINDS 12  // 0 decompose, 1-3 warp beam tiers 64/128/256, 4 CTA beam tier 1024, 5 beam large, 6 scan, 7 merge,
+                                // 8 tensor-core prefilter sweep, 9 its plan+pack, 10 its re-rank, 11 spare
 
 struct WsDevBuf {
   void* p = nullptr;
@@ -129,6 +131,19 @@ struct ws_index {
       bitmap, flush;
   unsigned long long* d_stats = nullptr;
   uint64_t launches = 0;
+
+  // tensor-core prefilter (ws_gemm.cuh)
+  int64_t opt_gemm = 2;          // 0 never, 1 whenever eligible, 2 auto (host-sampled mean window >= opt_gemm_min_window)
+  int64_t opt_gemm_min_window = 2048;
+  int64_t opt_gemm_items = 0;    // target work items per plan (0: 4 per SM)
+  int64_t opt_gemm_min_tiles = 8;
+  bool gemm_ready = false;
+  WsDevBuf g_norms, g_ctrl, g_perm, g_row_a, g_row_b, g_items, g_group_items, g_group_cnt, g_qpack, g_slack, g_cand,
+      g_cand_cnt, g_cand_thr, g_res_keys, g_res_cnt, g_thr0, g_qnorm;
+  CUtensorMap g_tm_b{};
+  CUtensorMap g_tm_a{};
+  const void* g_tm_a_ptr = nullptr;
+  uint32_t g_tm_a_rows = 0;
 
   // optional per-kernel CUDA-event timing (ws_index_kernel_times)
   int64_t opt_profile = 0;
@@ -297,7 +312,10 @@ void ws_index_destroy(ws_index* idx) {
     for (void* p : idx->build_allocs) cudaFree(p);
     for (void* p : idx->geom_dev_allocs) cudaFree(p);
     WsDevBuf* bufs[] = {&idx->tasks, &idx->res_keys, &idx->res_cnt, &idx->counts, &idx->queues, &idx->ctrl,
-                        &idx->d_queries, &idx->d_windows, &idx->d_ids, &idx->d_dists, &idx->bitmap, &idx->flush};
+                        &idx->d_queries, &idx->d_windows, &idx->d_ids, &idx->d_dists, &idx->bitmap, &idx->flush,
+                        &idx->g_norms, &idx->g_ctrl, &idx->g_perm, &idx->g_row_a, &idx->g_row_b, &idx->g_items,
+                        &idx->g_group_items, &idx->g_group_cnt, &idx->g_qpack, &idx->g_slack, &idx->g_cand,
+                        &idx->g_cand_cnt, &idx->g_cand_thr, &idx->g_res_keys, &idx->g_res_cnt, &idx->g_thr0, &idx->g_qnorm};
     for (WsDevBuf* b : bufs) cudaFree(b->p);
     for (cudaEvent_t e : idx->ev_pool) cudaEventDestroy(e);
     if (idx->ev0) cudaEventDestroy(idx->ev0);
@@ -603,6 +621,155 @@ static int ws_pick_kq(uint32_t dpad) {
   return 32;
 }
 
+// ------------------------------------------------------------------------------------------
+// tensor-core prefilter (ws_gemm.cuh): host orchestration
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*ws_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// libcuda is not linked (the library must load on machines without a driver): the encoder
+// comes from the runtime's driver entry point table.
+static int ws_tmap_encoder(ws_tmap_encode_fn* out) {
+  static ws_tmap_encode_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    WS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr));
+    if (!p || qr != cudaDriverEntryPointSuccess) return ws_fail(WS_ERR_CUDA, "cuTensorMapEncodeTiled not available from this driver");
+    fn = (ws_tmap_encode_fn)p;
+  }
+  *out = fn;
+  return WS_OK;
+}
+
+// [rows][dpad] fp32 row-major -> boxes of 128 rows x 32 columns, 128-byte swizzle, zero fill
+static int ws_make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t dpad) {
+  ws_tmap_encode_fn enc;
+  WS_TRY(ws_tmap_encoder(&enc));
+  cuuint64_t gdim[2] = {dpad, rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)dpad * sizeof(float)};
+  cuuint32_t box[2] = {WSG_KBLK, WSG_TILE_N};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return ws_fail(WS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %llu x %u", (int)r, (unsigned long long)rows, dpad);
+  return WS_OK;
+}
+
+static bool ws_gemm_eligible(const ws_index* idx, uint32_t k) {
+  return idx->label_sorted && k <= WSG_KTOP && idx->dpad <= WSG_MAX_KB * WSG_KBLK && idx->n >= 2 * WSG_TILE_N &&
+         idx->n < 0xFFFFFE00ull;
+}
+
+// one-time per index: |x|^2 table, max norm, tensor map of the arena
+static int ws_gemm_prepare(ws_index* idx) {
+  if (idx->gemm_ready) return WS_OK;
+  const uint64_t npad = idx->n + 2 * WSG_TILE_N;
+  WS_TRY(ws_ensure(idx, idx->g_norms, npad * sizeof(float)));
+  WS_TRY(ws_ensure(idx, idx->g_ctrl, 64 * sizeof(unsigned long long)));
+  WS_CUDA(cudaMemsetAsync(idx->g_ctrl.p, 0, 64 * sizeof(unsigned long long), idx->stream));
+  WsGemmNormArgs na;
+  na.vecs = idx->d_vecs; na.n = idx->n; na.dpad = idx->dpad; na.npad = (uint32_t)npad; na.metric = idx->metric;
+  na.norms = (float*)idx->g_norms.p; na.max_sq = (uint32_t*)idx->g_ctrl.p + 8;
+  WS_CUDA(wsg_launch_norm(idx->num_sms * 8, idx->stream, na));
+  idx->launches++;
+  WS_TRY(ws_make_tmap(&idx->g_tm_b, idx->d_vecs, idx->n, idx->dpad));
+  idx->gemm_ready = true;
+  return WS_OK;
+}
+
+// PrefilterIndex::batch_search (prefiltering.h:124-146) for a whole batch on the tensor cores.
+// dq/dw/dids/ddists are device pointers; work is only enqueued on the index stream.
+static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw, uint64_t nq, uint32_t k, uint32_t* dids,
+                                 float* ddists, const uint32_t* decode, uint32_t pad_id, uint32_t* overflow_flag) {
+  WS_TRY(ws_gemm_prepare(idx));
+  cudaStream_t st = idx->stream;
+  const uint32_t max_rows = (uint32_t)std::min<uint64_t>(WSG_MAX_ROWS, (nq + 127) / 128 * 128);
+  const uint32_t max_groups = max_rows / 128;
+  const uint32_t target = (uint32_t)(idx->opt_gemm_items > 0 ? idx->opt_gemm_items : 4 * (int64_t)idx->num_sms);
+  const uint32_t max_items = target + 2 * max_groups + 8;
+  WS_TRY(ws_ensure(idx, idx->g_perm, max_rows * sizeof(uint32_t)));
+  WS_TRY(ws_ensure(idx, idx->g_row_a, max_rows * sizeof(uint32_t)));
+  WS_TRY(ws_ensure(idx, idx->g_row_b, max_rows * sizeof(uint32_t)));
+  WS_TRY(ws_ensure(idx, idx->g_items, max_items * sizeof(WsGemmItem)));
+  WS_TRY(ws_ensure(idx, idx->g_group_items, (size_t)max_groups * WSG_MAX_SPLITS * sizeof(uint32_t)));
+  WS_TRY(ws_ensure(idx, idx->g_group_cnt, max_groups * sizeof(uint32_t)));
+  WS_TRY(ws_ensure(idx, idx->g_qpack, (size_t)max_rows * idx->dpad * sizeof(float)));
+  WS_TRY(ws_ensure(idx, idx->g_slack, max_rows * sizeof(float)));
+  WS_TRY(ws_ensure(idx, idx->g_thr0, max_rows * sizeof(float)));
+  WS_TRY(ws_ensure(idx, idx->g_qnorm, max_rows * sizeof(float)));
+  WS_TRY(ws_ensure(idx, idx->g_cand, (size_t)max_items * WSG_CAND_CAP * WSG_TILE_M * sizeof(uint64_t)));
+  WS_TRY(ws_ensure(idx, idx->g_cand_cnt, (size_t)max_items * WSG_TILE_M * sizeof(uint32_t)));
+  WS_TRY(ws_ensure(idx, idx->g_cand_thr, (size_t)max_items * WSG_TILE_M * sizeof(float)));
+  WS_TRY(ws_ensure(idx, idx->g_res_keys, (size_t)max_rows * k * sizeof(uint64_t)));
+  WS_TRY(ws_ensure(idx, idx->g_res_cnt, max_rows * sizeof(uint32_t)));
+  if (idx->g_tm_a_ptr != idx->g_qpack.p || idx->g_tm_a_rows != max_rows) {
+    WS_TRY(ws_make_tmap(&idx->g_tm_a, idx->g_qpack.p, max_rows, idx->dpad));
+    idx->g_tm_a_ptr = idx->g_qpack.p;
+    idx->g_tm_a_rows = max_rows;
+  }
+  const size_t gemm_smem = wsg_topk_smem_bytes();
+  if (gemm_smem > idx->smem_optin) return ws_fail(WS_ERR_CUDA, "tensor-core prefilter needs %zu B of shared memory (> %zu)", gemm_smem, idx->smem_optin);
+  static bool attr_set = false;
+  if (!attr_set) {
+    WS_CUDA(wsg_init_attributes());
+    attr_set = true;
+  }
+  unsigned long long* gctrl = (unsigned long long*)idx->g_ctrl.p;  // [0] survivors, [1] fallbacks, u32 view: [8] max |x|^2, [10] nitems
+  uint32_t* gctrl32 = (uint32_t*)idx->g_ctrl.p;
+  const int kq = ws_pick_kq(idx->dpad);
+  const bool exact_rows = (uint32_t)kq * WS_TEAM * 4 == idx->dpad;
+
+  for (uint64_t q0 = 0; q0 < nq; q0 += WSG_MAX_ROWS) {
+    const uint32_t sn = (uint32_t)std::min<uint64_t>(WSG_MAX_ROWS, nq - q0);
+    const uint32_t rows_pad = (sn + 127) / 128 * 128;
+    uint32_t nsort = 128;
+    while (nsort < rows_pad) nsort <<= 1;
+    WsGemmPlanArgs pa;
+    pa.windows = dw + 2 * q0; pa.labels = idx->d_labels; pa.n = idx->n; pa.nq = sn; pa.rows_pad = rows_pad;
+    pa.perm = (uint32_t*)idx->g_perm.p; pa.row_a = (uint32_t*)idx->g_row_a.p; pa.row_b = (uint32_t*)idx->g_row_b.p;
+    pa.items = (WsGemmItem*)idx->g_items.p; pa.nitems = gctrl32 + 10; pa.max_items = max_items;
+    pa.group_items = (uint32_t*)idx->g_group_items.p; pa.group_cnt = (uint32_t*)idx->g_group_cnt.p;
+    pa.target_items = target; pa.min_tiles = (uint32_t)std::max<int64_t>(1, idx->opt_gemm_min_tiles);
+    pa.overflow = overflow_flag;
+    WsGemmPackArgs ka;
+    ka.queries = dq + q0 * idx->dim; ka.dim = idx->dim; ka.dpad = idx->dpad; ka.rows_pad = rows_pad; ka.metric = idx->metric;
+    ka.perm = pa.perm; ka.max_sq = gctrl32 + 8; ka.qpack = (float*)idx->g_qpack.p; ka.slack = (float*)idx->g_slack.p;
+    ka.qnorm = (float*)idx->g_qnorm.p;
+    WsGemmSeedArgs sa;
+    sa.vecs = idx->d_vecs; sa.queries = ka.queries; sa.dim = idx->dim; sa.dpad = idx->dpad; sa.rows_pad = rows_pad; sa.k = k;
+    sa.perm = pa.perm; sa.row_a = pa.row_a; sa.row_b = pa.row_b; sa.slack = ka.slack; sa.qnorm = ka.qnorm; sa.thr0 = (float*)idx->g_thr0.p;
+    {
+      WsKernelScope ks(idx, 9);
+      WS_CUDA(wsg_launch_plan(nsort, st, pa));
+      WS_CUDA(wsg_launch_pack(st, ka));
+      WS_CUDA(wsg_launch_seed(kq, idx->metric, exact_rows, st, sa));
+      idx->launches += 2;
+    }
+    WsGemmArgs ga;
+    ga.items = pa.items; ga.nitems = pa.nitems; ga.row_a = pa.row_a; ga.row_b = pa.row_b; ga.slack = ka.slack; ga.thr0 = sa.thr0;
+    ga.norms = (const float*)idx->g_norms.p; ga.cand = (uint64_t*)idx->g_cand.p; ga.cand_cnt = (uint32_t*)idx->g_cand_cnt.p;
+    ga.cand_thr = (float*)idx->g_cand_thr.p; ga.nkb = (idx->dpad + WSG_KBLK - 1) / WSG_KBLK; ga.k = k;
+    {
+      WsKernelScope ks(idx, 8);
+      WS_CUDA(wsg_launch_topk(idx->num_sms, st, idx->g_tm_a, idx->g_tm_b, ga));
+    }
+    WsGemmRerankArgs ra;
+    ra.vecs = idx->d_vecs; ra.queries = ka.queries; ra.dim = idx->dim; ra.dpad = idx->dpad; ra.rows_pad = rows_pad;
+    ra.perm = pa.perm; ra.row_a = pa.row_a; ra.row_b = pa.row_b; ra.group_items = pa.group_items; ra.group_cnt = pa.group_cnt;
+    ra.cand = ga.cand; ra.cand_cnt = ga.cand_cnt; ra.cand_thr = ga.cand_thr; ra.k = k;
+    ra.out_ids = dids + q0 * k; ra.out_dists = ddists + q0 * k; ra.decode = decode; ra.pad_id = pad_id;
+    ra.res_keys = (uint64_t*)idx->g_res_keys.p; ra.res_cnt = (uint32_t*)idx->g_res_cnt.p; ra.stats = idx->d_stats; ra.gstats = gctrl;
+    {
+      WsKernelScope ks(idx, 10);
+      WS_CUDA(wsg_launch_rerank(kq, idx->metric, exact_rows, st, ra));
+    }
+  }
+  return WS_OK;
+}
+
 struct WsBatchPlan {
   int mode;
   int32_t node;
@@ -674,6 +841,25 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
   WS_CUDA(cudaMemsetAsync(ctrl, 0, 64 * sizeof(uint32_t), st));
   uint32_t* queues = (uint32_t*)idx->queues.p;
 
+  // ---- prefilter batches with large windows: dense query x slice contraction on the tensor cores
+  bool use_gemm = false;
+  if (plan.mode == WS_MODE_PREFILTER && idx->opt_gemm != 0 && ws_gemm_eligible(idx, k)) {
+    if (idx->opt_gemm == 1) use_gemm = true;
+    else if (!dev_ptrs && nq >= 256) {  // auto: mean window size of a host-side sample
+      const std::vector<float>& L = idx->h_labels;
+      const uint64_t step = std::max<uint64_t>(1, nq / 64);
+      double sum = 0; uint64_t cnt = 0;
+      for (uint64_t i = 0; i < nq; i += step, cnt++) {
+        const uint64_t a = std::lower_bound(L.begin(), L.end(), windows[2 * i]) - L.begin();
+        const uint64_t b = std::lower_bound(L.begin(), L.end(), windows[2 * i + 1]) - L.begin();
+        sum += b > a ? (double)(b - a) : 0.0;
+      }
+      use_gemm = cnt > 0 && sum / (double)cnt >= (double)idx->opt_gemm_min_window;
+    }
+  }
+  if (use_gemm) {
+    WS_TRY(ws_run_prefilter_gemm(idx, dq, dw, nq, k, dids, ddists, plan.use_decode ? idx->d_decode : nullptr, plan.pad_id, ctrl + 16));
+  } else {
   // ---- tiers: which launch takes fresh graph tasks
   const int kq = ws_pick_kq(idx->dpad);
   const int lowest_tier = idx->opt_warp_tiers ? 0 : WS_NUM_WARP_TIERS;
@@ -845,6 +1031,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
     }
     WS_CUDA(cudaGetLastError());
   }
+  }  // !use_gemm
 
   if (!dev_ptrs) {
     uint32_t h_overflow = 0;
@@ -1301,6 +1488,17 @@ int ws_index_set_option(ws_index* idx, const char* name, int64_t value) {
   } else if (s == "build_expand_width") {
     if (value < 1 || value > 8) return ws_fail(WS_ERR_BADARG, "build_expand_width must be 1..8");
     idx->opt_build_expand = value;
+  } else if (s == "gemm_prefilter") {
+    if (value < 0 || value > 2) return ws_fail(WS_ERR_BADARG, "gemm_prefilter must be 0 (never), 1 (always when eligible) or 2 (auto)");
+    idx->opt_gemm = value;
+  } else if (s == "gemm_min_window") {
+    idx->opt_gemm_min_window = value < 0 ? 0 : value;
+  } else if (s == "gemm_items") {
+    if (value < 0 || value > 65536) return ws_fail(WS_ERR_BADARG, "gemm_items must be 0..65536");
+    idx->opt_gemm_items = value;
+  } else if (s == "gemm_min_tiles") {
+    if (value < 1) return ws_fail(WS_ERR_BADARG, "gemm_min_tiles must be >= 1");
+    idx->opt_gemm_min_tiles = value;
   } else if (s == "profile_kernels") {
     idx->opt_profile = value != 0;
   } else if (s == "hash_factor") {
