@@ -7,8 +7,9 @@
 Metric: QPS at recall@10 >= 0.95 over the 17 filter fractions 2^-16..2^0 (k = 10, 10 000
 queries per fraction).  One "step" = one pass over all 17 fractions: for each fraction the
 batch of `nq` queries is answered by the fastest (method, beam, final_multiply) operating
-point that reaches recall@10 >= 0.95 — methods: prefilter, range-filter tree ("fenwick"),
-optimized postfilter — chosen in an untimed sweep, exactly the pareto rule of the
+point that reaches recall@10 >= 0.95 — methods: prefilter (streaming scan, or the tensor-core
+sweep "prefilter_tc" — same rows), range-filter tree ("fenwick"), optimized postfilter — chosen
+in an untimed sweep, exactly the pareto rule of the
 reference's plots (experiments/plot.py:14-28).  value = queries answered per second.
 
   value      inputs resident in HBM, CUDA-event timed on the engine's stream
@@ -214,7 +215,10 @@ class EngineRunner:
 
     def launch_dev(self, power, op):
         method, beam, mult = op
-        if method == "prefilter":
+        if method in ("prefilter", "prefilter_tc"):
+            # "prefilter_tc": the same PrefilterIndex::batch_search, answered by the tensor-core sweep +
+            # fp32 re-rank (csrc/ws_gemm.cu) instead of the streaming scan; rows are bit-identical
+            self.h.set_option("gemm_prefilter", 1 if method == "prefilter_tc" else 0)
             self.h.prefilter_batch(self.dq, self.dwin[power], self.nq, K, self.dids, self.ddists, device_ptrs=True)
         else:
             qp = self.capi.query_params(k=K, beam=beam, final_multiply=mult)
@@ -245,6 +249,10 @@ def choose_operating_points(runner: EngineRunner, gts, rank):
         r = recall_at_k(runner.fetch(), gts[p])
         ms = runner.time_dev(p, ("prefilter", 0, 0))
         per_method["prefilter"] = dict(op=("prefilter", 0, 0), recall=r, ms=ms)
+        runner.launch_dev(p, ("prefilter_tc", 0, 0))
+        r = recall_at_k(runner.fetch(), gts[p])
+        ms = runner.time_dev(p, ("prefilter_tc", 0, 0))
+        per_method["prefilter_tc"] = dict(op=("prefilter_tc", 0, 0), recall=r, ms=ms)
         for method in ("fenwick", "optimized_postfilter"):
             best = None
             for mult in (MULTS if method == "optimized_postfilter" else [1]):
@@ -354,9 +362,10 @@ def run_engine(args, rank, world, local_rank):
     def step_e2e():
         for p in POWERS:
             method, beam, mult = ops[p]
-            if method == "prefilter":
+            if method in ("prefilter", "prefilter_tc"):
                 ids = np.empty((cfg["nq"], K), np.uint32)
                 dd = np.empty((cfg["nq"], K), np.float32)
+                h.set_option("gemm_prefilter", 1 if method == "prefilter_tc" else 0)
                 h.prefilter_batch(hq, hw[p], cfg["nq"], K, ids, dd)
             else:
                 qp = eng.QueryParams(K, beam, 1.35, 10_000_000, 10_000, mult, 10000, None, False)
@@ -397,6 +406,23 @@ def run_engine(args, rank, world, local_rank):
     # graph search: visited * R*4 + dist_cmps * d_pad*4 + (beam*4 per search)
     beam_bytes = stats["visited"] * 64 * 4 + stats["dist_cmps"] * dpad_bytes + stats["beam_sum"] * 4
     scan_bytes = stats["scan_points"] * dpad_bytes
+    # tensor-core prefilter sweep: 2*d flops per (query, in-window point); the points are
+    # counted from the windows of the fractions whose operating point is prefilter_tc
+    gemm_ms = ktimes.get("gemm_sweep", {}).get("ms", 0.0)
+    gemm_pairs = sum(int(np.sum((np.searchsorted(np.sort(labels), windows[p][:, 1]) -
+                                 np.searchsorted(np.sort(labels), windows[p][:, 0])).clip(min=0)))
+                     for p in POWERS if ops[p][0] == "prefilter_tc") * args.steps
+    gemm_flops = 2.0 * cfg["d"] * gemm_pairs
+    tensor_peak = float(peaks.get("bf16_tflops", 1590.0))
+    gemm_info = None
+    if gemm_ms > 0:
+        gemm_info = {"kernel": "ws_gemm_topk_kernel (tcgen05 kind::tf32)", "bound": "tensor",
+                     "achieved": round(gemm_flops / (gemm_ms / 1000.0) / 1e12, 1), "peak": tensor_peak, "unit": "TFLOP/s",
+                     "frac": round(gemm_flops / (gemm_ms / 1000.0) / 1e12 / tensor_peak, 4),
+                     "peak_source": "measured dense bf16 (MEASURED_PEAKS.json bf16_tflops); the kernel runs tf32, whose "
+                                    "dense rate is half of bf16",
+                     "ms_per_step": round(gemm_ms / args.steps, 4),
+                     "flops_per_step": gemm_flops / args.steps}
     if beam_ms >= scan_ms:
         dom, dom_ms, dom_bytes, dom_launches = "ws_beam_warp_kernel (+ ws_beam_cta2_kernel tail tiers)", beam_ms, beam_bytes, beam_launches
     else:
@@ -409,7 +435,8 @@ def run_engine(args, rank, world, local_rank):
                 "ms_per_launch": round(dom_ms / max(1, dom_launches), 4),
                 "beam_GBps": round(beam_bytes / (beam_ms / 1000.0) / 1e9, 1) if beam_ms > 0 else None,
                 "scan_GBps": round(scan_bytes / (scan_ms / 1000.0) / 1e9, 1) if scan_ms > 0 else None,
-                "kernel_ms_per_step": {kname: round(v["ms"] / args.steps, 4) for kname, v in ktimes.items()}}
+                "kernel_ms_per_step": {kname: round(v["ms"] / args.steps, 4) for kname, v in ktimes.items()},
+                "tensor_prefilter": gemm_info}
 
     cpu = cpu_baseline(args, cfg, data, queries, labels, windows, gts, table, ops) if not args.no_cpu else None
 
@@ -486,6 +513,8 @@ def cpu_baseline(args, cfg, data, queries, labels, windows, gts, table, ops):
     for p in POWERS:
         best = None
         for method, v in table[p].items():
+            if method == "prefilter_tc":  # the reference has one prefilter implementation (timed as "prefilter")
+                continue
             ns = min(args.cpu_sample, cfg["nq"])
             t_probe, _ = ref_time(ref, tree, pre, queries, windows[p], v["op"], min(64, ns))
             per_q = t_probe / min(64, ns)

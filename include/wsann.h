@@ -202,7 +202,7 @@ int ws_index_launch_count(const ws_index* idx, uint64_t* out);
 /* tuning knobs: "emulate_query_id_skip" (beamSearch.h:128 `a == p.id()`, default 1),
  * "scan_chunk" (rows per brute-force task), "profile_kernels", "warp_tiers", "warp_hash",
  * "gemm_prefilter" (tensor-core prefilter: 0 never, 1 whenever eligible, 2 auto = host-sampled mean
- * window >= "gemm_min_window"), "gemm_items", "gemm_min_tiles",
+ * window >= "gemm_min_window"), "gemm_items", "gemm_min_tiles", "gemm_chunk_mb",
  * "warp_scan", "fuse_scan", "hash_factor", "build_expand_width" (nodes expanded per step by
  * the device-side graph BUILDER; the query kernels always expand one node per step, as the
  * reference does) */
@@ -212,7 +212,7 @@ int ws_index_hbm_bytes(const ws_index* idx, uint64_t* out);
  * index stream.  Returns accumulated milliseconds / launch counts per kernel kind:
  * 0 decompose, 1..3 beam search warp-per-task tiers (beam <= 64 / 128 / 256), 4 beam search
  * CTA-per-task tier (1024), 5 beam search large tier, 6 scan, 7 merge, 8 tensor-core prefilter
- * sweep, 9 its plan + pack kernels, 10 its re-rank kernel, 11 spare.
+ * sweep, 9 its bounds + plan + pack kernels, 10 its re-rank kernel, 11 its seed-threshold kernel.
  * ms_out / launches_out are [12]. */
 int ws_index_kernel_times(ws_index* idx, double* ms_out, uint64_t* launches_out, int reset);
 

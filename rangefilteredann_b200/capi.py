@@ -157,7 +157,7 @@ class Handle:
         check(lib().ws_index_set_option(self.raw, name.encode(), int(value)), "ws_index_set_option")
 
     KERNEL_KINDS = ("decompose", "beam_warp64", "beam_warp128", "beam_warp256", "beam1024", "beam_large", "scan", "merge",
-                    "gemm_sweep", "gemm_plan_pack", "gemm_rerank", "spare")
+                    "gemm_sweep", "gemm_plan_pack", "gemm_rerank", "gemm_seed")
 
     def kernel_times(self, reset=True) -> dict:
         ms = np.zeros(len(self.KERNEL_KINDS), np.float64)

@@ -184,6 +184,16 @@ __device__ __forceinline__ uint32_t wsg_bound(const float* labels, uint64_t n, f
   return (uint32_t)l;
 }
 
+// window -> [a,b) for every query of the slice (one thread each; the plan CTA only sorts)
+__global__ void __launch_bounds__(128) ws_gemm_bounds_kernel(WsGemmPlanArgs A) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.nq) return;
+  uint32_t a = wsg_bound(A.labels, A.n, A.windows[2 * (size_t)i]);
+  uint32_t b = wsg_bound(A.labels, A.n, A.windows[2 * (size_t)i + 1]);
+  if (b <= a) { a = 0; b = 0; }
+  A.qa[i] = a; A.qb[i] = b;
+}
+
 __global__ void __launch_bounds__(WSG_PLAN_THREADS) ws_gemm_plan_kernel(WsGemmPlanArgs A) {
   extern __shared__ uint64_t s_keys[];  // [pow2 >= rows_pad]
   __shared__ uint32_t s_ga[WSG_MAX_ROWS / 128], s_gb[WSG_MAX_ROWS / 128];
@@ -193,12 +203,11 @@ __global__ void __launch_bounds__(WSG_PLAN_THREADS) ws_gemm_plan_kernel(WsGemmPl
   const int tid = threadIdx.x;
   int nsort = 128;
   while ((uint32_t)nsort < A.rows_pad) nsort <<= 1;
-  // 1. window starts; empty windows sort behind everything else
+  // 1. keys = (window start, query); empty windows sort behind everything else
   for (int i = tid; i < nsort; i += WSG_PLAN_THREADS) {
     uint64_t key = WS_KEY_MAX;
     if ((uint32_t)i < A.nq) {
-      const uint32_t a = wsg_bound(A.labels, A.n, A.windows[2 * (size_t)i]);
-      const uint32_t b = wsg_bound(A.labels, A.n, A.windows[2 * (size_t)i + 1]);
+      const uint32_t a = A.qa[i], b = A.qb[i];
       key = ((uint64_t)(b > a ? a : 0xFFFFFFFEu) << 32) | (uint32_t)i;
     }
     s_keys[i] = key;
@@ -220,36 +229,37 @@ __global__ void __launch_bounds__(WSG_PLAN_THREADS) ws_gemm_plan_kernel(WsGemmPl
       __syncthreads();
     }
   }
-  // 3. sorted rows
-  for (uint32_t r = tid; r < A.rows_pad; r += WSG_PLAN_THREADS) {
-    const uint64_t key = s_keys[r];
-    uint32_t q = 0xFFFFFFFFu, a = 0, b = 0;
-    if (key != WS_KEY_MAX) {
-      q = (uint32_t)key;
-      a = wsg_bound(A.labels, A.n, A.windows[2 * (size_t)q]);
-      b = wsg_bound(A.labels, A.n, A.windows[2 * (size_t)q + 1]);
-      if (b <= a) { a = 0; b = 0; }
-    }
-    A.perm[r] = q; A.row_a[r] = a; A.row_b[r] = b;
-  }
-  __syncthreads();
-  // 4. group extents
+  // 3. sorted rows, 4. group extents (one warp per group of 128 rows)
   const uint32_t groups = A.rows_pad / 128;
-  if ((uint32_t)tid < groups) {
+  for (uint32_t g = tid >> 5; g < groups; g += WSG_PLAN_THREADS / 32) {
     uint32_t ga = 0xFFFFFFFFu, gb = 0;
-    for (int i = 0; i < 128; i++) {
-      const uint32_t a = A.row_a[tid * 128 + i], b = A.row_b[tid * 128 + i];
+    for (uint32_t r = g * 128 + (tid & 31); r < (g + 1) * 128; r += 32) {
+      const uint64_t key = s_keys[r];
+      uint32_t q = 0xFFFFFFFFu, a = 0, b = 0;
+      if (key != WS_KEY_MAX) {
+        q = (uint32_t)key;
+        a = A.qa[q]; b = A.qb[q];
+      }
+      A.perm[r] = q; A.row_a[r] = a; A.row_b[r] = b;
       if (b > a) { ga = min(ga, a); gb = max(gb, b); }
     }
-    if (gb == 0) ga = 0;
-    s_ga[tid] = ga; s_gb[tid] = gb;
-    atomicAdd(&s_total, (unsigned long long)((gb - ga + WSG_TILE_N - 1) / WSG_TILE_N));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ga = min(ga, __shfl_xor_sync(0xffffffffu, ga, o));
+      gb = max(gb, __shfl_xor_sync(0xffffffffu, gb, o));
+    }
+    if ((tid & 31) == 0) {
+      if (gb == 0) ga = 0;
+      s_ga[g] = ga; s_gb[g] = gb;
+      atomicAdd(&s_total, (unsigned long long)((gb - ga + WSG_TILE_N - 1) / WSG_TILE_N));
+    }
   }
   __syncthreads();
   // 5. chunk the label axis so that about target_items items of equal size come out
   if (tid == 0) {
     unsigned long long per = (s_total + A.target_items - 1) / A.target_items;
     if (per < A.min_tiles) per = A.min_tiles;
+    if (per > A.max_tiles) per = A.max_tiles;  // the slices swept concurrently must stay L2-resident
     unsigned long long pts = per * WSG_TILE_N;
     const unsigned long long floor_pts = (A.n + WSG_MAX_SPLITS - 1) / WSG_MAX_SPLITS;
     if (pts < floor_pts) pts = floor_pts;
@@ -379,45 +389,66 @@ struct WsGemmSmem {
   float thr[WSG_TILE_M];                         // per query: k-th best score~ so far + slack
   uint32_t cnt[WSG_TILE_M];                      // survivors appended so far
   uint32_t head[WSG_TILE_M];                     // fresh scores pushed into the ring so far
+  uint32_t warps_done;                           // epilogue warps that finished an item (monotonic)
+  uint32_t pad2_[3];
   uint32_t ring[WSG_RING][WSG_TILE_M];           // fresh scores (float bits), consumed by the owner thread
 };
 #define WSG_SENT 0xFFFFFFFFu
 
-// Owner thread of a query: fold the fresh scores other warps pushed into the ring into the
-// running top-KTOP (ascending, registers) and publish the new threshold.  Slots are taken with
+// Tiles of an item may be swept in any order.  Every group sweeps the same slice of the label
+// axis at the same time (that is what makes the points L2 hits), but if all of them started at
+// the slice's first tile, every SM would ask the same few L2 slices for the same lines at the
+// same moment.  Each group therefore starts at its own offset and wraps around.
+__device__ __forceinline__ uint32_t wsg_rotation(const WsGemmItem& item) {
+  return (uint32_t)(((item.row0 >> 7) * 2654435761u) >> 8) % item.ntiles;
+}
+__device__ __forceinline__ uint32_t wsg_tile(uint32_t t, uint32_t rot, uint32_t ntiles) {
+  const uint32_t x = t + rot;
+  return x >= ntiles ? x - ntiles : x;
+}
+
+// Threshold thread of a query: fold the fresh scores the epilogue warps pushed into the ring into
+// the running top-KTOP (ascending, registers) and publish the new threshold.  Slots are taken with
 // an atomic exchange, so a score is folded at most once; a slot whose value has not landed yet
 // (or was overwritten on wrap-around) is simply skipped — that can only leave thr looser.
-__device__ __forceinline__ void wsg_flush(float (&tk)[WSG_KTOP], WsGemmSmem* S, int lrow, uint32_t& last_head, int k,
+__device__ __forceinline__ bool wsg_flush(float (&tk)[WSG_KTOP], WsGemmSmem* S, int lrow, uint32_t& last_head, int k,
                                           float slack, float& thr, float thr0) {
   const uint32_t h = *(volatile uint32_t*)&S->head[lrow];
   const uint32_t nnew = min(h - last_head, (uint32_t)WSG_RING);
-  if (!__any_sync(0xffffffffu, nnew != 0)) return;
+  if (!__any_sync(0xffffffffu, nnew != 0)) return false;
+  // tk holds KTOP - k phantom entries of -inf in front, so the k-th best real score is always tk[KTOP-1]
+  float kth = tk[WSG_KTOP - 1];
+  bool changed = false;
 #pragma unroll 1
   for (uint32_t i = 0; i < WSG_RING; i++) {
     if (!__any_sync(0xffffffffu, i < nnew)) break;
     uint32_t bits = WSG_SENT;
     if (i < nnew) bits = atomicExch(&S->ring[(h - 1 - i) & (WSG_RING - 1)][lrow], WSG_SENT);
     float v = bits == WSG_SENT ? __int_as_float(0x7f800000) : __uint_as_float(bits);
+    // scores between the k-th best and the threshold pass the filter but cannot move the top-k
+    if (!__any_sync(0xffffffffu, v < kth)) continue;
+    changed = true;
 #pragma unroll
     for (int x = 0; x < WSG_KTOP; x++) {
       const float lo = fminf(tk[x], v);
       v = fmaxf(tk[x], v);
       tk[x] = lo;
     }
+    kth = tk[WSG_KTOP - 1];
   }
   last_head = h;
-  float kth = tk[0];
-#pragma unroll
-  for (int x = 1; x < WSG_KTOP; x++) kth = (x == k - 1) ? tk[x] : kth;
-  thr = fminf(thr0, kth + slack);  // the seed threshold while fewer than k points have been seen
-  *(volatile float*)&S->thr[lrow] = thr;
+  if (changed) {
+    thr = fminf(thr0, kth + slack);  // the seed threshold while fewer than k points have been seen
+    *(volatile float*)&S->thr[lrow] = thr;
+  }
+  return true;
 }
 
 __global__ void __launch_bounds__(WSG_THREADS, 1)
 ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, WsGemmArgs A) {
   extern __shared__ unsigned char wsg_smem_raw[];
   // operand blocks need 1024-byte alignment (128B swizzle atoms)
-  unsigned char* base = (unsigned char*)(((uintptr_t)wsg_smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* base = wsg_smem_raw + ((1024u - (wsg_smem_u32(wsg_smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = base;                                  // nkb x 16 KB, resident per item
   unsigned char* sB = base + WSG_MAX_KB * WSG_KBLK_BYTES;    // ring of 16 KB point blocks
   WsGemmSmem* S = (WsGemmSmem*)(sB + WSG_B_STAGES * WSG_KBLK_BYTES);
@@ -434,6 +465,7 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     wsg_prefetch_tmap(&tmB);
   }
   if (warp == 1) wsg_tmem_alloc(&S->tmem_base, WSG_ACC_STAGES * WSG_TILE_N);
+  if (threadIdx.x == 64) S->warps_done = 0;
   wsg_tc_fence_before();
   __syncthreads();
   wsg_tc_fence_after();
@@ -450,8 +482,9 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (uint32_t kb = 0; kb < nkb; kb++)
           wsg_tma_load_2d(sA + kb * WSG_KBLK_BYTES, &tmA, &S->a_full, (int)(kb * WSG_KBLK), (int)item.row0);
         a_phase ^= 1;
+        const uint32_t rot = wsg_rotation(item);
         for (uint32_t t = 0; t < item.ntiles; t++) {
-          const int p = (int)(item.p0 + t * WSG_TILE_N);
+          const int p = (int)(item.p0 + wsg_tile(t, rot, item.ntiles) * WSG_TILE_N);
           for (uint32_t kb = 0; kb < nkb; kb++) {
             wsg_mbar_wait(&S->empty[stage], phase ^ 1);
             wsg_mbar_expect_tx(&S->full[stage], WSG_KBLK_BYTES);
@@ -491,51 +524,38 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         wsg_mma_commit(&S->a_empty);
       }
     }
-  } else {
+  } else if (warp < 2 + WSG_EPI_WARPS) {
     // ===== epilogue: 16 warps; a query is one TMEM lane, served by the four warps of its lane
-    // quarter, each scanning 32 of the tile's 128 columns.  The chunk-0 warp owns the query's
-    // running top-k (registers) and threshold; the others only filter and append. =====
+    // quarter, each scanning 32 of the tile's 128 columns: filter against the query's published
+    // threshold, append survivors, push their scores to the query's ring. =====
     const int e = warp - 2;
     const int quarter = warp & 3;               // the TMEM lane quarter this warp may read
     const int chunk = e >> 2;                   // its 32 columns of every tile
-    const bool owner = chunk == 0;
     const int lrow = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float INF = __int_as_float(0x7f800000);
-    const int k = (int)A.k;
     float* my_norm = S->wnorm[e];
     uint32_t acc = 0, acc_phase = 0;
     for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
       const WsGemmItem item = A.items[it];
       const uint32_t row = item.row0 + lrow;
-      // the query's window clipped to this item's slice of the label axis
-      const long long wa = max(A.row_a[row], item.p0), wb = min(A.row_b[row], item.pend);
-      const float slack = A.slack[row];
       uint64_t* cand = A.cand + (size_t)it * WSG_CAND_CAP * WSG_TILE_M + lrow;
-      float tk[WSG_KTOP];
-      float thr;
-      uint32_t last_head = 0;
-      const float thr0 = A.thr0[row];
-      thr = thr0;
-      if (owner) {
-#pragma unroll
-        for (int x = 0; x < WSG_KTOP; x++) tk[x] = INF;
-        S->thr[lrow] = thr0; S->cnt[lrow] = 0; S->head[lrow] = 0;
-#pragma unroll
-        for (int i = 0; i < WSG_RING; i++) S->ring[i][lrow] = WSG_SENT;
-      }
-      asm volatile("bar.sync 1, 512;" ::: "memory");  // per-query state reset, visible to the 16 epilogue warps
-      float nrm_next = __ldg(A.norms + item.p0 + chunk * 32 + lane);
+      const uint32_t rot = wsg_rotation(item);
+      // the query's window clipped to this item's slice of the label axis (ranks < 2^31)
+      const int wlo = (int)max(A.row_a[row], item.p0), whi = (int)min(A.row_b[row], item.pend);
+      asm volatile("bar.sync 1, 640;" ::: "memory");  // per-query state reset by the threshold warps
+      float nrm_next = __ldg(A.norms + item.p0 + rot * WSG_TILE_N + chunk * 32 + lane);
       for (uint32_t t = 0; t < item.ntiles; t++) {
-        const long long cbase = (long long)item.p0 + (long long)t * WSG_TILE_N + chunk * 32;
+        const int cbase = (int)(item.p0 + wsg_tile(t, rot, item.ntiles) * WSG_TILE_N + chunk * 32);
         __syncwarp();
         my_norm[lane] = nrm_next;
         __syncwarp();
-        if (t + 1 < item.ntiles) nrm_next = __ldg(A.norms + cbase + WSG_TILE_N + lane);
+        if (t + 1 < item.ntiles)
+          nrm_next = __ldg(A.norms + item.p0 + wsg_tile(t + 1, rot, item.ntiles) * WSG_TILE_N + chunk * 32 + lane);
         wsg_mbar_wait(&S->acc_full[acc], acc_phase);
         wsg_tc_fence_after();
-        const int lo = (int)max(0ll, min(32ll, wa - cbase));
-        const int hi = (int)max(0ll, min(32ll, wb - cbase));
+        const int lo = max(0, min(32, wlo - cbase));
+        const int hi = max(0, min(32, whi - cbase));
         if (__any_sync(0xffffffffu, hi > lo)) {
           const bool whole = __all_sync(0xffffffffu, lo == 0 && hi == 32);
           float s[32];
@@ -550,7 +570,7 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; j++) s[j] = (j >= lo && j < hi) ? s[j] : INF;
           }
-          if (!owner) thr = *(volatile float*)&S->thr[lrow];
+          const float thr = *(volatile float*)&S->thr[lrow];
           float m4[8];
 #pragma unroll
           for (int g = 0; g < 8; g++) m4[g] = fminf(fminf(s[4 * g], s[4 * g + 1]), fminf(s[4 * g + 2], s[4 * g + 3]));
@@ -575,16 +595,43 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         wsg_tc_fence_before();
         __syncwarp();
         if (lane == 0) wsg_mbar_arrive(&S->acc_empty[acc]);
-        if (owner) wsg_flush(tk, S, lrow, last_head, k, slack, thr, thr0);
         if (++acc == WSG_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
-      asm volatile("bar.sync 1, 512;" ::: "memory");  // every append of this item has been issued
-      if (owner) {
-        wsg_flush(tk, S, lrow, last_head, k, slack, thr, thr0);
-        const uint32_t c = S->cnt[lrow];
-        A.cand_cnt[(size_t)it * WSG_TILE_M + lrow] = c > WSG_CAND_CAP ? 0xFFFFFFFFu : c;
-        A.cand_thr[(size_t)it * WSG_TILE_M + lrow] = thr;
+      __syncwarp();
+      if (lane == 0) atomicAdd(&S->warps_done, 1u);
+      asm volatile("bar.sync 1, 640;" ::: "memory");  // every append of this item has been issued
+    }
+  } else {
+    // ===== threshold warps (4): thread = query.  Hold the query's running top-k of approximate
+    // scores in registers, fold what the epilogue warps push into the ring, publish
+    // thr = min(seed, k-th best + slack).  Off the accumulator pipeline on purpose: a slow fold never
+    // delays the release of a TMEM stage. =====
+    const int lrow = (warp - 2 - WSG_EPI_WARPS) * 32 + lane;
+    const float INF = __int_as_float(0x7f800000);
+    const int k = (int)A.k;
+    uint32_t seq = 0;
+    for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+      const uint32_t row = A.items[it].row0 + lrow;
+      const float slack = A.slack[row];
+      const float thr0 = A.thr0[row];
+      float tk[WSG_KTOP];
+#pragma unroll
+      for (int x = 0; x < WSG_KTOP; x++) tk[x] = x < WSG_KTOP - k ? -INF : INF;
+      float thr = thr0;
+      uint32_t last_head = 0;
+      S->thr[lrow] = thr0; S->cnt[lrow] = 0; S->head[lrow] = 0;
+#pragma unroll
+      for (int i = 0; i < WSG_RING; i++) S->ring[i][lrow] = WSG_SENT;
+      asm volatile("bar.sync 1, 640;" ::: "memory");
+      seq++;
+      while (*(volatile uint32_t*)&S->warps_done < seq * WSG_EPI_WARPS) {
+        if (!wsg_flush(tk, S, lrow, last_head, k, slack, thr, thr0)) __nanosleep(64);
       }
+      asm volatile("bar.sync 1, 640;" ::: "memory");
+      wsg_flush(tk, S, lrow, last_head, k, slack, thr, thr0);
+      const uint32_t c = S->cnt[lrow];
+      A.cand_cnt[(size_t)it * WSG_TILE_M + lrow] = c > WSG_CAND_CAP ? 0xFFFFFFFFu : c;
+      A.cand_thr[(size_t)it * WSG_TILE_M + lrow] = thr;
     }
   }
   wsg_tc_fence_before();
@@ -769,6 +816,7 @@ cudaError_t wsg_launch_norm(int grid, cudaStream_t st, const WsGemmNormArgs& a) 
   return cudaGetLastError();
 }
 cudaError_t wsg_launch_plan(uint32_t nsort, cudaStream_t st, const WsGemmPlanArgs& a) {
+  ws_gemm_bounds_kernel<<<(a.nq + 127) / 128, 128, 0, st>>>(a);
   ws_gemm_plan_kernel<<<1, WSG_PLAN_THREADS, nsort * sizeof(uint64_t), st>>>(a);
   return cudaGetLastError();
 }

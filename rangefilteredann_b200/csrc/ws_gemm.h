@@ -15,7 +15,7 @@
 #define WSG_CAND_CAP 512     // survivors kept per (item, query)
 #define WSG_RING 16          // per-query ring of fresh scores waiting to be folded into the running top-k
 #define WSG_EPI_WARPS 16     // 4 per TMEM lane quarter: each takes 32 of a tile's 128 columns
-#define WSG_THREADS 576      // warp 0: TMA producer, warp 1: MMA issuer, warps 2-17: epilogue
+#define WSG_THREADS 704      // warp 0: TMA producer, warp 1: MMA issuer, warps 2-17: epilogue, 18-21: thresholds
 #define WSG_PLAN_THREADS 1024
 #define WSG_MAX_ROWS 16384   // queries per plan (one CTA sorts them in shared memory)
 #define WSG_MAX_SPLITS 256   // chunks of the label axis
@@ -44,6 +44,8 @@ struct WsGemmPlanArgs {
   uint64_t n;
   uint32_t nq;            // <= WSG_MAX_ROWS
   uint32_t rows_pad;      // nq rounded up to 128
+  uint32_t* qa;           // [nq] scratch: window bounds per query (ws_gemm_bounds_kernel)
+  uint32_t* qb;
   uint32_t* perm;         // [rows_pad] sorted row -> query of the slice (0xFFFFFFFF: padding row)
   uint32_t* row_a;        // [rows_pad]
   uint32_t* row_b;        // [rows_pad]
@@ -54,6 +56,7 @@ struct WsGemmPlanArgs {
   uint32_t* group_cnt;    // [groups]
   uint32_t target_items;
   uint32_t min_tiles;
+  uint32_t max_tiles;
   uint32_t* overflow;
 };
 

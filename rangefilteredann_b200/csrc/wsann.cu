@@ -61,7 +61,7 @@ static const uint32_t kBeamCapLarge = 12288;                // global-bitmap tie
 static const uint32_t kMaxK = WS_TOPK_BUF / 2;
 static const size_t kAdjSlabBytes = 256ull << 20;
 #define WS_NUM_KERNEL_KINDS 12  // 0 decompose, 1-3 warp beam tiers 64/128/256, 4 CTA beam tier 1024, 5 beam large, 6 scan, 7 merge,
-                                // 8 tensor-core prefilter sweep, 9 its plan+pack, 10 its re-rank, 11 spare
+                                // 8 tensor-core prefilter sweep, 9 its bounds+plan+pack, 10 its re-rank, 11 its seed thresholds
 
 struct WsDevBuf {
   void* p = nullptr;
@@ -137,9 +137,10 @@ struct ws_index {
   int64_t opt_gemm_min_window = 2048;
   int64_t opt_gemm_items = 0;    // target work items per plan (0: 4 per SM)
   int64_t opt_gemm_min_tiles = 8;
+  int64_t opt_gemm_chunk_mb = 32; // largest slice of the label axis one work item sweeps
   bool gemm_ready = false;
   WsDevBuf g_norms, g_ctrl, g_perm, g_row_a, g_row_b, g_items, g_group_items, g_group_cnt, g_qpack, g_slack, g_cand,
-      g_cand_cnt, g_cand_thr, g_res_keys, g_res_cnt, g_thr0, g_qnorm;
+      g_cand_cnt, g_cand_thr, g_res_keys, g_res_cnt, g_thr0, g_qnorm, g_qa, g_qb;
   CUtensorMap g_tm_b{};
   CUtensorMap g_tm_a{};
   const void* g_tm_a_ptr = nullptr;
@@ -315,7 +316,7 @@ void ws_index_destroy(ws_index* idx) {
                         &idx->d_queries, &idx->d_windows, &idx->d_ids, &idx->d_dists, &idx->bitmap, &idx->flush,
                         &idx->g_norms, &idx->g_ctrl, &idx->g_perm, &idx->g_row_a, &idx->g_row_b, &idx->g_items,
                         &idx->g_group_items, &idx->g_group_cnt, &idx->g_qpack, &idx->g_slack, &idx->g_cand,
-                        &idx->g_cand_cnt, &idx->g_cand_thr, &idx->g_res_keys, &idx->g_res_cnt, &idx->g_thr0, &idx->g_qnorm};
+                        &idx->g_cand_cnt, &idx->g_cand_thr, &idx->g_res_keys, &idx->g_res_cnt, &idx->g_thr0, &idx->g_qnorm, &idx->g_qa, &idx->g_qb};
     for (WsDevBuf* b : bufs) cudaFree(b->p);
     for (cudaEvent_t e : idx->ev_pool) cudaEventDestroy(e);
     if (idx->ev0) cudaEventDestroy(idx->ev0);
@@ -660,7 +661,7 @@ static int ws_make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint32
 
 static bool ws_gemm_eligible(const ws_index* idx, uint32_t k) {
   return idx->label_sorted && k <= WSG_KTOP && idx->dpad <= WSG_MAX_KB * WSG_KBLK && idx->n >= 2 * WSG_TILE_N &&
-         idx->n < 0xFFFFFE00ull;
+         idx->n < 0x7FFFFE00ull;
 }
 
 // one-time per index: |x|^2 table, max norm, tensor map of the arena
@@ -689,7 +690,12 @@ static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw
   const uint32_t max_rows = (uint32_t)std::min<uint64_t>(WSG_MAX_ROWS, (nq + 127) / 128 * 128);
   const uint32_t max_groups = max_rows / 128;
   const uint32_t target = (uint32_t)(idx->opt_gemm_items > 0 ? idx->opt_gemm_items : 4 * (int64_t)idx->num_sms);
-  const uint32_t max_items = target + 2 * max_groups + 8;
+  // slices of the label axis swept at the same time by different query groups must stay in L2
+  const uint32_t max_tiles = (uint32_t)std::max<uint64_t>(32, ((uint64_t)idx->opt_gemm_chunk_mb << 20) / ((uint64_t)idx->dpad * 4 * WSG_TILE_N));
+  const uint64_t tiles_bound = (uint64_t)max_groups * ((idx->n + WSG_TILE_N - 1) / WSG_TILE_N);
+  const uint32_t max_items = (uint32_t)(target + tiles_bound / max_tiles + 2 * max_groups + 8);
+  WS_TRY(ws_ensure(idx, idx->g_qa, max_rows * sizeof(uint32_t)));
+  WS_TRY(ws_ensure(idx, idx->g_qb, max_rows * sizeof(uint32_t)));
   WS_TRY(ws_ensure(idx, idx->g_perm, max_rows * sizeof(uint32_t)));
   WS_TRY(ws_ensure(idx, idx->g_row_a, max_rows * sizeof(uint32_t)));
   WS_TRY(ws_ensure(idx, idx->g_row_b, max_rows * sizeof(uint32_t)));
@@ -729,6 +735,7 @@ static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw
     while (nsort < rows_pad) nsort <<= 1;
     WsGemmPlanArgs pa;
     pa.windows = dw + 2 * q0; pa.labels = idx->d_labels; pa.n = idx->n; pa.nq = sn; pa.rows_pad = rows_pad;
+    pa.qa = (uint32_t*)idx->g_qa.p; pa.qb = (uint32_t*)idx->g_qb.p; pa.max_tiles = max_tiles;
     pa.perm = (uint32_t*)idx->g_perm.p; pa.row_a = (uint32_t*)idx->g_row_a.p; pa.row_b = (uint32_t*)idx->g_row_b.p;
     pa.items = (WsGemmItem*)idx->g_items.p; pa.nitems = gctrl32 + 10; pa.max_items = max_items;
     pa.group_items = (uint32_t*)idx->g_group_items.p; pa.group_cnt = (uint32_t*)idx->g_group_cnt.p;
@@ -745,8 +752,11 @@ static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw
       WsKernelScope ks(idx, 9);
       WS_CUDA(wsg_launch_plan(nsort, st, pa));
       WS_CUDA(wsg_launch_pack(st, ka));
-      WS_CUDA(wsg_launch_seed(kq, idx->metric, exact_rows, st, sa));
       idx->launches += 2;
+    }
+    {
+      WsKernelScope ks(idx, 11);
+      WS_CUDA(wsg_launch_seed(kq, idx->metric, exact_rows, st, sa));
     }
     WsGemmArgs ga;
     ga.items = pa.items; ga.nitems = pa.nitems; ga.row_a = pa.row_a; ga.row_b = pa.row_b; ga.slack = ka.slack; ga.thr0 = sa.thr0;
@@ -1496,6 +1506,9 @@ int ws_index_set_option(ws_index* idx, const char* name, int64_t value) {
   } else if (s == "gemm_items") {
     if (value < 0 || value > 65536) return ws_fail(WS_ERR_BADARG, "gemm_items must be 0..65536");
     idx->opt_gemm_items = value;
+  } else if (s == "gemm_chunk_mb") {
+    if (value < 1 || value > 4096) return ws_fail(WS_ERR_BADARG, "gemm_chunk_mb must be 1..4096");
+    idx->opt_gemm_chunk_mb = value;
   } else if (s == "gemm_min_tiles") {
     if (value < 1) return ws_fail(WS_ERR_BADARG, "gemm_min_tiles must be >= 1");
     idx->opt_gemm_min_tiles = value;
