@@ -60,12 +60,45 @@ __device__ __forceinline__ bool wsg_mbar_try(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // A pipeline bug must surface as a launch error, not as a hung device: trap after ~2 s.
+// The clock is only consulted every 4096 failed polls, so the spin loop itself stays three
+// instructions long and does not crowd the issue slots of the other warps of its SM sub-core.
 __device__ __forceinline__ void wsg_mbar_wait(uint64_t* bar, uint32_t parity) {
   if (wsg_mbar_try(bar, parity)) return;
-  const long long t0 = clock64();
+  long long t0 = 0;
+  uint32_t polls = 0;
   while (!wsg_mbar_try(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
+    if ((++polls & 4095u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
   }
+}
+// Same, for warps that can afford to be late (epilogue): back off between polls so that the
+// MMA-issuing and TMA-issuing warps sharing the sub-core get the issue slots.
+__device__ __forceinline__ void wsg_mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (wsg_mbar_try(bar, parity)) return;
+  long long t0 = 0;
+  uint32_t polls = 0;
+  while (!wsg_mbar_try(bar, parity)) {
+    __nanosleep(32);
+    if ((++polls & 1023u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
+  }
+}
+// one lane of a converged warp (elect.sync): the compiler then emits the single-thread tcgen05 /
+// TMA instructions as plain predicated instructions instead of a per-lane serialisation loop
+__device__ __forceinline__ bool wsg_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void wsg_fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void wsg_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -99,6 +132,36 @@ __device__ __forceinline__ void wsg_mma_tf32(uint32_t tmem_d, uint64_t desc_a, u
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// Same with the A operand in TMEM (lane = row, one 32-bit column per tf32 element): only the
+// point block is read from shared memory — an SS-mode 128x128x8 tf32 MMA needs 8 KB of shared
+// memory operands per 64 tensor cycles, twice what the operand path delivers (measured: 140
+// cycles per MMA, 45 % tensor utilisation with nothing else running).
+__device__ __forceinline__ void wsg_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(z), "r"(z), "r"(z), "r"(z)
+      : "memory");
+}
+// 32 consecutive 32-bit columns of this thread's TMEM lane <- registers
+__device__ __forceinline__ void wsg_tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 // arrives on the mbarrier once every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void wsg_mma_commit(uint64_t* bar) {
@@ -449,8 +512,7 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ unsigned char wsg_smem_raw[];
   // operand blocks need 1024-byte alignment (128B swizzle atoms)
   unsigned char* base = wsg_smem_raw + ((1024u - (wsg_smem_u32(wsg_smem_raw) & 1023u)) & 1023u);
-  unsigned char* sA = base;                                  // nkb x 16 KB, resident per item
-  unsigned char* sB = base + WSG_MAX_KB * WSG_KBLK_BYTES;    // ring of 16 KB point blocks
+  unsigned char* sB = base;                                  // ring of 16 KB point blocks
   WsGemmSmem* S = (WsGemmSmem*)(sB + WSG_B_STAGES * WSG_KBLK_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t nitems = *A.nitems;
@@ -458,71 +520,74 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < WSG_B_STAGES; i++) { wsg_mbar_init(&S->full[i], 1); wsg_mbar_init(&S->empty[i], 1); }
-    wsg_mbar_init(&S->a_full, 1); wsg_mbar_init(&S->a_empty, 1);
+    wsg_mbar_init(&S->a_full, WSG_EPI_WARPS); wsg_mbar_init(&S->a_empty, 1);
     for (int i = 0; i < WSG_ACC_STAGES; i++) { wsg_mbar_init(&S->acc_full[i], 1); wsg_mbar_init(&S->acc_empty[i], WSG_EPI_WARPS); }
     wsg_fence_barrier_init();
     wsg_prefetch_tmap(&tmA);
     wsg_prefetch_tmap(&tmB);
   }
-  if (warp == 1) wsg_tmem_alloc(&S->tmem_base, WSG_ACC_STAGES * WSG_TILE_N);
+  if (warp == 1) wsg_tmem_alloc(&S->tmem_base, 512);
   if (threadIdx.x == 64) S->warps_done = 0;
   wsg_tc_fence_before();
   __syncthreads();
   wsg_tc_fence_after();
   const uint32_t tmem_base = S->tmem_base;
 
+  // A pipeline stage holds one whole tile of points (nkb blocks of 16 KB): one barrier round trip and one
+  // pair of tcgen05.commit per 4*nkb MMAs.  (With a stage per 32-column block the tensor pipe drained at
+  // every commit: 1830 cycles per tile instead of the 1024 its 16 MMAs need.)
+  const uint32_t nstages = WSG_B_STAGES / nkb;
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, a_phase = 0;
-      for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
-        const WsGemmItem item = A.items[it];
-        wsg_mbar_wait(&S->a_empty, a_phase ^ 1);
-        wsg_mbar_expect_tx(&S->a_full, nkb * WSG_KBLK_BYTES);
-        for (uint32_t kb = 0; kb < nkb; kb++)
-          wsg_tma_load_2d(sA + kb * WSG_KBLK_BYTES, &tmA, &S->a_full, (int)(kb * WSG_KBLK), (int)item.row0);
-        a_phase ^= 1;
-        const uint32_t rot = wsg_rotation(item);
-        for (uint32_t t = 0; t < item.ntiles; t++) {
-          const int p = (int)(item.p0 + wsg_tile(t, rot, item.ntiles) * WSG_TILE_N);
-          for (uint32_t kb = 0; kb < nkb; kb++) {
-            wsg_mbar_wait(&S->empty[stage], phase ^ 1);
-            wsg_mbar_expect_tx(&S->full[stage], WSG_KBLK_BYTES);
-            wsg_tma_load_2d(sB + stage * WSG_KBLK_BYTES, &tmB, &S->full[stage], (int)(kb * WSG_KBLK), p);
-            if (++stage == WSG_B_STAGES) { stage = 0; phase ^= 1; }
+    // ===== TMA producer (whole warp walks the loop, one elected lane issues) =====
+    uint32_t stage = 0, phase = 0;
+    for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+      const WsGemmItem item = A.items[it];
+      const uint32_t rot = wsg_rotation(item);
+      for (uint32_t t = 0; t < item.ntiles; t++) {
+        const int p = (int)(item.p0 + wsg_tile(t, rot, item.ntiles) * WSG_TILE_N);
+        wsg_mbar_wait(&S->empty[stage], phase ^ 1);
+        if (wsg_elect_one()) {
+          if (A.dbg & 2) {
+            wsg_mbar_arrive(&S->full[stage]);
+          } else {
+            wsg_mbar_expect_tx(&S->full[stage], nkb * WSG_KBLK_BYTES);
+            for (uint32_t kb = 0; kb < nkb; kb++)
+              wsg_tma_load_2d(sB + (stage * nkb + kb) * WSG_KBLK_BYTES, &tmB, &S->full[stage], (int)(kb * WSG_KBLK), p);
           }
         }
+        __syncwarp();
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = wsg_make_idesc();
-      uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
-      for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
-        const uint32_t ntiles = A.items[it].ntiles;
-        wsg_mbar_wait(&S->a_full, a_phase);
-        a_phase ^= 1;
-        for (uint32_t t = 0; t < ntiles; t++) {
-          wsg_mbar_wait(&S->acc_empty[acc], acc_phase ^ 1);
-          wsg_tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * WSG_TILE_N;
+    // ===== MMA issuer (whole warp walks the loop, one elected lane issues) =====
+    const uint32_t idesc = wsg_make_idesc();
+    uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
+    for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+      const uint32_t ntiles = A.items[it].ntiles;
+      wsg_mbar_wait(&S->a_full, a_phase);
+      a_phase ^= 1;
+      for (uint32_t t = 0; t < ntiles; t++) {
+        wsg_mbar_wait(&S->acc_empty[acc], acc_phase ^ 1);
+        wsg_mbar_wait(&S->full[stage], phase);
+        wsg_tc_fence_after();
+        const uint32_t d_tmem = tmem_base + WSG_TILE_N + acc * WSG_TILE_N;  // columns [0,128) hold the queries
+        if (wsg_elect_one()) {
           for (uint32_t kb = 0; kb < nkb; kb++) {
-            wsg_mbar_wait(&S->full[stage], phase);
-            wsg_tc_fence_after();
-            const uint64_t da = wsg_make_desc(wsg_smem_u32(sA + kb * WSG_KBLK_BYTES));
-            const uint64_t db = wsg_make_desc(wsg_smem_u32(sB + stage * WSG_KBLK_BYTES));
+            const uint64_t db = wsg_make_desc(wsg_smem_u32(sB + (stage * nkb + kb) * WSG_KBLK_BYTES));
 #pragma unroll
-            for (uint32_t ks = 0; ks < 4; ks++)  // UMMA_K = 8 tf32 = 32 bytes: advance the start address
-              wsg_mma_tf32(d_tmem, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, (kb | ks) != 0 ? 1u : 0u);
-            wsg_mma_commit(&S->empty[stage]);
-            if (++stage == WSG_B_STAGES) { stage = 0; phase ^= 1; }
+            for (uint32_t ks = 0; ks < 4; ks++)  // UMMA_K = 8 tf32: 8 TMEM columns of A, 32 bytes of the B rows
+              wsg_mma_tf32_ts(d_tmem, tmem_base + kb * WSG_KBLK + ks * 8, db + (uint64_t)(ks * 2), idesc, (kb | ks) != 0 ? 1u : 0u);
           }
+          wsg_mma_commit(&S->empty[stage]);
           wsg_mma_commit(&S->acc_full[acc]);
-          if (++acc == WSG_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
-        wsg_mma_commit(&S->a_empty);
+        __syncwarp();
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
+        if (++acc == WSG_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
+      if (wsg_elect_one()) wsg_mma_commit(&S->a_empty);
+      __syncwarp();
     }
   } else if (warp < 2 + WSG_EPI_WARPS) {
     // ===== epilogue: 16 warps; a query is one TMEM lane, served by the four warps of its lane
@@ -535,7 +600,7 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float INF = __int_as_float(0x7f800000);
     float* my_norm = S->wnorm[e];
-    uint32_t acc = 0, acc_phase = 0;
+    uint32_t acc = 0, acc_phase = 0, a_phase = 0;
     for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
       const WsGemmItem item = A.items[it];
       const uint32_t row = item.row0 + lrow;
@@ -543,6 +608,25 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t rot = wsg_rotation(item);
       // the query's window clipped to this item's slice of the label axis (ranks < 2^31)
       const int wlo = (int)max(A.row_a[row], item.p0), whi = (int)min(A.row_b[row], item.pend);
+      {
+        // the group's queries -> TMEM columns [32*chunk, 32*chunk+32) of lanes [32*quarter, +32), once the
+        // previous item's MMAs have drained
+        wsg_mbar_wait(&S->a_empty, a_phase ^ 1);
+        a_phase ^= 1;
+        wsg_tc_fence_after();
+        float qv[32];
+        const float* qrow = A.qpack + (size_t)row * A.dpad + chunk * 32;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if ((uint32_t)(chunk * 32 + 4 * j) < A.dpad) x = __ldg(reinterpret_cast<const float4*>(qrow) + j);
+          qv[4 * j] = x.x; qv[4 * j + 1] = x.y; qv[4 * j + 2] = x.z; qv[4 * j + 3] = x.w;
+        }
+        wsg_tmem_st32(tmem_base + lane_addr + chunk * 32, qv);
+        wsg_tc_fence_before();
+        __syncwarp();
+        if (lane == 0) wsg_mbar_arrive(&S->a_full);
+      }
       asm volatile("bar.sync 1, 640;" ::: "memory");  // per-query state reset by the threshold warps
       float nrm_next = __ldg(A.norms + item.p0 + rot * WSG_TILE_N + chunk * 32 + lane);
       for (uint32_t t = 0; t < item.ntiles; t++) {
@@ -552,14 +636,14 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();
         if (t + 1 < item.ntiles)
           nrm_next = __ldg(A.norms + item.p0 + wsg_tile(t + 1, rot, item.ntiles) * WSG_TILE_N + chunk * 32 + lane);
-        wsg_mbar_wait(&S->acc_full[acc], acc_phase);
+        wsg_mbar_wait_relaxed(&S->acc_full[acc], acc_phase);
         wsg_tc_fence_after();
         const int lo = max(0, min(32, wlo - cbase));
         const int hi = max(0, min(32, whi - cbase));
-        if (__any_sync(0xffffffffu, hi > lo)) {
+        if (__any_sync(0xffffffffu, hi > lo) && !(A.dbg & 1)) {
           const bool whole = __all_sync(0xffffffffu, lo == 0 && hi == 32);
           float s[32];
-          wsg_tmem_ld32(tmem_base + lane_addr + acc * WSG_TILE_N + chunk * 32, s);
+          wsg_tmem_ld32(tmem_base + lane_addr + WSG_TILE_N + acc * WSG_TILE_N + chunk * 32, s);
           const float4* nr = reinterpret_cast<const float4*>(my_norm);
 #pragma unroll
           for (int j = 0; j < 8; j++) {
@@ -638,7 +722,7 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    wsg_tmem_dealloc(tmem_base, WSG_ACC_STAGES * WSG_TILE_N);
+    wsg_tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -804,7 +888,7 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32) ws_gemm_rerank_kernel(W
 }
 
 // ---- launchers -------------------------------------------------------------------------------
-size_t wsg_topk_smem_bytes() { return 1024 + (size_t)(WSG_MAX_KB + WSG_B_STAGES) * WSG_KBLK_BYTES + sizeof(WsGemmSmem); }
+size_t wsg_topk_smem_bytes() { return 1024 + (size_t)WSG_B_STAGES * WSG_KBLK_BYTES + sizeof(WsGemmSmem); }
 
 cudaError_t wsg_init_attributes() {
   cudaError_t e = cudaFuncSetAttribute(ws_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsg_topk_smem_bytes());

@@ -9,8 +9,8 @@
 #define WSG_KBLK 32          // fp32 columns per 128-byte swizzle block
 #define WSG_KBLK_BYTES (WSG_TILE_N * 128)  // one operand block: 128 rows x 128 B = 16 KB
 #define WSG_MAX_KB 4         // dpad <= 128
-#define WSG_B_STAGES 8       // ring of point blocks (128 KB)
-#define WSG_ACC_STAGES 4     // 4 x 128 columns = all 512 TMEM columns
+#define WSG_B_STAGES 12      // ring of point blocks (192 KB)
+#define WSG_ACC_STAGES 3     // 3 x 128 accumulator columns + 128 columns holding the query operand = 512
 #define WSG_KTOP 16          // k <= 16 on this path
 #define WSG_CAND_CAP 512     // survivors kept per (item, query)
 #define WSG_RING 16          // per-query ring of fresh scores waiting to be folded into the running top-k
@@ -95,8 +95,12 @@ struct WsGemmArgs {
   uint64_t* cand;       // [max_items][WSG_CAND_CAP][128]  (score~, point) keys
   uint32_t* cand_cnt;   // [max_items][128]   0xFFFFFFFF: overflow
   float* cand_thr;      // [max_items][128]   final threshold
+  const float* qpack;   // [rows_pad][dpad] packed queries (the A operand, copied into TMEM per item)
+  uint32_t dpad;
   uint32_t nkb;         // 32-column blocks per row
   uint32_t k;
+  uint32_t dbg;         // timing experiments only (results invalid): 1 = epilogue releases stages without
+                        // reading them, 2 = producer signals point blocks without loading them
 };
 
 struct WsGemmRerankArgs {

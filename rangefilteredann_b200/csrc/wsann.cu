@@ -137,6 +137,7 @@ struct ws_index {
   int64_t opt_gemm_min_window = 2048;
   int64_t opt_gemm_items = 0;    // target work items per plan (0: 4 per SM)
   int64_t opt_gemm_min_tiles = 8;
+  int64_t opt_gemm_debug = 0;     // timing experiments (ws_gemm.h WsGemmArgs::dbg); results are invalid when set
   int64_t opt_gemm_chunk_mb = 32; // largest slice of the label axis one work item sweeps
   bool gemm_ready = false;
   WsDevBuf g_norms, g_ctrl, g_perm, g_row_a, g_row_b, g_items, g_group_items, g_group_cnt, g_qpack, g_slack, g_cand,
@@ -761,7 +762,7 @@ static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw
     WsGemmArgs ga;
     ga.items = pa.items; ga.nitems = pa.nitems; ga.row_a = pa.row_a; ga.row_b = pa.row_b; ga.slack = ka.slack; ga.thr0 = sa.thr0;
     ga.norms = (const float*)idx->g_norms.p; ga.cand = (uint64_t*)idx->g_cand.p; ga.cand_cnt = (uint32_t*)idx->g_cand_cnt.p;
-    ga.cand_thr = (float*)idx->g_cand_thr.p; ga.nkb = (idx->dpad + WSG_KBLK - 1) / WSG_KBLK; ga.k = k;
+    ga.cand_thr = (float*)idx->g_cand_thr.p; ga.nkb = (idx->dpad + WSG_KBLK - 1) / WSG_KBLK; ga.k = k; ga.dbg = (uint32_t)idx->opt_gemm_debug; ga.qpack = ka.qpack; ga.dpad = idx->dpad;
     {
       WsKernelScope ks(idx, 8);
       WS_CUDA(wsg_launch_topk(idx->num_sms, st, idx->g_tm_a, idx->g_tm_b, ga));
@@ -1506,6 +1507,8 @@ int ws_index_set_option(ws_index* idx, const char* name, int64_t value) {
   } else if (s == "gemm_items") {
     if (value < 0 || value > 65536) return ws_fail(WS_ERR_BADARG, "gemm_items must be 0..65536");
     idx->opt_gemm_items = value;
+  } else if (s == "gemm_debug") {
+    idx->opt_gemm_debug = value;
   } else if (s == "gemm_chunk_mb") {
     if (value < 1 || value > 4096) return ws_fail(WS_ERR_BADARG, "gemm_chunk_mb must be 1..4096");
     idx->opt_gemm_chunk_mb = value;
