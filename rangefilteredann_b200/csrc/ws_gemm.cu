@@ -257,52 +257,72 @@ __global__ void __launch_bounds__(128) ws_gemm_bounds_kernel(WsGemmPlanArgs A) {
   A.qa[i] = a; A.qb[i] = b;
 }
 
+#define WSG_PLAN_BUCKETS 4096
 __global__ void __launch_bounds__(WSG_PLAN_THREADS) ws_gemm_plan_kernel(WsGemmPlanArgs A) {
-  extern __shared__ uint64_t s_keys[];  // [pow2 >= rows_pad]
+  extern __shared__ uint32_t s_sorted[];  // [rows_pad] query of every sorted row
+  __shared__ uint32_t s_hist[WSG_PLAN_BUCKETS + 1];
+  __shared__ uint32_t s_warp_sum[WSG_PLAN_THREADS / 32];
   __shared__ uint32_t s_ga[WSG_MAX_ROWS / 128], s_gb[WSG_MAX_ROWS / 128];
   __shared__ uint32_t s_chunk_cnt[WSG_MAX_SPLITS], s_chunk_off[WSG_MAX_SPLITS];
   __shared__ unsigned long long s_total;
   __shared__ uint32_t s_chunk_pts, s_nchunks;
   const int tid = threadIdx.x;
-  int nsort = 128;
-  while ((uint32_t)nsort < A.rows_pad) nsort <<= 1;
-  // 1. keys = (window start, query); empty windows sort behind everything else
-  for (int i = tid; i < nsort; i += WSG_PLAN_THREADS) {
-    uint64_t key = WS_KEY_MAX;
-    if ((uint32_t)i < A.nq) {
-      const uint32_t a = A.qa[i], b = A.qb[i];
-      key = ((uint64_t)(b > a ? a : 0xFFFFFFFEu) << 32) | (uint32_t)i;
-    }
-    s_keys[i] = key;
-  }
+  // 1. order the queries by window start.  Only locality matters (rows of a group should start
+  //    near each other), so a counting sort over 4096 buckets of the label axis replaces a full
+  //    sort; empty windows go to a last bucket of their own.
+  for (int i = tid; i <= WSG_PLAN_BUCKETS; i += WSG_PLAN_THREADS) s_hist[i] = 0;
   if (tid == 0) s_total = 0;
   if (tid < WSG_MAX_SPLITS) s_chunk_cnt[tid] = 0;
   __syncthreads();
-  // 2. bitonic sort
-  for (int k = 2; k <= nsort; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < nsort; i += WSG_PLAN_THREADS) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const uint64_t x = s_keys[i], y = s_keys[ixj];
-          const bool up = ((i & k) == 0);
-          if ((x > y) == up) { s_keys[i] = y; s_keys[ixj] = x; }
-        }
-      }
-      __syncthreads();
-    }
+  for (uint32_t i = tid; i < A.nq; i += WSG_PLAN_THREADS) {
+    const uint32_t a = A.qa[i], b = A.qb[i];
+    const uint32_t bucket = b > a ? (uint32_t)(((uint64_t)a * WSG_PLAN_BUCKETS) / A.n) : WSG_PLAN_BUCKETS;
+    atomicAdd(&s_hist[bucket], 1u);
   }
+  __syncthreads();
+  {  // exclusive scan of the 4097 counters: 4 per thread (+ the last one), warp scan, block scan
+    uint32_t v[4], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { v[j] = s_hist[tid * 4 + j]; sum += v[j]; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((tid & 31) >= o) incl += y;
+    }
+    if ((tid & 31) == 31) s_warp_sum[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+      uint32_t w = s_warp_sum[tid], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, wi, o);
+        if (tid >= o) wi += y;
+      }
+      s_warp_sum[tid] = wi - w;
+    }
+    __syncthreads();
+    uint32_t run = s_warp_sum[tid >> 5] + incl - sum;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { s_hist[tid * 4 + j] = run; run += v[j]; }
+    if (tid == WSG_PLAN_THREADS - 1) s_hist[WSG_PLAN_BUCKETS] = run;  // empties start after every real bucket
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < A.nq; i += WSG_PLAN_THREADS) {
+    const uint32_t a = A.qa[i], b = A.qb[i];
+    const uint32_t bucket = b > a ? (uint32_t)(((uint64_t)a * WSG_PLAN_BUCKETS) / A.n) : WSG_PLAN_BUCKETS;
+    s_sorted[atomicAdd(&s_hist[bucket], 1u)] = i;
+  }
+  for (uint32_t r = A.nq + tid; r < A.rows_pad; r += WSG_PLAN_THREADS) s_sorted[r] = 0xFFFFFFFFu;
+  __syncthreads();
   // 3. sorted rows, 4. group extents (one warp per group of 128 rows)
   const uint32_t groups = A.rows_pad / 128;
   for (uint32_t g = tid >> 5; g < groups; g += WSG_PLAN_THREADS / 32) {
     uint32_t ga = 0xFFFFFFFFu, gb = 0;
     for (uint32_t r = g * 128 + (tid & 31); r < (g + 1) * 128; r += 32) {
-      const uint64_t key = s_keys[r];
-      uint32_t q = 0xFFFFFFFFu, a = 0, b = 0;
-      if (key != WS_KEY_MAX) {
-        q = (uint32_t)key;
-        a = A.qa[q]; b = A.qb[q];
-      }
+      const uint32_t q = s_sorted[r];
+      uint32_t a = 0, b = 0;
+      if (q != 0xFFFFFFFFu) { a = A.qa[q]; b = A.qb[q]; }
       A.perm[r] = q; A.row_a[r] = a; A.row_b[r] = b;
       if (b > a) { ga = min(ga, a); gb = max(gb, b); }
     }
@@ -901,7 +921,7 @@ cudaError_t wsg_launch_norm(int grid, cudaStream_t st, const WsGemmNormArgs& a) 
 }
 cudaError_t wsg_launch_plan(uint32_t nsort, cudaStream_t st, const WsGemmPlanArgs& a) {
   ws_gemm_bounds_kernel<<<(a.nq + 127) / 128, 128, 0, st>>>(a);
-  ws_gemm_plan_kernel<<<1, WSG_PLAN_THREADS, nsort * sizeof(uint64_t), st>>>(a);
+  ws_gemm_plan_kernel<<<1, WSG_PLAN_THREADS, nsort * sizeof(uint32_t), st>>>(a);
   return cudaGetLastError();
 }
 cudaError_t wsg_launch_pack(cudaStream_t st, const WsGemmPackArgs& a) {
