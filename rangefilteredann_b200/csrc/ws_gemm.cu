@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32) ws_gemm_seed_kernel(WsG
     const float e = 0.5f * A.slack[row];
     out = METRIC == 0 ? D - A.qnorm[row] + e : D + e;
   }
-  if (lane == 0) A.thr0[row] = out;
+  if (lane == 0) A.thr0[row] = ws_ord(out);
 }
 
 
@@ -581,30 +581,46 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ===== MMA issuer (whole warp walks the loop, one elected lane issues) =====
+    // tcgen05.mma issue is in lock step with the tensor pipe (a short queue), so every instruction
+    // between the last MMA of a tile and the first MMA of the next one is a bubble on the pipe
+    // (measured: 330-640 idle cycles per 1024-cycle tile).  The barrier waits of tile t+1 are
+    // therefore taken in the MIDDLE of tile t's MMAs, and descriptors are plain adds.
     const uint32_t idesc = wsg_make_idesc();
+    const uint64_t desc0 = wsg_make_desc(wsg_smem_u32(sB));
+    const uint32_t tmem_acc0 = tmem_base + WSG_TILE_N;  // columns [0,128) hold the queries
+    const uint32_t nmma = nkb * 4, half = nmma / 2;
     uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
     for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
       const uint32_t ntiles = A.items[it].ntiles;
       wsg_mbar_wait(&S->a_full, a_phase);
       a_phase ^= 1;
+      wsg_mbar_wait(&S->acc_empty[acc], acc_phase ^ 1);
+      wsg_mbar_wait(&S->full[stage], phase);
+      wsg_tc_fence_after();
       for (uint32_t t = 0; t < ntiles; t++) {
-        wsg_mbar_wait(&S->acc_empty[acc], acc_phase ^ 1);
-        wsg_mbar_wait(&S->full[stage], phase);
-        wsg_tc_fence_after();
-        const uint32_t d_tmem = tmem_base + WSG_TILE_N + acc * WSG_TILE_N;  // columns [0,128) hold the queries
+        const uint32_t d_tmem = tmem_acc0 + acc * WSG_TILE_N;
+        const uint64_t db = desc0 + (uint64_t)(stage * nkb) * (WSG_KBLK_BYTES >> 4);
         if (wsg_elect_one()) {
-          for (uint32_t kb = 0; kb < nkb; kb++) {
-            const uint64_t db = wsg_make_desc(wsg_smem_u32(sB + (stage * nkb + kb) * WSG_KBLK_BYTES));
-#pragma unroll
-            for (uint32_t ks = 0; ks < 4; ks++)  // UMMA_K = 8 tf32: 8 TMEM columns of A, 32 bytes of the B rows
-              wsg_mma_tf32_ts(d_tmem, tmem_base + kb * WSG_KBLK + ks * 8, db + (uint64_t)(ks * 2), idesc, (kb | ks) != 0 ? 1u : 0u);
-          }
+          for (uint32_t i = 0; i < half; i++)  // MMA i: 32-column block i/4, 8-column step i%4
+            wsg_mma_tf32_ts(d_tmem, tmem_base + i * 8, db + (uint64_t)((i >> 2) * (WSG_KBLK_BYTES >> 4) + (i & 3) * 2), idesc, i != 0 ? 1u : 0u);
+        }
+        __syncwarp();
+        uint32_t nstage = stage + 1, nphase = phase, nacc = acc + 1, nacc_phase = acc_phase;
+        if (nstage == nstages) { nstage = 0; nphase ^= 1; }
+        if (nacc == WSG_ACC_STAGES) { nacc = 0; nacc_phase ^= 1; }
+        if (t + 1 < ntiles) {  // next tile's operands and accumulator, while this tile's MMAs are queued
+          wsg_mbar_wait(&S->acc_empty[nacc], nacc_phase ^ 1);
+          wsg_mbar_wait(&S->full[nstage], nphase);
+          wsg_tc_fence_after();
+        }
+        if (wsg_elect_one()) {
+          for (uint32_t i = half; i < nmma; i++)
+            wsg_mma_tf32_ts(d_tmem, tmem_base + i * 8, db + (uint64_t)((i >> 2) * (WSG_KBLK_BYTES >> 4) + (i & 3) * 2), idesc, 1u);
           wsg_mma_commit(&S->empty[stage]);
           wsg_mma_commit(&S->acc_full[acc]);
         }
         __syncwarp();
-        if (++stage == nstages) { stage = 0; phase ^= 1; }
-        if (++acc == WSG_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        stage = nstage; phase = nphase; acc = nacc; acc_phase = nacc_phase;
       }
       if (wsg_elect_one()) wsg_mma_commit(&S->a_empty);
       __syncwarp();
@@ -664,6 +680,10 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const bool whole = __all_sync(0xffffffffu, lo == 0 && hi == 32);
           float s[32];
           wsg_tmem_ld32(tmem_base + lane_addr + WSG_TILE_N + acc * WSG_TILE_N + chunk * 32, s);
+          // the scores are in registers: hand the accumulator stage back before filtering them
+          wsg_tc_fence_before();
+          __syncwarp();
+          if (lane == 0) wsg_mbar_arrive(&S->acc_empty[acc]);
           const float4* nr = reinterpret_cast<const float4*>(my_norm);
 #pragma unroll
           for (int j = 0; j < 8; j++) {
@@ -695,10 +715,11 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
             }
           }
+        } else {
+          wsg_tc_fence_before();
+          __syncwarp();
+          if (lane == 0) wsg_mbar_arrive(&S->acc_empty[acc]);
         }
-        wsg_tc_fence_before();
-        __syncwarp();
-        if (lane == 0) wsg_mbar_arrive(&S->acc_empty[acc]);
         if (++acc == WSG_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
       __syncwarp();
@@ -717,22 +738,35 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
       const uint32_t row = A.items[it].row0 + lrow;
       const float slack = A.slack[row];
-      const float thr0 = A.thr0[row];
+      // A threshold reached by ANY work item of the query (k-th best of a subset + slack) bounds the
+      // query's true k-th distance, so items share it through global memory: later slices of the label
+      // axis start from the threshold earlier ones reached instead of the seed.
+      uint32_t* gthr = A.gthr + row;
+      float thr0 = ws_unord(*(volatile uint32_t*)gthr);
       float tk[WSG_KTOP];
 #pragma unroll
       for (int x = 0; x < WSG_KTOP; x++) tk[x] = x < WSG_KTOP - k ? -INF : INF;
-      float thr = thr0;
-      uint32_t last_head = 0;
+      float thr = thr0, pub = thr0;
+      uint32_t last_head = 0, polls = 0;
       S->thr[lrow] = thr0; S->cnt[lrow] = 0; S->head[lrow] = 0;
 #pragma unroll
       for (int i = 0; i < WSG_RING; i++) S->ring[i][lrow] = WSG_SENT;
       asm volatile("bar.sync 1, 640;" ::: "memory");
       seq++;
       while (*(volatile uint32_t*)&S->warps_done < seq * WSG_EPI_WARPS) {
-        if (!wsg_flush(tk, S, lrow, last_head, k, slack, thr, thr0)) __nanosleep(64);
+        const bool got = wsg_flush(tk, S, lrow, last_head, k, slack, thr, thr0);
+        if (thr < pub) { atomicMin(gthr, ws_ord(thr)); pub = thr; }
+        if (!got) {
+          if ((++polls & 15u) == 0) {
+            const float g = ws_unord(*(volatile uint32_t*)gthr);
+            if (g < thr) { thr0 = g; thr = g; pub = g; *(volatile float*)&S->thr[lrow] = g; }
+          }
+          __nanosleep(64);
+        }
       }
       asm volatile("bar.sync 1, 640;" ::: "memory");
       wsg_flush(tk, S, lrow, last_head, k, slack, thr, thr0);
+      if (thr < pub) atomicMin(gthr, ws_ord(thr));
       const uint32_t c = S->cnt[lrow];
       A.cand_cnt[(size_t)it * WSG_TILE_M + lrow] = c > WSG_CAND_CAP ? 0xFFFFFFFFu : c;
       A.cand_thr[(size_t)it * WSG_TILE_M + lrow] = thr;

@@ -81,7 +81,7 @@ struct WsGemmSeedArgs {
   const uint32_t* row_b;
   const float* slack;
   const float* qnorm;
-  float* thr0;            // [rows_pad]
+  uint32_t* thr0;         // [rows_pad] seed threshold, order-preserving uint encoding (ws_ord)
 };
 
 struct WsGemmArgs {
@@ -90,7 +90,8 @@ struct WsGemmArgs {
   const uint32_t* row_a;
   const uint32_t* row_b;
   const float* slack;
-  const float* thr0;    // seed threshold per sorted row (ws_gemm_seed_kernel)
+  uint32_t* gthr;       // [rows_pad] per query: best threshold any of its work items has reached so far
+                        // (ws_ord encoding, atomicMin); seeded by ws_gemm_seed_kernel
   const float* norms;
   uint64_t* cand;       // [max_items][WSG_CAND_CAP][128]  (score~, point) keys
   uint32_t* cand_cnt;   // [max_items][128]   0xFFFFFFFF: overflow

@@ -135,7 +135,7 @@ struct ws_index {
   // tensor-core prefilter (ws_gemm.cuh)
   int64_t opt_gemm = 2;          // 0 never, 1 whenever eligible, 2 auto (host-sampled mean window >= opt_gemm_min_window)
   int64_t opt_gemm_min_window = 2048;
-  int64_t opt_gemm_items = 0;    // target work items per plan (0: 4 per SM)
+  int64_t opt_gemm_items = 0;    // target work items per plan (0: 2 per SM)
   int64_t opt_gemm_min_tiles = 8;
   int64_t opt_gemm_debug = 0;     // timing experiments (ws_gemm.h WsGemmArgs::dbg); results are invalid when set
   int64_t opt_gemm_chunk_mb = 32; // largest slice of the label axis one work item sweeps
@@ -690,7 +690,7 @@ static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw
   cudaStream_t st = idx->stream;
   const uint32_t max_rows = (uint32_t)std::min<uint64_t>(WSG_MAX_ROWS, (nq + 127) / 128 * 128);
   const uint32_t max_groups = max_rows / 128;
-  const uint32_t target = (uint32_t)(idx->opt_gemm_items > 0 ? idx->opt_gemm_items : 4 * (int64_t)idx->num_sms);
+  const uint32_t target = (uint32_t)(idx->opt_gemm_items > 0 ? idx->opt_gemm_items : 2 * (int64_t)idx->num_sms);
   // slices of the label axis swept at the same time by different query groups must stay in L2
   const uint32_t max_tiles = (uint32_t)std::max<uint64_t>(32, ((uint64_t)idx->opt_gemm_chunk_mb << 20) / ((uint64_t)idx->dpad * 4 * WSG_TILE_N));
   const uint64_t tiles_bound = (uint64_t)max_groups * ((idx->n + WSG_TILE_N - 1) / WSG_TILE_N);
@@ -748,7 +748,7 @@ static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw
     ka.qnorm = (float*)idx->g_qnorm.p;
     WsGemmSeedArgs sa;
     sa.vecs = idx->d_vecs; sa.queries = ka.queries; sa.dim = idx->dim; sa.dpad = idx->dpad; sa.rows_pad = rows_pad; sa.k = k;
-    sa.perm = pa.perm; sa.row_a = pa.row_a; sa.row_b = pa.row_b; sa.slack = ka.slack; sa.qnorm = ka.qnorm; sa.thr0 = (float*)idx->g_thr0.p;
+    sa.perm = pa.perm; sa.row_a = pa.row_a; sa.row_b = pa.row_b; sa.slack = ka.slack; sa.qnorm = ka.qnorm; sa.thr0 = (uint32_t*)idx->g_thr0.p;
     {
       WsKernelScope ks(idx, 9);
       WS_CUDA(wsg_launch_plan(nsort, st, pa));
@@ -760,7 +760,7 @@ static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw
       WS_CUDA(wsg_launch_seed(kq, idx->metric, exact_rows, st, sa));
     }
     WsGemmArgs ga;
-    ga.items = pa.items; ga.nitems = pa.nitems; ga.row_a = pa.row_a; ga.row_b = pa.row_b; ga.slack = ka.slack; ga.thr0 = sa.thr0;
+    ga.items = pa.items; ga.nitems = pa.nitems; ga.row_a = pa.row_a; ga.row_b = pa.row_b; ga.slack = ka.slack; ga.gthr = sa.thr0;
     ga.norms = (const float*)idx->g_norms.p; ga.cand = (uint64_t*)idx->g_cand.p; ga.cand_cnt = (uint32_t*)idx->g_cand_cnt.p;
     ga.cand_thr = (float*)idx->g_cand_thr.p; ga.nkb = (idx->dpad + WSG_KBLK - 1) / WSG_KBLK; ga.k = k; ga.dbg = (uint32_t)idx->opt_gemm_debug; ga.qpack = ka.qpack; ga.dpad = idx->dpad;
     {
