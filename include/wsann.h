@@ -117,7 +117,10 @@ int ws_index_add_graph(ws_index* idx, uint64_t start, uint64_t count, uint32_t m
 
 /* B-WST geometry (range_filter_tree.h:129-189): `rows` rows, row r has row_nb[r] buckets,
  * offsets_flat holds the concatenated per-row offset arrays (row_nb[r]+1 entries each),
- * node_ids_flat the node handle of every bucket (row-major). */
+ * node_ids_flat the node handle of every bucket (row-major).  node_ids_flat == NULL selects the
+ * reference's other instantiation, RangeFilterTreeIndex<T, Point, PrefilterIndex>
+ * (range_filter_tree.h:32, python_bindings.cpp:119-127): a bucket query is then PrefilterIndex::query_knn
+ * (prefiltering.h:154-204) over the bucket's own slice, i.e. a brute-force scan, and no graph is needed. */
 int ws_index_set_wst(ws_index* idx, uint32_t rows, uint32_t split_factor, int32_t cutoff,
                      const uint32_t* row_nb, const uint64_t* offsets_flat,
                      const int32_t* node_ids_flat);

@@ -101,6 +101,9 @@ struct Oracle {
   std::vector<std::vector<int>> wst_nodes;
   size_t split = 2;
   int32_t cutoff = 1000;
+  // RangeFilterTreeIndex<T, Point, PrefilterIndex> (range_filter_tree.h:32, python_bindings.cpp:119-127):
+  // bucket sub-indices are PrefilterIndex-es over the bucket's slice, not graphs
+  bool prefilter_nodes = false;
   // super tree
   std::vector<size_t> sup_size, sup_shift;
   std::vector<std::vector<int>> sup_nodes;
@@ -227,6 +230,19 @@ struct Oracle {
   // postfilter_vamana.h:141-188
   std::vector<Pid> node_query(const float* q, long qid, const Node& nd, float lo, float hi, const Params& P,
                               long final_mult, uint64_t* nvis, uint64_t* ncmp, uint64_t* ns) const {
+    if (prefilter_nodes) {  // PrefilterIndex::query -> query_knn over the bucket's own labels (prefiltering.h:148-204)
+      const float* nl = &labels[nd.start];
+      auto bound = [&](float v) {
+        size_t l = 0, r = nd.count - 1;
+        while (l < r) { size_t mid = (l + r) / 2; if (nl[mid] < v) l = mid + 1; else r = mid; }
+        return l;
+      };
+      size_t a = nd.start + bound(lo), e = nd.start + bound(hi);
+      std::vector<Pid> fr;
+      if (e > a) brute(q, a, e, fr);
+      sort_truncate(fr, P.k);
+      return fr;
+    }
     if (trace) {
       int64_t rec[4] = {0, (int64_t)nd.start, (int64_t)(nd.start + nd.count), final_mult != P.final_mult ? 1 : 0};
       trace->insert(trace->end(), rec, rec + 4);
@@ -449,7 +465,8 @@ extern "C" {
 
 const char* oracle_last_error() { return g_err.c_str(); }
 
-// kind: 0 prefilter (sorted arena, no graphs), 1 flat postfilter (unsorted, one graph),
+// kind: 0 prefilter (sorted arena, no graphs), 1 flat postfilter (unsorted, one graph), 4 B-WST over
+// PrefilterIndex sub-indices (no graphs),
 //       2 B-WST with Vamana nodes, 3 super-postfilter tree
 void* oracle_create(int kind, int metric, int dist_mode, uint64_t n, uint32_t dim, const float* points,
                     const float* labels, int32_t cutoff, float split_factor, float shift_factor, long L, long R,
@@ -472,7 +489,8 @@ void* oracle_create(int kind, int metric, int dist_mode, uint64_t n, uint32_t di
     std::string cache = cache_path ? cache_path : "<none>";
     if (kind == 1) {
       add_node(o, cache, L, R, alpha, 0, n);
-    } else if (kind == 2) {  // range_filter_tree.h:129-189
+    } else if (kind == 2 || kind == 4) {  // range_filter_tree.h:129-189
+      if (kind == 4) { o->prefilter_nodes = true; cache = "<none>"; }
       o->split = (size_t)split_factor; o->cutoff = cutoff;
       o->offs.push_back({0, (size_t)n});
       while ((long)o->offs.back()[1] > (long)cutoff) {

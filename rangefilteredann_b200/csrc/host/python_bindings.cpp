@@ -69,6 +69,7 @@ static void add_variant(py::module_& m, const std::string& sfx) {
   struct Prefilter : wsann::PrefilterIndex { using wsann::PrefilterIndex::PrefilterIndex; };
   struct Postfilter : wsann::PostfilterVamanaIndex { using wsann::PostfilterVamanaIndex::PostfilterVamanaIndex; };
   struct Tree : wsann::VamanaRangeFilterTreeIndex { using wsann::VamanaRangeFilterTreeIndex::VamanaRangeFilterTreeIndex; };
+  struct PreTree : wsann::RangeFilterTreeIndex { using wsann::RangeFilterTreeIndex::RangeFilterTreeIndex; };
   struct Super : wsann::SuperOptimizedPostfilterTree { using wsann::SuperOptimizedPostfilterTree::SuperOptimizedPostfilterTree; };
 
   py::class_<Prefilter>(m, ("PrefilterIndex" + sfx).c_str())
@@ -117,6 +118,26 @@ static void add_variant(py::module_& m, const std::string& sfx) {
            "queries"_a, "filters"_a, "num_queries"_a, "query_method"_a, "query_params"_a)
       .def("_arena_handle", [](Tree& self) { return (uintptr_t)self.arena().get(); })
       .def("_bucket_offsets", [](Tree& self) { return self.bucket_offsets(); });
+
+  // python_bindings.cpp:119-127 — the tree over PrefilterIndex sub-indices
+  py::class_<PreTree>(m, ("RangeFilterTreeIndex" + sfx).c_str())
+      .def(py::init([](FArray points, FArray filter_values, int32_t cutoff, size_t split_factor, BuildParams bp) {
+             Points p = check_points(points, filter_values);
+             return new PreTree(p.data, filter_values.data(), p.n, p.dim, METRIC, cutoff, split_factor, bp);
+           }),
+           "points"_a, "filter_values"_a, "cutoff"_a = 1000, "split_factor"_a = 2,
+           "build_params"_a = DEFAULT_BUILD_PARAMS)
+      .def("batch_search",
+           [](PreTree& self, FArray queries, FArray filters, uint64_t num_queries, const std::string& query_method,
+              QueryParams qp) {
+             Batch b = check_batch(queries, filters, num_queries, self.dim());
+             return run(b.nq, qp.k, [&](unsigned int* ids, float* dists) {
+               self.batch_search(b.queries, b.filters, b.nq, query_method, qp, ids, dists);
+             });
+           },
+           "queries"_a, "filters"_a, "num_queries"_a, "query_method"_a, "query_params"_a)
+      .def("_arena_handle", [](PreTree& self) { return (uintptr_t)self.arena().get(); })
+      .def("_bucket_offsets", [](PreTree& self) { return self.bucket_offsets(); });
 
   py::class_<Super>(m, ("SuperOptimizedPostfilterTreeIndex" + sfx).c_str())
       .def(py::init([](FArray points, FArray filter_values, int32_t cutoff, float split_factor, float shift_factor,

@@ -314,12 +314,16 @@ class PostfilterVamanaIndex {
   int32_t node_ = -1;
 };
 
-// ---- RangeFilterTreeIndex with Vamana sub-indices (src/range_filter_tree.h) --------------------
-class VamanaRangeFilterTreeIndex {
- public:
-  VamanaRangeFilterTreeIndex(const float* points, const float* labels, size_t n, size_t dim, int metric,
-                             int32_t cutoff, size_t split_factor, const BuildParams& bp,
-                             int device = default_device()) {
+// ---- RangeFilterTreeIndex (src/range_filter_tree.h) --------------------------------------------
+// The reference instantiates the template twice (python_bindings.cpp:119-127,136-145): with
+// PostfilterVamanaIndex sub-indices ("VamanaRangeFilterTreeIndex…") and with PrefilterIndex
+// sub-indices ("RangeFilterTreeIndex…", the template's default, range_filter_tree.h:32).  Geometry,
+// query methods and result conventions are the same; only what answers a bucket differs.
+class RangeFilterTreeBase {
+ protected:
+  RangeFilterTreeBase(const float* points, const float* labels, size_t n, size_t dim, int metric,
+                      int32_t cutoff, size_t split_factor, const BuildParams& bp, bool vamana_nodes,
+                      int device) {
     if (split_factor < 2) throw std::runtime_error("split_factor must be at least 2");
     arena_.init_sorted(points, labels, n, dim, metric, device);
     const std::vector<float>& sl = arena_.labels();
@@ -349,15 +353,20 @@ class VamanaRangeFilterTreeIndex {
     for (auto& row : offsets_) {
       row_nb.push_back((uint32_t)row.size() - 1);
       off_flat.insert(off_flat.end(), row.begin(), row.end());
-      for (size_t b = 0; b + 1 < row.size(); b++)
-        arena_.plan_graph(row[b], row[b + 1] - row[b], sl[row[b]], sl[row[b + 1] - 1]);
+      if (vamana_nodes)
+        for (size_t b = 0; b + 1 < row.size(); b++)
+          arena_.plan_graph(row[b], row[b + 1] - row[b], sl[row[b]], sl[row[b + 1] - 1]);
     }
-    std::vector<int32_t> nodes_flat = arena_.realize_graphs(bp);
+    // no node handles = PrefilterIndex sub-indices: a bucket query is a scan of the bucket's slice
+    std::vector<int32_t> nodes_flat;
+    if (vamana_nodes) nodes_flat = arena_.realize_graphs(bp);
     check(ws_index_set_wst(arena_.get(), (uint32_t)offsets_.size(), (uint32_t)split_factor, cutoff, row_nb.data(),
-                           off_flat.data(), nodes_flat.data()),
+                           off_flat.data(), vamana_nodes ? nodes_flat.data() : nullptr),
           "ws_index_set_wst");
     check(ws_index_finalize(arena_.get()), "ws_index_finalize");
   }
+
+ public:
 
   // range_filter_tree.h:62-96: any method string other than the two named ones is "fenwick"
   static int method_from_string(const std::string& m) {
@@ -378,6 +387,23 @@ class VamanaRangeFilterTreeIndex {
  private:
   Arena arena_;
   std::vector<std::vector<uint64_t>> offsets_;
+};
+
+// RangeFilterTreeIndex<T, Point, PostfilterVamanaIndex<T, Point>> (python_bindings.cpp:136-145)
+class VamanaRangeFilterTreeIndex : public RangeFilterTreeBase {
+ public:
+  VamanaRangeFilterTreeIndex(const float* points, const float* labels, size_t n, size_t dim, int metric,
+                             int32_t cutoff, size_t split_factor, const BuildParams& bp,
+                             int device = default_device())
+      : RangeFilterTreeBase(points, labels, n, dim, metric, cutoff, split_factor, bp, true, device) {}
+};
+
+// RangeFilterTreeIndex<T, Point> = PrefilterIndex sub-indices (python_bindings.cpp:119-127)
+class RangeFilterTreeIndex : public RangeFilterTreeBase {
+ public:
+  RangeFilterTreeIndex(const float* points, const float* labels, size_t n, size_t dim, int metric,
+                       int32_t cutoff, size_t split_factor, const BuildParams& bp, int device = default_device())
+      : RangeFilterTreeBase(points, labels, n, dim, metric, cutoff, split_factor, bp, false, device) {}
 };
 
 // ---- SuperOptimizedPostfilterTree (src/super_optimized_postfilter_tree.h) ------------------------

@@ -53,6 +53,7 @@ struct WsGeom {
   const uint64_t* wst_off;       // concatenated offsets
   const uint32_t* wst_node_ptr;  // [rows] start of row r's node handles in wst_nodes
   const int32_t* wst_nodes;
+  uint32_t wst_prefilter_nodes;  // != 0: the buckets' sub-indices are PrefilterIndex-es, not graphs
   // ---- super-postfilter tree (super_optimized_postfilter_tree.h:118-171)
   uint32_t sup_rows;
   const uint64_t* sup_size;      // [rows]
@@ -133,6 +134,23 @@ WS_HD int32_t ws_wst_node(const WsGeom& g, uint32_t row, uint64_t i) {
   return g.wst_nodes[g.wst_node_ptr[row] + i];
 }
 
+// One sub-index query of a B-WST bucket (range_filter_tree.h:346,353,372-381,468,490-498: `index->query`).
+// With Vamana sub-indices that is a graph task.  With PrefilterIndex sub-indices
+// (RangeFilterTreeIndex<T, Point>, python_bindings.cpp:119-127; range_filter_tree.h:32 default template
+// argument) it is query_knn (prefiltering.h:154-204) over the bucket's own sorted labels: a scan of
+// [lb(lo), lb(hi)) with `r` starting at count-1, so a bucket's last point is never returned.
+WS_HD void ws_emit_wst_node(const WsGeom& g, uint32_t row, uint64_t b, float lo, float hi, uint32_t flags,
+                            WsEmitter& em) {
+  if (!g.wst_prefilter_nodes) {
+    em.graph(ws_wst_node(g, row, b), lo, hi, flags);
+    return;
+  }
+  uint64_t ns = ws_wst_off(g, row, b), cnt = ws_wst_off(g, row, b + 1) - ns;
+  uint64_t a = ns + ws_prefilter_bound(g.labels + ns, cnt, lo);
+  uint64_t e = ns + ws_prefilter_bound(g.labels + ns, cnt, hi);
+  em.scan(a, e, lo, hi);
+}
+
 // range_filter_tree.h:213-232: bucket of `row` containing sorted rank `index` (< n).
 WS_HD uint64_t ws_find_range_containing(const WsGeom& g, uint32_t row, uint64_t index) {
   uint64_t left = 0, right = g.wst_nb[row];  // invariant: off[left] <= index < off[right]
@@ -210,7 +228,7 @@ WS_HD void ws_decompose_fenwick(const WsGeom& g, float lo, float hi, uint32_t fl
     em.scan(s, e, lo, hi);
     return;
   }
-  for (uint64_t b = c.first; b < c.last; b++) em.graph(ws_wst_node(g, c.row, b), lo, hi, flags);
+  for (uint64_t b = c.first; b < c.last; b++) ws_emit_wst_node(g, c.row, b, lo, hi, flags, em);
   uint64_t cover_s = c.cover_s, cover_e = c.cover_e;
   uint64_t left = c.first, right = c.last - 1;
   for (uint32_t row = c.row + 1; row < g.wst_rows; row++) {
@@ -221,14 +239,14 @@ WS_HD void ws_decompose_fenwick(const WsGeom& g, float lo, float hi, uint32_t fl
       if (nls < s) break;
       cover_s = nls;
       left -= 1;
-      em.graph(ws_wst_node(g, row, left), lo, hi, flags);
+      ws_emit_wst_node(g, row, left, lo, hi, flags, em);
     }
     while (right + 1 < g.wst_nb[row]) {
       uint64_t nre = ws_wst_off(g, row, right + 2);
       if (nre > e) break;
       cover_e = nre;
       right += 1;
-      em.graph(ws_wst_node(g, row, right), lo, hi, flags);
+      ws_emit_wst_node(g, row, right, lo, hi, flags, em);
     }
   }
   em.scan(s, cover_s, lo, hi);
@@ -267,7 +285,7 @@ WS_HD void ws_decompose_opt_postfilter(const WsGeom& g, float lo, float hi,
     ws_decompose_fenwick(g, lo, hi, 0, em);
     return;
   }
-  em.graph(ws_wst_node(g, row, idx), lo, hi, 0);
+  ws_emit_wst_node(g, row, idx, lo, hi, 0, em);
 }
 
 // range_filter_tree.h:473-540
@@ -283,7 +301,7 @@ WS_HD void ws_decompose_three_split(const WsGeom& g, float lo, float hi,
     return;
   }
   for (uint64_t b = c.first; b < c.last; b++)
-    em.graph(ws_wst_node(g, c.row, b), lo, hi, WS_TF_MULT1);
+    ws_emit_wst_node(g, c.row, b, lo, hi, WS_TF_MULT1, em);
   if (c.cover_s > s) ws_decompose_opt_postfilter(g, lo, g.labels[c.cover_s], p, em);
   if (e > c.cover_e) ws_decompose_opt_postfilter(g, g.labels[c.cover_e], hi, p, em);
 }

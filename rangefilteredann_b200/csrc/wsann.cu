@@ -106,6 +106,7 @@ struct ws_index {
   std::vector<uint32_t> sup_nb, sup_node_ptr;
   std::vector<int32_t> sup_nodes;
   uint32_t wst_rows = 0, split = 0, sup_rows = 0;
+  bool wst_prefilter_nodes = false;  // B-WST buckets answered by PrefilterIndex sub-indices (no graphs)
   int32_t cutoff = 0, sup_cutoff = 0;
   WsGeom hgeom{};
   WsGeom dgeom{};
@@ -387,9 +388,10 @@ int ws_index_add_graph(ws_index* idx, uint64_t start, uint64_t count, uint32_t m
 int ws_index_set_wst(ws_index* idx, uint32_t rows, uint32_t split_factor, int32_t cutoff,
                      const uint32_t* row_nb, const uint64_t* offsets_flat,
                      const int32_t* node_ids_flat) {
-  if (!idx || !row_nb || !offsets_flat || !node_ids_flat) return ws_fail(WS_ERR_BADARG, "null argument");
+  if (!idx || !row_nb || !offsets_flat) return ws_fail(WS_ERR_BADARG, "null argument");
   if (idx->finalized) return ws_fail(WS_ERR_STATE, "index already finalized");
   if (!idx->label_sorted) return ws_fail(WS_ERR_BADARG, "tree geometry needs a label-sorted arena");
+  idx->wst_prefilter_nodes = node_ids_flat == nullptr;
   if (rows == 0 || split_factor < 2) return ws_fail(WS_ERR_BADARG, "rows=%u split_factor=%u", rows, split_factor);
   idx->wst_rows = rows;
   idx->split = split_factor;
@@ -405,12 +407,14 @@ int ws_index_set_wst(ws_index* idx, uint32_t rows, uint32_t split_factor, int32_
     nn += row_nb[r];
   }
   idx->wst_off.assign(offsets_flat, offsets_flat + no);
-  idx->wst_nodes.assign(node_ids_flat, node_ids_flat + nn);
+  if (node_ids_flat) idx->wst_nodes.assign(node_ids_flat, node_ids_flat + nn);
+  else idx->wst_nodes.assign(nn, -1);
   for (uint32_t r = 0; r < rows; r++) {
     const uint64_t* o = &idx->wst_off[idx->wst_off_ptr[r]];
     if (o[0] != 0 || o[row_nb[r]] != idx->n) return ws_fail(WS_ERR_BADARG, "row %u offsets do not span [0,n)", r);
     for (uint32_t b = 0; b < row_nb[r]; b++) {
       if (o[b + 1] <= o[b]) return ws_fail(WS_ERR_BADARG, "row %u bucket %u empty", r, b);
+      if (idx->wst_prefilter_nodes) continue;
       int32_t h = idx->wst_nodes[idx->wst_node_ptr[r] + b];
       if (h < 0 || (size_t)h >= idx->h_nodes.size()) return ws_fail(WS_ERR_BADARG, "row %u bucket %u: bad node handle %d", r, b, h);
       if (idx->h_nodes[h].start != o[b] || idx->h_nodes[h].count != o[b + 1] - o[b])
@@ -472,6 +476,7 @@ int ws_index_finalize(ws_index* idx) {
   h.wst_rows = idx->wst_rows; h.split = idx->split; h.cutoff = idx->cutoff;
   h.wst_nb = idx->wst_nb.data(); h.wst_off_ptr = idx->wst_off_ptr.data(); h.wst_off = idx->wst_off.data();
   h.wst_node_ptr = idx->wst_node_ptr.data(); h.wst_nodes = idx->wst_nodes.data();
+  h.wst_prefilter_nodes = idx->wst_prefilter_nodes ? 1u : 0u;
   h.sup_rows = idx->sup_rows;
   h.sup_size = idx->sup_size.data(); h.sup_shift = idx->sup_shift.data(); h.sup_nb = idx->sup_nb.data();
   h.sup_node_ptr = idx->sup_node_ptr.data(); h.sup_nodes = idx->sup_nodes.data();
@@ -516,6 +521,8 @@ static uint32_t ws_task_capacity(const ws_index* idx, int mode) {
   // an uncovered window is shorter than ~2 buckets of the row above the last one
   uint64_t scans = 2ull * scan_tasks(std::max<uint64_t>(2 * first_bucket_prev, 4 * last_bucket));
   uint64_t fen = graph + scans;
+  // PrefilterIndex sub-indices: every bucket of the cover is scanned, in scan_chunk pieces
+  if (idx->wst_prefilter_nodes) fen += scan_tasks(idx->n);
   if (mode == WS_METHOD_THREE_SPLIT) return (uint32_t)(3 * fen);
   return (uint32_t)fen;
 }
@@ -800,7 +807,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
   if (nq > (1ull << 24)) return ws_fail(WS_ERR_BADARG, "nq=%llu above 2^24 per batch", (unsigned long long)nq);
   const uint32_t k = plan.k;
   if (k == 0 || k > kMaxK) return ws_fail(WS_ERR_BADARG, "k=%u outside 1..%u", k, kMaxK);
-  const bool needs_graph = plan.mode != WS_MODE_PREFILTER;
+  const bool needs_graph = plan.mode != WS_MODE_PREFILTER && !(plan.mode <= 2 && idx->wst_prefilter_nodes);
   const ws_query_params& qp = plan.qp;
   if (needs_graph) {
     if (idx->h_nodes.empty()) return ws_fail(WS_ERR_STATE, "index has no graphs");

@@ -6,6 +6,9 @@ container where /root/reference exists.  Committed outputs:
                                 (3000 x 16, seed 7; rangefilteredann_b200.synth.make_dataset)
   tiny_ref_outputs.npz          reference batch_search ids/dists for every query method on
                                 fixed windows (incl. the edge cases of SURVEY.md App. D)
+  tiny_pretree_ref_outputs.npz  the same windows through RangeFilterTreeIndexFloatEuclidian (the tree over
+                                PrefilterIndex sub-indices, python_bindings.cpp:119-127); `--only pretree`
+                                regenerates just this file
 
 Run: python tests/golden/make_golden.py      (after `make -C oracle ref`)
 """
@@ -26,8 +29,28 @@ from rangefilteredann_b200 import synth  # noqa: E402
 from golden_cases import tiny_cases, tiny_mips_cases, TINY, TINY_MIPS  # noqa: E402
 
 
+def pretree(ref):
+    data, queries, labels = synth.make_dataset(TINY["n"], TINY["d"], TINY["nq"], TINY["seed"])
+    tree = ref.RangeFilterTreeIndexFloatEuclidian(data, labels, TINY["cutoff"], 2, ref.BuildParams(64, 500, 1.0, ""))
+    out = {}
+    for name, windows, qkw in tiny_cases(labels):
+        nq = len(windows)
+        qp = ref.QueryParams(10, qkw["beam"], 1.35, 10_000_000, 10_000, qkw["mult"], qkw["max_beam"], qkw.get("ratio"), False)
+        out[f"{name}/windows"] = windows
+        for method in ("fenwick", "optimized_postfilter", "three_split"):
+            if method == "fenwick" and qkw.get("skip_fenwick"):
+                continue
+            ids, d = tree.batch_search(queries[:nq], windows, nq, method, qp)
+            out[f"{name}/{method}/ids"], out[f"{name}/{method}/dists"] = ids, d
+    np.savez_compressed(os.path.join(HERE, "tiny_pretree_ref_outputs.npz"), **out)
+    print("wrote", len(out), "pretree arrays")
+
+
 def main():
     ref = _load_ext(find_ext(os.path.join(ROOT, "oracle", "_ref")))
+    pretree(ref)
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "pretree":
+        return
     data, queries, labels = synth.make_dataset(TINY["n"], TINY["d"], TINY["nq"], TINY["seed"])
     out = {}
     tiny_dir = os.path.join(HERE, "tiny")

@@ -6,7 +6,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "oracle", "libwsann_oracle.so")
-KINDS = {"prefilter": 0, "flat": 1, "wst": 2, "super": 3}
+KINDS = {"prefilter": 0, "flat": 1, "wst": 2, "super": 3, "pretree": 4}
 METHODS = {"fenwick": 0, "optimized_postfilter": 1, "three_split": 2, "super": 3, "prefilter": 10, "flat": 11}
 
 _lib = None

@@ -13,8 +13,9 @@ from oracle_api import Oracle
 from rangefilteredann_b200 import capi, synth
 
 
-def build_host_tree(labels_sorted, cutoff, split=2, super_params=None):
-    """Host-only (device -1) index with the reference's B-WST / super geometry."""
+def build_host_tree(labels_sorted, cutoff, split=2, super_params=None, prefilter_nodes=False):
+    """Host-only (device -1) index with the reference's B-WST / super geometry.  prefilter_nodes: the
+    B-WST buckets are PrefilterIndex sub-indices (ws_index_set_wst without node handles)."""
     n = len(labels_sorted)
     L = capi.lib()
     h = C.c_void_p()
@@ -41,8 +42,11 @@ def build_host_tree(labels_sorted, cutoff, split=2, super_params=None):
         offs.append(nxt)
     row_nb = np.array([len(r) - 1 for r in offs], np.uint32)
     off_flat = np.array([x for r in offs for x in r], np.uint64)
-    nodes = np.array([add(r[b], r[b + 1] - r[b]) for r in offs for b in range(len(r) - 1)], np.int32)
-    capi.check(L.ws_index_set_wst(idx.raw, len(offs), split, cutoff, capi.ptr(row_nb), capi.ptr(off_flat), capi.ptr(nodes)))
+    if prefilter_nodes:
+        capi.check(L.ws_index_set_wst(idx.raw, len(offs), split, cutoff, capi.ptr(row_nb), capi.ptr(off_flat), None))
+    else:
+        nodes = np.array([add(r[b], r[b + 1] - r[b]) for r in offs for b in range(len(r) - 1)], np.int32)
+        capi.check(L.ws_index_set_wst(idx.raw, len(offs), split, cutoff, capi.ptr(row_nb), capi.ptr(off_flat), capi.ptr(nodes)))
     if super_params:
         sf, sh = super_params
         sizes, shifts, nbs, snodes = [n], [0], [1], [add(0, n)]
@@ -83,10 +87,23 @@ def host_decompose(idx, method, windows, beam=10, mult=2, ratio=None):
     return res
 
 
-def check_against_oracle(idx, orc, method, windows, ratio=None):
+def join_chunks(tasks, chunk=8192):
+    """The engine cuts a long scan into scan_chunk-row tasks; the oracle records the slice whole."""
+    out = []
+    for t in tasks.tolist():
+        if out and t[0] == -1 and out[-1][0] == -1 and out[-1][2] == t[1] and (out[-1][2] - out[-1][1]) % chunk == 0:
+            out[-1][2] = t[2]
+        else:
+            out.append(list(t))
+    return np.array(out, np.int64).reshape(-1, 4)
+
+
+def check_against_oracle(idx, orc, method, windows, ratio=None, join=False):
     got = host_decompose(idx, method, windows, ratio=ratio)
     for i, w in enumerate(windows):
         exp = orc.decompose(method, float(w[0]), float(w[1]), ratio=ratio)
+        if join:
+            got[i] = join_chunks(got[i])
         assert np.array_equal(got[i], exp), f"{method} window {w}: engine {got[i].tolist()} vs oracle {exp.tolist()}"
 
 
@@ -99,6 +116,25 @@ def test_decompose_tiny(method):
     orc = Oracle(kind, data, labels, None, cutoff=TINY["cutoff"])
     for name, windows, qkw in tiny_cases(labels):
         check_against_oracle(idx, orc, method, windows, ratio=qkw.get("ratio") if method != "super" else None)
+
+
+@pytest.mark.parametrize("method", ["fenwick", "optimized_postfilter", "three_split"])
+def test_decompose_prefilter_nodes(method):
+    """RangeFilterTreeIndex over PrefilterIndex sub-indices (python_bindings.cpp:119-127): every bucket
+    query becomes a scan of [lb(lo), lb(hi)) inside the bucket, with query_knn's r = count-1 rule."""
+    data, queries, labels = synth.make_dataset(TINY["n"], TINY["d"], TINY["nq"], TINY["seed"])
+    idx = build_host_tree(np.sort(labels), TINY["cutoff"], prefilter_nodes=True)
+    orc = Oracle("pretree", data, labels, None, cutoff=TINY["cutoff"])
+    for name, windows, qkw in tiny_cases(labels):
+        check_against_oracle(idx, orc, method, windows, ratio=qkw.get("ratio"))
+    # config-2 geometry: bucket scans longer than scan_chunk are cut into pieces
+    n = 1_000_000
+    rng = np.random.default_rng(6)
+    labels = (rng.permutation(n).astype(np.float64) / n).astype(np.float32)
+    idx = build_host_tree(np.sort(labels), 1000, prefilter_nodes=True)
+    orc = Oracle("pretree", np.zeros((n, 1), np.float32), labels, None, cutoff=1000)
+    for power in (-12, -6, -2, 0):
+        check_against_oracle(idx, orc, method, synth.make_windows(labels, power, 24, seed=power + 70), join=True)
 
 
 @pytest.mark.parametrize("method", ["fenwick", "optimized_postfilter", "three_split", "super"])

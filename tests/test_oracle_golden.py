@@ -54,6 +54,28 @@ def test_oracle_matches_reference_bit_for_bit(tiny, method):
     assert checked > 0
 
 
+@pytest.mark.parametrize("method", ["fenwick", "optimized_postfilter", "three_split"])
+def test_oracle_matches_reference_prefilter_nodes(tiny, method):
+    """RangeFilterTreeIndexFloatEuclidian — the tree whose buckets are PrefilterIndex sub-indices
+    (python_bindings.cpp:119-127) — against tests/golden/tiny_pretree_ref_outputs.npz."""
+    data, queries, labels = synth.make_dataset(TINY["n"], TINY["d"], TINY["nq"], TINY["seed"])
+    gold = np.load(os.path.join(GOLDEN, "tiny_pretree_ref_outputs.npz"))
+    orc = Oracle("pretree", data, labels, None, cutoff=TINY["cutoff"])
+    checked = 0
+    for name, windows, qkw in tiny["cases"]:
+        key = f"{name}/{method}/ids"
+        if key not in gold:
+            continue
+        rids, rd = gold[key], gold[f"{name}/{method}/dists"]
+        ids, d = orc.batch(method, queries[: len(windows)], windows, k=10, beam=qkw["beam"], mult=qkw["mult"],
+                           max_beam=qkw["max_beam"], ratio=qkw.get("ratio"), pad_id=0)
+        assert np.array_equal(d, rd), f"{name}/{method}"
+        for i, j in zip(*np.nonzero(ids != rids)):
+            assert (rd[i] == rd[i, j]).sum() > 1 or rd[i, j] == rd[i, -1], f"{name}/{method} row {i} col {j}"
+        checked += 1
+    assert checked > 0
+
+
 def test_device_order_mode_is_close(tiny):
     """dist_mode 1 (the kernels' summation order) differs from the reference order only in
     the last bits."""
