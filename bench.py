@@ -429,8 +429,19 @@ def run_engine(args, rank, world, local_rank):
         dom, dom_ms, dom_bytes = "ws_scan_kernel", scan_ms, scan_bytes
         dom_launches = ktimes["scan"]["launches"]
     achieved = dom_bytes / (dom_ms / 1000.0) / 1e9 if dom_ms > 0 else 0.0
+    # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture of one of its launches
+    traffic, traffic_note = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        ent = tr["ws_beam_warp_kernel" if beam_ms >= scan_ms else "ws_scan_warp_kernel"]
+        traffic = int(ent["traffic_bytes"])
+        traffic_note = (f"ncu capture of one launch ({ent['launch']}): {ent['traffic_bytes'] / 1e9:.2f} GB DRAM for "
+                        f"{ent['algorithmic_bytes'] / 1e9:.2f} GB algorithmic ({ent['source']}); bytes_per_launch above "
+                        f"is the mean over this run's launches")
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                 "bytes_per_launch": int(dom_bytes / max(1, dom_launches)),
                 "ms_per_launch": round(dom_ms / max(1, dom_launches), 4),
                 "beam_GBps": round(beam_bytes / (beam_ms / 1000.0) / 1e9, 1) if beam_ms > 0 else None,

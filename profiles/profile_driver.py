@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--nq", type=int, default=10000)
     ap.add_argument("--opt", action="append", default=[], help="name=value engine option")
+    ap.add_argument("--index", default="tree", choices=["tree", "prefilter"],
+                    help="prefilter: PrefilterIndex only (no graphs to load; for captures of the scan / tensor-core kernels)")
     a = ap.parse_args()
     cfg = bench.CONFIGS[a.config]
     eng = load_engine()
@@ -33,7 +35,10 @@ def main():
     cdir = bench.cache_dir(a.config)
     os.makedirs(cdir, exist_ok=True)
     t0 = time.time()
-    tree = eng.VamanaRangeFilterTreeIndexFloatEuclidian(data, labels, cfg["cutoff"], 2, eng.BuildParams(64, 500, 1.0, cdir))
+    if a.index == "prefilter":
+        tree = eng.PrefilterIndexFloatEuclidian(data, labels)
+    else:
+        tree = eng.VamanaRangeFilterTreeIndexFloatEuclidian(data, labels, cfg["cutoff"], 2, eng.BuildParams(64, 500, 1.0, cdir))
     print(f"index ready in {time.time() - t0:.1f}s", flush=True)
     h = capi.Handle.borrow(tree)
     for o in a.opt:
