@@ -3,8 +3,12 @@
 // Mirrors the part of the reference module that experiments/wrapper.py and
 // experiments/run_our_method.py use (python_bindings/python_bindings.cpp:111-157,204-213):
 // the same class names, constructor keyword arguments, batch_search argument order and
-// return type (tuple of uint32 ids [nq,k] and float32 distances [nq,k]).  Only the float
-// variants exist — they are the only ones wrapper.py can reach.
+// return type (tuple of uint32 ids [nq,k] and float32 distances [nq,k]).  The float variants are
+// the ones wrapper.py reaches; the reference also registers UInt8 / Int8 variants
+// (python_bindings.cpp:74-86,233-236), provided here over the same fp32 arena: their distances are
+// integer sums (euclidian_point.h:44-60, mips_point.h:44-58) cast to float, which fp32 arithmetic
+// reproduces exactly, in any summation order, while every partial sum stays below 2^24 — checked at
+// construction (dim * 255^2, or dim * 128^2 for int8 MIPS).
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
@@ -17,37 +21,77 @@ using wsann::BuildParams;
 using wsann::QueryParams;
 
 using FArray = py::array_t<float, py::array::c_style | py::array::forcecast>;
+template <class T>
+using TArray = py::array_t<T, py::array::c_style | py::array::forcecast>;
 using Result = std::pair<py::array_t<unsigned int>, py::array_t<float>>;
 
 static wsann::BuildParams DEFAULT_BUILD_PARAMS(64, 500, 1.175, "index_cache");  // python_bindings.cpp:88
 
+// fp32 view of a [rows][dim] array of T: the array itself for float, a widened copy otherwise
+template <class T>
+struct Widened {
+  std::vector<float> copy;
+  const float* ptr = nullptr;
+  Widened(const T* src, size_t count) {
+    if constexpr (std::is_same<T, float>::value) {
+      ptr = src;
+    } else {
+      copy.resize(count);
+      for (size_t i = 0; i < count; i++) copy[i] = (float)src[i];
+      ptr = copy.data();
+    }
+  }
+};
+
+template <class T>
 struct Points {
+  Widened<T> w;
   const float* data;
   size_t n, dim;
 };
 
+// integer variants: the exactness domain of the fp32 arena (see the header comment)
+template <class T, int METRIC>
+static void check_exact_domain(size_t dim) {
+  if constexpr (!std::is_same<T, float>::value) {
+    const uint64_t term = (std::is_same<T, int8_t>::value && METRIC == WS_METRIC_MIPS) ? 128ull * 128ull : 255ull * 255ull;
+    if ((uint64_t)dim * term >= (1ull << 24))
+      throw std::runtime_error("8-bit variants are supported up to " + std::to_string(((1ull << 24) - 1) / term) +
+                               " dimensions (integer distances must stay exactly representable in fp32)");
+  }
+}
+
 // prefiltering.h:78-98 / tree_utils.h:44-60 error behaviour
-static Points check_points(const FArray& points, const FArray& filter_values) {
+template <class T, int METRIC>
+static Points<T> check_points(const TArray<T>& points, const FArray& filter_values) {
   if (points.ndim() != 2) throw std::runtime_error("points numpy array must be 2-dimensional");
   if (filter_values.ndim() != 1) throw std::runtime_error("filter data numpy array must be 1-dimensional");
   if (filter_values.shape(0) != points.shape(0))
     throw std::runtime_error("filter data numpy array must have the same number of elements as the points array");
-  return Points{points.data(), (size_t)points.shape(0), (size_t)points.shape(1)};
+  check_exact_domain<T, METRIC>((size_t)points.shape(1));
+  Points<T> p{Widened<T>(points.data(), (size_t)points.size()), nullptr, (size_t)points.shape(0), (size_t)points.shape(1)};
+  p.data = p.w.ptr;
+  return p;
 }
 
+template <class T>
 struct Batch {
+  Widened<T> w;
   const float* queries;
   const float* filters;
   uint64_t nq;
 };
 
-static Batch check_batch(const FArray& queries, const FArray& filters, uint64_t num_queries, size_t dim) {
+template <class T>
+static Batch<T> check_batch(const TArray<T>& queries, const FArray& filters, uint64_t num_queries, size_t dim) {
   if (queries.ndim() != 2 || (size_t)queries.shape(1) != dim)
     throw std::runtime_error("queries must be a 2-dimensional array with the index's dimension");
   if ((uint64_t)queries.shape(0) < num_queries) throw std::runtime_error("fewer query rows than num_queries");
   if (filters.ndim() != 2 || filters.shape(1) != 2) throw std::runtime_error("filters must be a sequence of (lo, hi) pairs");
   if ((uint64_t)filters.shape(0) < num_queries) throw std::runtime_error("fewer filters than num_queries");
-  return Batch{queries.data(), filters.data(), num_queries};
+  Batch<T> b{Widened<T>(queries.data(), (size_t)num_queries * dim), nullptr, filters.data(), num_queries};
+  b.queries = b.w.ptr;
+  return b;
 }
 
 template <class F>
@@ -64,7 +108,7 @@ static Result run(uint64_t nq, long k, F&& f) {
   return std::make_pair(ids, dists);
 }
 
-template <int METRIC>
+template <class T, int METRIC>
 static void add_variant(py::module_& m, const std::string& sfx) {
   struct Prefilter : wsann::PrefilterIndex { using wsann::PrefilterIndex::PrefilterIndex; };
   struct Postfilter : wsann::PostfilterVamanaIndex { using wsann::PostfilterVamanaIndex::PostfilterVamanaIndex; };
@@ -73,44 +117,44 @@ static void add_variant(py::module_& m, const std::string& sfx) {
   struct Super : wsann::SuperOptimizedPostfilterTree { using wsann::SuperOptimizedPostfilterTree::SuperOptimizedPostfilterTree; };
 
   py::class_<Prefilter>(m, ("PrefilterIndex" + sfx).c_str())
-      .def(py::init([](FArray points, FArray filter_values, BuildParams bp) {
-             Points p = check_points(points, filter_values);
+      .def(py::init([](TArray<T> points, FArray filter_values, BuildParams bp) {
+             Points<T> p = check_points<T, METRIC>(points, filter_values);
              return new Prefilter(p.data, filter_values.data(), p.n, p.dim, METRIC, bp);
            }),
            "points"_a, "filter_values"_a, "build_params"_a = DEFAULT_BUILD_PARAMS)
       .def("batch_search",
-           [](Prefilter& self, FArray queries, FArray filters, uint64_t num_queries, QueryParams qp) {
-             Batch b = check_batch(queries, filters, num_queries, self.dim());
+           [](Prefilter& self, TArray<T> queries, FArray filters, uint64_t num_queries, QueryParams qp) {
+             Batch<T> b = check_batch<T>(queries, filters, num_queries, self.dim());
              return run(b.nq, qp.k, [&](unsigned int* ids, float* dists) { self.batch_search(b.queries, b.filters, b.nq, qp, ids, dists); });
            },
            "queries"_a, "filters"_a, "num_queries"_a, "query_params"_a)
       .def("_arena_handle", [](Prefilter& self) { return (uintptr_t)self.arena().get(); });
 
   py::class_<Postfilter>(m, ("PostfilterVamanaIndex" + sfx).c_str())
-      .def(py::init([](FArray points, FArray filters, BuildParams bp) {
-             Points p = check_points(points, filters);
+      .def(py::init([](TArray<T> points, FArray filters, BuildParams bp) {
+             Points<T> p = check_points<T, METRIC>(points, filters);
              return new Postfilter(p.data, filters.data(), p.n, p.dim, METRIC, bp);
            }),
            "points"_a, "filters"_a, "build_params"_a = DEFAULT_BUILD_PARAMS)
       .def("batch_search",
-           [](Postfilter& self, FArray queries, FArray filters, uint64_t num_queries, QueryParams qp) {
-             Batch b = check_batch(queries, filters, num_queries, self.dim());
+           [](Postfilter& self, TArray<T> queries, FArray filters, uint64_t num_queries, QueryParams qp) {
+             Batch<T> b = check_batch<T>(queries, filters, num_queries, self.dim());
              return run(b.nq, qp.k, [&](unsigned int* ids, float* dists) { self.batch_search(b.queries, b.filters, b.nq, qp, ids, dists); });
            },
            "queries"_a, "filters"_a, "num_queries"_a, "query_params"_a)
       .def("_arena_handle", [](Postfilter& self) { return (uintptr_t)self.arena().get(); });
 
   py::class_<Tree>(m, ("VamanaRangeFilterTreeIndex" + sfx).c_str())
-      .def(py::init([](FArray points, FArray filter_values, int32_t cutoff, size_t split_factor, BuildParams bp) {
-             Points p = check_points(points, filter_values);
+      .def(py::init([](TArray<T> points, FArray filter_values, int32_t cutoff, size_t split_factor, BuildParams bp) {
+             Points<T> p = check_points<T, METRIC>(points, filter_values);
              return new Tree(p.data, filter_values.data(), p.n, p.dim, METRIC, cutoff, split_factor, bp);
            }),
            "points"_a, "filter_values"_a, "cutoff"_a = 1000, "split_factor"_a = 2,
            "build_params"_a = DEFAULT_BUILD_PARAMS)
       .def("batch_search",
-           [](Tree& self, FArray queries, FArray filters, uint64_t num_queries, const std::string& query_method,
+           [](Tree& self, TArray<T> queries, FArray filters, uint64_t num_queries, const std::string& query_method,
               QueryParams qp) {
-             Batch b = check_batch(queries, filters, num_queries, self.dim());
+             Batch<T> b = check_batch<T>(queries, filters, num_queries, self.dim());
              return run(b.nq, qp.k, [&](unsigned int* ids, float* dists) {
                self.batch_search(b.queries, b.filters, b.nq, query_method, qp, ids, dists);
              });
@@ -121,16 +165,16 @@ static void add_variant(py::module_& m, const std::string& sfx) {
 
   // python_bindings.cpp:119-127 — the tree over PrefilterIndex sub-indices
   py::class_<PreTree>(m, ("RangeFilterTreeIndex" + sfx).c_str())
-      .def(py::init([](FArray points, FArray filter_values, int32_t cutoff, size_t split_factor, BuildParams bp) {
-             Points p = check_points(points, filter_values);
+      .def(py::init([](TArray<T> points, FArray filter_values, int32_t cutoff, size_t split_factor, BuildParams bp) {
+             Points<T> p = check_points<T, METRIC>(points, filter_values);
              return new PreTree(p.data, filter_values.data(), p.n, p.dim, METRIC, cutoff, split_factor, bp);
            }),
            "points"_a, "filter_values"_a, "cutoff"_a = 1000, "split_factor"_a = 2,
            "build_params"_a = DEFAULT_BUILD_PARAMS)
       .def("batch_search",
-           [](PreTree& self, FArray queries, FArray filters, uint64_t num_queries, const std::string& query_method,
+           [](PreTree& self, TArray<T> queries, FArray filters, uint64_t num_queries, const std::string& query_method,
               QueryParams qp) {
-             Batch b = check_batch(queries, filters, num_queries, self.dim());
+             Batch<T> b = check_batch<T>(queries, filters, num_queries, self.dim());
              return run(b.nq, qp.k, [&](unsigned int* ids, float* dists) {
                self.batch_search(b.queries, b.filters, b.nq, query_method, qp, ids, dists);
              });
@@ -140,16 +184,16 @@ static void add_variant(py::module_& m, const std::string& sfx) {
       .def("_bucket_offsets", [](PreTree& self) { return self.bucket_offsets(); });
 
   py::class_<Super>(m, ("SuperOptimizedPostfilterTreeIndex" + sfx).c_str())
-      .def(py::init([](FArray points, FArray filter_values, int32_t cutoff, float split_factor, float shift_factor,
+      .def(py::init([](TArray<T> points, FArray filter_values, int32_t cutoff, float split_factor, float shift_factor,
                        BuildParams bp) {
-             Points p = check_points(points, filter_values);
+             Points<T> p = check_points<T, METRIC>(points, filter_values);
              return new Super(p.data, filter_values.data(), p.n, p.dim, METRIC, cutoff, split_factor, shift_factor, bp);
            }),
            "points"_a, "filter_values"_a, "cutoff"_a = 1000, "split_factor"_a = 2, "shift_factor"_a = 0.5,
            "build_params"_a = DEFAULT_BUILD_PARAMS)
       .def("batch_search",
-           [](Super& self, FArray queries, FArray filters, uint64_t num_queries, QueryParams qp) {
-             Batch b = check_batch(queries, filters, num_queries, self.dim());
+           [](Super& self, TArray<T> queries, FArray filters, uint64_t num_queries, QueryParams qp) {
+             Batch<T> b = check_batch<T>(queries, filters, num_queries, self.dim());
              return run(b.nq, qp.k, [&](unsigned int* ids, float* dists) { self.batch_search(b.queries, b.filters, b.nq, qp, ids, dists); });
            },
            "queries"_a, "filters"_a, "num_queries"_a, "query_params"_a)
@@ -179,8 +223,14 @@ PYBIND11_MODULE(_window_ann_b200, m) {
   py::class_<BuildParams>(m, "BuildParams")
       .def(py::init<long, long, double, std::string>(), "max_degree"_a, "limit"_a, "alpha"_a, "cache_path"_a);
 
-  add_variant<WS_METRIC_L2>(m, "FloatEuclidian");
-  add_variant<WS_METRIC_MIPS>(m, "FloatMips");
+  add_variant<float, WS_METRIC_L2>(m, "FloatEuclidian");
+  add_variant<float, WS_METRIC_MIPS>(m, "FloatMips");
+  // python_bindings.cpp:74-86,233-236 (registered as "UInt8…"; wrapper.py:244-330 asks for "Uint8…" and so
+  // never reaches them, SURVEY.md §A-10 — both spellings are not provided, only the registered one)
+  add_variant<uint8_t, WS_METRIC_L2>(m, "UInt8Euclidian");
+  add_variant<uint8_t, WS_METRIC_MIPS>(m, "UInt8Mips");
+  add_variant<int8_t, WS_METRIC_L2>(m, "Int8Euclidian");
+  add_variant<int8_t, WS_METRIC_MIPS>(m, "Int8Mips");
 
   m.def("device_count", []() {
     int c = 0;

@@ -9,6 +9,8 @@ container where /root/reference exists.  Committed outputs:
   tiny_pretree_ref_outputs.npz  the same windows through RangeFilterTreeIndexFloatEuclidian (the tree over
                                 PrefilterIndex sub-indices, python_bindings.cpp:119-127); `--only pretree`
                                 regenerates just this file
+  tiny_u8_ref_outputs.npz       the UInt8Euclidian / Int8Mips prefilter and prefilter-bucket tree classes on
+                                quantised data (1200 x 64; `--only u8`)
 
 Run: python tests/golden/make_golden.py      (after `make -C oracle ref`)
 """
@@ -26,7 +28,7 @@ os.environ["PARLAY_NUM_THREADS"] = "8"
 
 from conftest import _load_ext, find_ext  # noqa: E402
 from rangefilteredann_b200 import synth  # noqa: E402
-from golden_cases import tiny_cases, tiny_mips_cases, TINY, TINY_MIPS  # noqa: E402
+from golden_cases import tiny_cases, tiny_mips_cases, tiny_u8_cases, tiny_u8_dataset, TINY, TINY_MIPS, TINY_U8  # noqa: E402
 
 
 def pretree(ref):
@@ -46,10 +48,36 @@ def pretree(ref):
     print("wrote", len(out), "pretree arrays")
 
 
+def eight_bit(ref):
+    """UInt8Euclidian and Int8Mips: PrefilterIndex and the tree over prefilter buckets.  The graph classes
+    are not covered: the reference's own 8-bit Vamana build segfaults (observed with oracle/_ref on this
+    data, 1 and 8 threads, right after its first "beam search time" print), so it cannot produce vectors."""
+    out = {}
+    for sfx, signed in (("UInt8Euclidian", False), ("Int8Mips", True)):
+        data, queries, labels = tiny_u8_dataset(signed)
+        pre = getattr(ref, "PrefilterIndex" + sfx)(data, labels)
+        ptree = getattr(ref, "RangeFilterTreeIndex" + sfx)(data, labels, TINY_U8["cutoff"], 2, ref.BuildParams(64, 500, 1.0, ""))
+        for name, windows, qkw in tiny_u8_cases(labels):
+            nq = len(windows)
+            qp = ref.QueryParams(10, qkw["beam"], 1.35, 10_000_000, 10_000, qkw["mult"], qkw["max_beam"], None, False)
+            out[f"{sfx}/{name}/windows"] = windows
+            ids, d = pre.batch_search(queries[:nq], windows, nq, qp)
+            out[f"{sfx}/{name}/prefilter/ids"], out[f"{sfx}/{name}/prefilter/dists"] = ids, d
+            for method in ("fenwick", "optimized_postfilter", "three_split"):
+                ids, d = ptree.batch_search(queries[:nq], windows, nq, method, qp)
+                out[f"{sfx}/{name}/pretree_{method}/ids"], out[f"{sfx}/{name}/pretree_{method}/dists"] = ids, d
+    np.savez_compressed(os.path.join(HERE, "tiny_u8_ref_outputs.npz"), **out)
+    print("wrote", len(out), "8-bit arrays")
+
+
 def main():
     ref = _load_ext(find_ext(os.path.join(ROOT, "oracle", "_ref")))
-    pretree(ref)
-    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "pretree":
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
+    if only in (None, "pretree"):
+        pretree(ref)
+    if only in (None, "u8"):
+        eight_bit(ref)
+    if only is not None:
         return
     data, queries, labels = synth.make_dataset(TINY["n"], TINY["d"], TINY["nq"], TINY["seed"])
     out = {}

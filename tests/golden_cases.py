@@ -45,3 +45,26 @@ def tiny_mips_cases(labels):
         w = synth.make_windows(labels, power, TINY_MIPS["nq"], seed=200 + power)
         cases.append((f"mips_pow{power}", w, dict(beam=10, mult=2, max_beam=10000, prefilter=True)))
     return cases
+
+
+# ---- 8-bit variants (python_bindings.cpp:74-86,233-236).  64 columns: the reference's own 8-bit point
+# storage needs rows that are a multiple of 64 bytes (it crashes on d = 16).
+TINY_U8 = dict(n=1200, d=64, nq=32, seed=11, cutoff=600)
+
+
+def tiny_u8_dataset(signed: bool):
+    """Quantised Gaussian-mixture data, queries and unique labels for the 8-bit classes."""
+    data, queries, labels = synth.make_dataset(TINY_U8["n"], TINY_U8["d"], TINY_U8["nq"], TINY_U8["seed"])
+    if signed:
+        quant = lambda x: np.clip(np.round(x * 24.0), -128, 127).astype(np.int8)
+    else:
+        quant = lambda x: np.clip(np.round(x * 24.0 + 128.0), 0, 255).astype(np.uint8)
+    return quant(data), quant(queries), labels
+
+
+def tiny_u8_cases(labels):
+    cases = []
+    for power in (-5, -2, 0):
+        w = synth.make_windows(labels, power, TINY_U8["nq"], seed=400 + power)
+        cases.append((f"u8_pow{power}", w, dict(beam=20, mult=2, max_beam=10000)))
+    return cases

@@ -67,8 +67,9 @@ def test_create_validation():
 
 
 def test_engine_module_surface(engine):
-    for sfx in ("FloatEuclidian", "FloatMips"):
-        for cls in ("PrefilterIndex", "PostfilterVamanaIndex", "VamanaRangeFilterTreeIndex",
+    # every index class x variant the reference registers (python_bindings.cpp:111-157,231-236)
+    for sfx in ("FloatEuclidian", "FloatMips", "UInt8Euclidian", "UInt8Mips", "Int8Euclidian", "Int8Mips"):
+        for cls in ("PrefilterIndex", "PostfilterVamanaIndex", "RangeFilterTreeIndex", "VamanaRangeFilterTreeIndex",
                     "SuperOptimizedPostfilterTreeIndex"):
             assert hasattr(engine, cls + sfx)
     qp = engine.QueryParams(10, 20, 1.35, 10_000_000, 10_000, 1, 10000, None, False)
@@ -76,3 +77,8 @@ def test_engine_module_surface(engine):
     assert engine.BuildParams(64, 500, 1.0, "x/") is not None
     with pytest.raises(RuntimeError, match="2-dimensional"):
         engine.PrefilterIndexFloatEuclidian(np.zeros(4, np.float32), np.zeros(4, np.float32))
+    # 8-bit variants: dimensions beyond the exactly-representable integer range are refused up front
+    with pytest.raises(RuntimeError, match="8-bit variants are supported up to 258"):
+        engine.PrefilterIndexUInt8Euclidian(np.zeros((4, 300), np.uint8), np.arange(4, dtype=np.float32))
+    with pytest.raises(RuntimeError, match="up to 1023"):
+        engine.PrefilterIndexInt8Mips(np.zeros((4, 1024), np.int8), np.arange(4, dtype=np.float32))

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN
-from golden_cases import TINY, TINY_MIPS, tiny_cases, tiny_mips_cases
+from golden_cases import TINY, TINY_MIPS, TINY_U8, tiny_cases, tiny_mips_cases, tiny_u8_cases, tiny_u8_dataset
 from oracle_api import Oracle
 from rangefilteredann_b200 import synth
 
@@ -103,3 +103,25 @@ def test_oracle_matches_reference_mips(method):
         diff = ids != rids
         for i, j in zip(*np.nonzero(diff)):
             assert (rd[i] == rd[i, j]).sum() > 1 or rd[i, j] == rd[i, -1]
+
+
+@pytest.mark.parametrize("sfx,signed,metric", [("UInt8Euclidian", False, 0), ("Int8Mips", True, 1)])
+@pytest.mark.parametrize("dist_mode", [0, 1])
+def test_oracle_matches_reference_8bit(sfx, signed, metric, dist_mode):
+    """The 8-bit classes (python_bindings.cpp:233-236) compute integer distances cast to float
+    (euclidian_point.h:44-60, mips_point.h:44-58).  On the widened fp32 data every partial sum is an
+    integer below 2^24, so BOTH summation orders of the oracle must reproduce the reference bit for bit."""
+    data, queries, labels = tiny_u8_dataset(signed)
+    gold = np.load(os.path.join(GOLDEN, "tiny_u8_ref_outputs.npz"))
+    fdata, fq = data.astype(np.float32), queries.astype(np.float32)
+    pre = Oracle("prefilter", fdata, labels, None, metric=metric, dist_mode=dist_mode)
+    tree = Oracle("pretree", fdata, labels, None, metric=metric, dist_mode=dist_mode, cutoff=TINY_U8["cutoff"])
+    for name, windows, qkw in tiny_u8_cases(labels):
+        nq = len(windows)
+        runs = [("prefilter", pre.batch("prefilter", fq[:nq], windows, pad_id=0xFFFFFFFF))]
+        runs += [(f"pretree_{m}", tree.batch(m, fq[:nq], windows, pad_id=0)) for m in ("fenwick", "optimized_postfilter", "three_split")]
+        for key, (ids, d) in runs:
+            rids, rd = gold[f"{sfx}/{name}/{key}/ids"], gold[f"{sfx}/{name}/{key}/dists"]
+            assert np.array_equal(d, rd), f"{sfx}/{name}/{key}"
+            for i, j in zip(*np.nonzero(ids != rids)):  # integer distances tie often; the reference's sort is unstable
+                assert (rd[i] == rd[i, j]).sum() > 1 or rd[i, j] == rd[i, -1], f"{sfx}/{name}/{key} row {i} col {j}"
