@@ -7,8 +7,8 @@
 Metric: QPS at recall@10 >= 0.95 over the 17 filter fractions 2^-16..2^0 (k = 10, 10 000
 queries per fraction).  One "step" = one pass over all 17 fractions: for each fraction the
 batch of `nq` queries is answered by the fastest (method, beam, final_multiply) operating
-point that reaches recall@10 >= 0.95 — methods: prefilter (streaming scan, or the tensor-core
-sweep "prefilter_tc" — same rows), range-filter tree ("fenwick"), optimized postfilter — chosen
+point that reaches recall@10 >= 0.95 — methods: prefilter (task path, the one-launch kernel
+"prefilter_direct", or the tensor-core sweep "prefilter_tc" — same rows), range-filter tree ("fenwick"), optimized postfilter — chosen
 in an untimed sweep, exactly the pareto rule of the
 reference's plots (experiments/plot.py:14-28).  value = queries answered per second.
 
@@ -47,6 +47,7 @@ K = 10
 BEAMS = [10, 20, 40, 80, 160, 320]
 MULTS = [1, 2, 4]
 RECALL_TARGET = 0.95
+PREFILTER_OPS = ("prefilter", "prefilter_direct", "prefilter_tc")
 
 
 def log(*a):
@@ -215,10 +216,12 @@ class EngineRunner:
 
     def launch_dev(self, power, op):
         method, beam, mult = op
-        if method in ("prefilter", "prefilter_tc"):
-            # "prefilter_tc": the same PrefilterIndex::batch_search, answered by the tensor-core sweep +
-            # fp32 re-rank (csrc/ws_gemm.cu) instead of the streaming scan; rows are bit-identical
+        if method in PREFILTER_OPS:
+            # three ways the engine answers the same PrefilterIndex::batch_search, rows bit-identical:
+            # "prefilter" = task path (K3 -> K1 scan -> K4), "prefilter_direct" = the one-launch kernel for
+            # small windows (K1d), "prefilter_tc" = tensor-core sweep + fp32 re-rank (csrc/ws_gemm.cu)
             self.h.set_option("gemm_prefilter", 1 if method == "prefilter_tc" else 0)
+            self.h.set_option("prefilter_direct", 1 if method == "prefilter_direct" else 0)
             self.h.prefilter_batch(self.dq, self.dwin[power], self.nq, K, self.dids, self.ddists, device_ptrs=True)
         else:
             qp = self.capi.query_params(k=K, beam=beam, final_multiply=mult)
@@ -249,10 +252,11 @@ def choose_operating_points(runner: EngineRunner, gts, rank):
         r = recall_at_k(runner.fetch(), gts[p])
         ms = runner.time_dev(p, ("prefilter", 0, 0))
         per_method["prefilter"] = dict(op=("prefilter", 0, 0), recall=r, ms=ms)
-        runner.launch_dev(p, ("prefilter_tc", 0, 0))
-        r = recall_at_k(runner.fetch(), gts[p])
-        ms = runner.time_dev(p, ("prefilter_tc", 0, 0))
-        per_method["prefilter_tc"] = dict(op=("prefilter_tc", 0, 0), recall=r, ms=ms)
+        for alt in ("prefilter_direct", "prefilter_tc"):
+            runner.launch_dev(p, (alt, 0, 0))
+            r = recall_at_k(runner.fetch(), gts[p])
+            ms = runner.time_dev(p, (alt, 0, 0))
+            per_method[alt] = dict(op=(alt, 0, 0), recall=r, ms=ms)
         for method in ("fenwick", "optimized_postfilter"):
             best = None
             for mult in (MULTS if method == "optimized_postfilter" else [1]):
@@ -362,10 +366,11 @@ def run_engine(args, rank, world, local_rank):
     def step_e2e():
         for p in POWERS:
             method, beam, mult = ops[p]
-            if method in ("prefilter", "prefilter_tc"):
+            if method in PREFILTER_OPS:
                 ids = np.empty((cfg["nq"], K), np.uint32)
                 dd = np.empty((cfg["nq"], K), np.float32)
                 h.set_option("gemm_prefilter", 1 if method == "prefilter_tc" else 0)
+                h.set_option("prefilter_direct", 1 if method == "prefilter_direct" else 0)
                 h.prefilter_batch(hq, hw[p], cfg["nq"], K, ids, dd)
             else:
                 qp = eng.QueryParams(K, beam, 1.35, 10_000_000, 10_000, mult, 10000, None, False)
@@ -524,7 +529,7 @@ def cpu_baseline(args, cfg, data, queries, labels, windows, gts, table, ops):
     for p in POWERS:
         best = None
         for method, v in table[p].items():
-            if method == "prefilter_tc":  # the reference has one prefilter implementation (timed as "prefilter")
+            if method in ("prefilter_tc", "prefilter_direct"):  # the reference has one prefilter implementation (timed as "prefilter")
                 continue
             ns = min(args.cpu_sample, cfg["nq"])
             t_probe, _ = ref_time(ref, tree, pre, queries, windows[p], v["op"], min(64, ns))

@@ -204,6 +204,8 @@ int ws_index_reset_stats(ws_index* idx);
 int ws_index_launch_count(const ws_index* idx, uint64_t* out);
 /* tuning knobs: "emulate_query_id_skip" (beamSearch.h:128 `a == p.id()`, default 1),
  * "scan_chunk" (rows per brute-force task), "profile_kernels", "warp_tiers", "warp_hash",
+ * "prefilter_direct" (one-launch prefilter kernel for batches of small windows: 0 never, 1 always,
+ * 2 auto = host-sampled mean window <= scan_chunk),
  * "gemm_prefilter" (tensor-core prefilter: 0 never, 1 whenever eligible, 2 auto = host-sampled mean
  * window >= "gemm_min_window"), "gemm_items", "gemm_min_tiles", "gemm_chunk_mb",
  * "warp_scan", "fuse_scan", "hash_factor", "build_expand_width" (nodes expanded per step by

@@ -1264,6 +1264,50 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_SCAN_MINBLOCKS) ws_s
 
 
 // ------------------------------------------------------------------------------------------
+// K1d: PrefilterIndex::batch_search in ONE launch for batches of small windows
+//      (prefiltering.h:124-204).  With a few hundred points per window the batch is bound by the
+//      launch chain (memset -> K3 -> K1 -> K4: ~60 us for 10 000 queries), not by bytes, so here a
+//      warp does everything for its query: the two r = n-1 binary searches on the labels
+//      (prefiltering.h:159-184), the streaming scan of [start, end) (ws_scan_task, the arithmetic
+//      and folding of K1 — rows are bit-identical), decode, padding and the final row.  No task
+//      slots, no queues, no control words.  Any window size is answered correctly (the warp
+//      streams the whole window); the host only routes batches here when windows are small.
+// ------------------------------------------------------------------------------------------
+struct WsPrefilterDirectArgs {
+  WsScanArgs s;            // tasks / q_in* unused
+  const float* labels;     // [n] sorted
+  uint64_t n;
+  const float* windows;    // [nq][2]
+  uint32_t nq;
+};
+
+template <int KQ, int METRIC, bool EXACT>
+__global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_SCAN_MINBLOCKS) ws_prefilter_direct_kernel(WsPrefilterDirectArgs A) {
+  __shared__ uint64_t s_fr[WS_WARPS_PER_CTA][128];
+  __shared__ uint64_t s_sk[WS_WARPS_PER_CTA][64];
+  __shared__ uint64_t s_sk2[WS_WARPS_PER_CTA][64];
+  __shared__ int s_cpos[WS_WARPS_PER_CTA][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tl = lane & (WS_TEAM - 1);
+  const int B = (int)A.s.k;
+  WsScanOut so;
+  so.vecs = A.s.vecs; so.dpad = A.s.dpad; so.res_keys = A.s.res_keys; so.res_cnt = A.s.res_cnt; so.stats = A.s.stats;
+  so.out_ids = A.s.out_ids; so.out_dists = A.s.out_dists; so.decode = A.s.decode; so.pad_id = A.s.pad_id;
+  const uint32_t nwarps = gridDim.x * WS_WARPS_PER_CTA;
+  for (uint32_t qi = blockIdx.x * WS_WARPS_PER_CTA + warp; qi < A.nq; qi += nwarps) {
+    const float lo = A.windows[2 * (size_t)qi], hi = A.windows[2 * (size_t)qi + 1];
+    WsTask task;
+    task.query = qi; task.node = -1; task.lo = lo; task.hi = hi; task.beam = 0; task.flags = WS_TF_SOLO;
+    task.a = (uint32_t)ws_prefilter_bound(A.labels, A.n, lo);  // warp-uniform: every lane walks the same path
+    task.b = (uint32_t)ws_prefilter_bound(A.labels, A.n, hi);
+    if (task.b < task.a) task.b = task.a;  // inverted window: empty, the row is all pads
+    float4 q[KQ];
+    ws_load_query_global<KQ, EXACT>(A.s.queries, A.s.dim, A.s.dpad, qi, tl, q);
+    ws_scan_task<KQ, METRIC, EXACT>(so, task, qi, q, B, s_fr[warp], s_sk[warp], s_sk2[warp], s_cpos[warp]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K4b: merge of per-shard partial top-k lists after the all-gather of the label-sharded mode
 //      (SURVEY.md §8e-2): parts x [nq][k] (id, dist) rows -> [nq][k], ascending (dist, id);
 //      pad rows (dist == FLT_MAX) are ignored and re-created at the tail.

@@ -134,6 +134,7 @@ struct ws_index {
   uint64_t launches = 0;
 
   // tensor-core prefilter (ws_gemm.cuh)
+  int64_t opt_direct = 2;        // one-launch prefilter (K1d): 0 never, 1 always, 2 auto (host-sampled mean window <= scan_chunk)
   int64_t opt_gemm = 2;          // 0 never, 1 whenever eligible, 2 auto (host-sampled mean window >= opt_gemm_min_window)
   int64_t opt_gemm_min_window = 2048;
   int64_t opt_gemm_items = 0;    // target work items per plan (0: 2 per SM)
@@ -592,6 +593,17 @@ static cudaError_t ws_launch_scan_warp_t(bool exact, int grid, cudaStream_t s, c
   return cudaGetLastError();
 }
 template <int KQ, int METRIC>
+static cudaError_t ws_launch_prefilter_direct_t(bool exact, int grid, cudaStream_t s, const WsPrefilterDirectArgs& a) {
+  if (exact) ws_prefilter_direct_kernel<KQ, METRIC, true><<<grid, WS_WARPS_PER_CTA * 32, 0, s>>>(a);
+  else ws_prefilter_direct_kernel<KQ, METRIC, false><<<grid, WS_WARPS_PER_CTA * 32, 0, s>>>(a);
+  return cudaGetLastError();
+}
+template <int KQ, int METRIC>
+static cudaError_t ws_prefilter_direct_occupancy_t(bool exact, int* blocks) {
+  if (exact) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_prefilter_direct_kernel<KQ, METRIC, true>, WS_WARPS_PER_CTA * 32, 0);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_prefilter_direct_kernel<KQ, METRIC, false>, WS_WARPS_PER_CTA * 32, 0);
+}
+template <int KQ, int METRIC>
 static cudaError_t ws_scan_warp_occupancy_t(bool exact, int* blocks) {
   if (exact) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_scan_warp_kernel<KQ, METRIC, true>, WS_WARPS_PER_CTA * 32, 0);
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_scan_warp_kernel<KQ, METRIC, false>, WS_WARPS_PER_CTA * 32, 0);
@@ -854,29 +866,60 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
     dids = (uint32_t*)idx->d_ids.p;
     ddists = (float*)idx->d_dists.p;
   }
-  // ctrl layout: [0..5] queue counts (beam tiers 0..4, scan = 5), [8..13] queue heads, [16] overflow
-  uint32_t* ctrl = (uint32_t*)idx->ctrl.p;
-  WS_CUDA(cudaMemsetAsync(ctrl, 0, 64 * sizeof(uint32_t), st));
-  uint32_t* queues = (uint32_t*)idx->queues.p;
-
-  // ---- prefilter batches with large windows: dense query x slice contraction on the tensor cores
+  // ---- prefilter batches: how the batch is answered depends on the window sizes.  With host buffers a
+  // sample of the batch's windows is measured here; device-pointer calls take the options as they are.
+  double mean_window = -1.0;  // rows per window over a sample of 64 queries (host buffers only)
+  if (plan.mode == WS_MODE_PREFILTER && !dev_ptrs && nq >= 256) {
+    const std::vector<float>& L = idx->h_labels;
+    const uint64_t step = std::max<uint64_t>(1, nq / 64);
+    double sum = 0; uint64_t cnt = 0;
+    for (uint64_t i = 0; i < nq; i += step, cnt++) {
+      const uint64_t a = std::lower_bound(L.begin(), L.end(), windows[2 * i]) - L.begin();
+      const uint64_t b = std::lower_bound(L.begin(), L.end(), windows[2 * i + 1]) - L.begin();
+      sum += b > a ? (double)(b - a) : 0.0;
+    }
+    if (cnt > 0) mean_window = sum / (double)cnt;
+  }
+  // large windows: dense query x slice contraction on the tensor cores (K1g)
   bool use_gemm = false;
   if (plan.mode == WS_MODE_PREFILTER && idx->opt_gemm != 0 && ws_gemm_eligible(idx, k)) {
     if (idx->opt_gemm == 1) use_gemm = true;
-    else if (!dev_ptrs && nq >= 256) {  // auto: mean window size of a host-side sample
-      const std::vector<float>& L = idx->h_labels;
-      const uint64_t step = std::max<uint64_t>(1, nq / 64);
-      double sum = 0; uint64_t cnt = 0;
-      for (uint64_t i = 0; i < nq; i += step, cnt++) {
-        const uint64_t a = std::lower_bound(L.begin(), L.end(), windows[2 * i]) - L.begin();
-        const uint64_t b = std::lower_bound(L.begin(), L.end(), windows[2 * i + 1]) - L.begin();
-        sum += b > a ? (double)(b - a) : 0.0;
-      }
-      use_gemm = cnt > 0 && sum / (double)cnt >= (double)idx->opt_gemm_min_window;
-    }
+    else use_gemm = mean_window >= (double)idx->opt_gemm_min_window;
   }
+  // small windows: the whole batch in one launch (K1d)
+  bool use_direct = false;
+  if (plan.mode == WS_MODE_PREFILTER && !use_gemm && k <= 128 && idx->opt_warp_scan && idx->opt_direct != 0) {
+    if (idx->opt_direct == 1) use_direct = true;
+    else use_direct = mean_window >= 0.0 && mean_window <= (double)idx->opt_scan_chunk;
+  }
+  // ctrl layout: [0..5] queue counts (beam tiers 0..4, scan = 5), [8..13] queue heads, [16] overflow
+  uint32_t* ctrl = (uint32_t*)idx->ctrl.p;
+  if (!use_direct) WS_CUDA(cudaMemsetAsync(ctrl, 0, 64 * sizeof(uint32_t), st));
+  uint32_t* queues = (uint32_t*)idx->queues.p;
+
   if (use_gemm) {
     WS_TRY(ws_run_prefilter_gemm(idx, dq, dw, nq, k, dids, ddists, plan.use_decode ? idx->d_decode : nullptr, plan.pad_id, ctrl + 16));
+  } else if (use_direct) {
+    const int kq = ws_pick_kq(idx->dpad);
+    const bool exact_rows = (uint32_t)kq * WS_TEAM * 4 == idx->dpad;
+    WsPrefilterDirectArgs pa;
+    pa.s.vecs = idx->d_vecs; pa.s.queries = dq; pa.s.dim = idx->dim; pa.s.dpad = idx->dpad;
+    pa.s.tasks = nullptr; pa.s.res_keys = (uint64_t*)idx->res_keys.p; pa.s.res_cnt = (uint32_t*)idx->res_cnt.p;
+    pa.s.k = k; pa.s.q_in = nullptr; pa.s.q_in_count = nullptr; pa.s.q_head = nullptr; pa.s.stats = idx->d_stats;
+    pa.s.out_ids = dids; pa.s.out_dists = ddists; pa.s.decode = plan.use_decode ? idx->d_decode : nullptr; pa.s.pad_id = plan.pad_id;
+    pa.labels = idx->d_labels; pa.n = idx->n; pa.windows = dw; pa.nq = (uint32_t)nq;
+    int occ = 0;
+#define WS_OCD(KQ_, M_) { cudaError_t _e = ws_prefilter_direct_occupancy_t<KQ_, M_>(exact_rows, &occ); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(_e)); }
+    WS_DISPATCH_KQ(kq, idx->metric, WS_OCD);
+#undef WS_OCD
+    if (occ < 1) return ws_fail(WS_ERR_CUDA, "prefilter kernel does not fit on an SM");
+    const int grid = (int)std::min<uint64_t>((nq + WS_WARPS_PER_CTA - 1) / WS_WARPS_PER_CTA, (uint64_t)idx->num_sms * occ);
+#define WS_LPD(KQ_, M_) { cudaError_t _e = ws_launch_prefilter_direct_t<KQ_, M_>(exact_rows, grid, st, pa); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "prefilter kernel launch: %s", cudaGetErrorString(_e)); }
+    {
+      WsKernelScope ks(idx, 6);
+      WS_DISPATCH_KQ(kq, idx->metric, WS_LPD);
+    }
+#undef WS_LPD
   } else {
   // ---- tiers: which launch takes fresh graph tasks
   const int kq = ws_pick_kq(idx->dpad);
@@ -1055,7 +1098,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
     uint32_t h_overflow = 0;
     WS_CUDA(cudaMemcpyAsync(ids, dids, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     WS_CUDA(cudaMemcpyAsync(dists, ddists, nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
-    WS_CUDA(cudaMemcpyAsync(&h_overflow, ctrl + 16, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (!use_direct) WS_CUDA(cudaMemcpyAsync(&h_overflow, ctrl + 16, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     WS_CUDA(cudaStreamSynchronize(st));
     if (h_overflow) return ws_fail(WS_ERR_STATE, "task slot capacity %u overflowed (internal bound too small)", cap);
   }
@@ -1506,6 +1549,9 @@ int ws_index_set_option(ws_index* idx, const char* name, int64_t value) {
   } else if (s == "build_expand_width") {
     if (value < 1 || value > 8) return ws_fail(WS_ERR_BADARG, "build_expand_width must be 1..8");
     idx->opt_build_expand = value;
+  } else if (s == "prefilter_direct") {
+    if (value < 0 || value > 2) return ws_fail(WS_ERR_BADARG, "prefilter_direct must be 0 (never), 1 (always) or 2 (auto)");
+    idx->opt_direct = value;
   } else if (s == "gemm_prefilter") {
     if (value < 0 || value > 2) return ws_fail(WS_ERR_BADARG, "gemm_prefilter must be 0 (never), 1 (always when eligible) or 2 (auto)");
     idx->opt_gemm = value;

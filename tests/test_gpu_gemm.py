@@ -22,6 +22,7 @@ def make(engine, n, d, nq, angular=False, seed=0):
 
 def run(h, queries, windows, k, mode):
     h.set_option("gemm_prefilter", mode)
+    h.set_option("prefilter_direct", 0)  # the baseline is the task path (K3 -> K1 -> K4)
     nq = len(windows)
     ids = np.empty((nq, k), np.uint32)
     dists = np.empty((nq, k), np.float32)
