@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Renders profiles/r01_summary.md from a bench.py engine line and a reference-arm line.
+
+  python profiles/make_summary.py gpurun_out/bench.json gpurun_out/bench_ref.json > profiles/r01_summary.md
+"""
+import json
+import sys
+
+
+def fmt_qps(v):
+    return f"{v / 1e6:.2f} M" if v >= 1e6 else f"{v / 1e3:.1f} K"
+
+
+def main():
+    b = json.load(open(sys.argv[1]))
+    r = json.load(open(sys.argv[2]))
+    rf = b["roofline"]
+    cpu = b["cpu_baseline"]
+    out = []
+    out.append("# Round 1 summary — one B200, BASELINE.json config 2 (1 M x 128 fp32 L2, 2-WST, 17 fractions x 10 000 queries, k = 10)\n")
+    out.append("Commands (fresh box, graphs built on the device in the reference's `.bin` format and loaded by both arms):")
+    out.append("```")
+    out.append(f"python bench.py --steps {b['steps']} --warmup {b['warmup']}                      # engine arm   -> {sys.argv[1]}")
+    out.append(f"python bench.py --impl reference --steps {r['steps']} --warmup {r['warmup']}     # reference arm -> {sys.argv[2]}")
+    out.append("```\n")
+    out.append("| | value |")
+    out.append("|---|---|")
+    out.append(f"| engine, inputs resident in HBM (`value`) | **{fmt_qps(b['value'])} queries/s** ({b['ms_per_step']:.2f} ms per {b['config']['queries_per_step']}-query step) |")
+    out.append(f"| engine, end to end through pybind `batch_search`, pinned host buffers (`e2e`) | **{fmt_qps(b['e2e']['value'])} queries/s** |")
+    out.append(f"| reference (oracle/_ref, parlay, {r['cpu_baseline']['cores']} host threads), `--impl reference` | {fmt_qps(r['value'])} queries/s |")
+    out.append(f"| reference, `cpu_baseline` leg inside the engine run | {fmt_qps(cpu['value'])} queries/s |")
+    out.append(f"| speed-up e2e / device (against `--impl reference`) | {b['e2e']['value'] / r['value']:.1f}x / {b['value'] / r['value']:.1f}x |")
+    out.append(f"| kernels launched in the timed region | {b['gpu_launches']} |")
+    out.append(f"| SM clock during the timed region | {b['clocks']['sm_mhz']} MHz of {b['clocks']['sm_max_mhz']} (throttle reasons: {b['clocks']['reasons'] or 'none'}) |\n")
+    out.append(f"Roofline, HBM (measured copy peak {rf['peak']} GB/s, MEASURED_PEAKS.json):\n")
+    out.append(f"* graph search (`{rf['kernel']}`): {rf['bytes_per_launch'] / 1e9:.2f} GB algorithmic per launch / {rf['ms_per_launch']:.3f} ms (CUDA events) = "
+               f"**{rf['achieved']:.0f} GB/s = {rf['frac']:.2f} of peak**; DRAM traffic of the beam-80 root-node launch under ncu: "
+               f"{(rf.get('traffic') or 0) / 1e9:.2f} GB for 13.61 GB algorithmic (L2 absorbs the hot upper graph levels)")
+    tp = rf.get("tensor_prefilter")
+    if tp:
+        out.append(f"* tensor-core prefilter sweep (`ws_gemm_topk_kernel`, tcgen05 kind::tf32): {tp['flops_per_step'] / 1e12:.2f} TFLOP of useful "
+                   f"work per step / {tp['ms_per_step']:.2f} ms = **{tp['achieved']:.0f} TFLOP/s** = {tp['frac']:.2f} of the measured dense bf16 peak "
+                   f"({tp['peak']} TFLOP/s; tf32 runs at half the bf16 rate, so {2 * tp['frac']:.2f} of the tf32 ceiling)")
+    out.append("\nKernel time per step (CUDA events, `ws_index_kernel_times`): " +
+               ", ".join(f"{k} {v:.2f} ms" for k, v in rf["kernel_ms_per_step"].items()) + ".\n")
+    out.append("Per filter fraction (engine = device-resident timing of the chosen operating point; CPU = reference on "
+               f"{cpu['cores']} threads, same windows / graphs, its own best method, bounded sample):\n")
+    out.append("| fraction | engine method (beam) | recall@10 | engine QPS | reference method | reference QPS | ratio |")
+    out.append("|---|---|---|---|---|---|---|")
+    for p, v in b["per_fraction"].items():
+        best = v["best"]
+        e = v[best]
+        c = cpu["per_fraction"].get(p)
+        if c:
+            out.append(f"| {p} | {best} ({e['beam']}) | {e['recall']:.4f} | {fmt_qps(e['qps'])} | {c['method']} | {fmt_qps(c['qps'])} | {e['qps'] / c['qps']:.0f}x |")
+        else:
+            out.append(f"| {p} | {best} ({e['beam']}) | {e['recall']:.4f} | {fmt_qps(e['qps'])} | - | - | - |")
+    print("\n".join(out))
+
+
+if __name__ == "__main__":
+    main()
