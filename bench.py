@@ -410,7 +410,6 @@ def run_engine(args, rank, world, local_rank):
     scan_ms = ktimes.get("scan", {}).get("ms", 0.0)
     # graph search: visited * R*4 + dist_cmps * d_pad*4 + (beam*4 per search)
     beam_bytes = stats["visited"] * 64 * 4 + stats["dist_cmps"] * dpad_bytes + stats["beam_sum"] * 4
-    scan_bytes = stats["scan_points"] * dpad_bytes
     # tensor-core prefilter sweep: 2*d flops per (query, in-window point); the points are
     # counted from the windows of the fractions whose operating point is prefilter_tc
     gemm_ms = ktimes.get("gemm_sweep", {}).get("ms", 0.0)
@@ -428,34 +427,59 @@ def run_engine(args, rank, world, local_rank):
                                     "dense rate is half of bf16",
                      "ms_per_step": round(gemm_ms / args.steps, 4),
                      "flops_per_step": gemm_flops / args.steps}
-    if beam_ms >= scan_ms:
+    # streaming-scan prefilter (task path or one-launch kernel): rows * d_pad * 4, rows counted
+    # from the windows of the fractions answered that way (the device counter also counts the tensor-core
+    # path's windows, so it cannot be used here)
+    sorted_labels = np.sort(labels)
+    win_rows = {p: int(np.sum((np.searchsorted(sorted_labels, windows[p][:, 1]) -
+                               np.searchsorted(sorted_labels, windows[p][:, 0])).clip(min=0))) for p in POWERS}
+    scan_bytes = sum(win_rows[p] for p in POWERS if ops[p][0] in ("prefilter", "prefilter_direct")) * args.steps * dpad_bytes
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    except Exception:
+        tr = {}
+
+    def traffic_of(key):
+        ent = tr.get(key)
+        if not ent:
+            return None, None
+        return int(ent["traffic_bytes"]), (f"ncu --set full capture of one launch ({ent['launch']}): {ent['traffic_bytes'] / 1e9:.2f} GB "
+                                           f"DRAM read+write for {ent['algorithmic']} algorithmic ({ent['source']}); the per-launch "
+                                           f"figures beside it are means over this run's launches")
+
+    cands = []
+    if beam_ms > 0:
         # per-launch figures refer to the launches of the tier that carries the time (each batch also launches the
         # tail tiers, which find their queues empty and return within microseconds)
         top = max((kn for kn in ktimes if kn.startswith("beam")), key=lambda kn: ktimes[kn]["ms"])
-        dom, dom_ms, dom_bytes, dom_launches = "ws_beam_warp_kernel (+ ws_beam_cta2_kernel tail tiers)", beam_ms, beam_bytes, ktimes[top]["launches"]
-    else:
-        dom, dom_ms, dom_bytes = "ws_scan_kernel", scan_ms, scan_bytes
-        dom_launches = ktimes["scan"]["launches"]
-    achieved = dom_bytes / (dom_ms / 1000.0) / 1e9 if dom_ms > 0 else 0.0
-    # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture of one of its launches
-    traffic, traffic_note = None, None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        ent = tr["ws_beam_warp_kernel" if beam_ms >= scan_ms else "ws_scan_warp_kernel"]
-        traffic = int(ent["traffic_bytes"])
-        traffic_note = (f"ncu capture of one launch ({ent['launch']}): {ent['traffic_bytes'] / 1e9:.2f} GB DRAM for "
-                        f"{ent['algorithmic_bytes'] / 1e9:.2f} GB algorithmic ({ent['source']}); bytes_per_launch above "
-                        f"is the mean over this run's launches")
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
-                "bytes_per_launch": int(dom_bytes / max(1, dom_launches)),
-                "ms_per_launch": round(dom_ms / max(1, dom_launches), 4),
-                "beam_GBps": round(beam_bytes / (beam_ms / 1000.0) / 1e9, 1) if beam_ms > 0 else None,
-                "scan_GBps": round(scan_bytes / (scan_ms / 1000.0) / 1e9, 1) if scan_ms > 0 else None,
-                "kernel_ms_per_step": {kname: round(v["ms"] / args.steps, 4) for kname, v in ktimes.items()},
-                "tensor_prefilter": gemm_info}
+        nl = max(1, ktimes[top]["launches"])
+        ach = beam_bytes / (beam_ms / 1000.0) / 1e9
+        t, tn = traffic_of("ws_beam_warp_kernel")
+        cands.append({"bound": "hbm", "kernel": "ws_beam_warp_kernel (+ ws_beam_cta2_kernel tail tiers)", "achieved": round(ach, 1),
+                      "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": t, "traffic_note": tn,
+                      "peak_source": peak_src, "bytes_per_launch": int(beam_bytes / nl), "ms_per_launch": round(beam_ms / nl, 4),
+                      "ms_per_step": round(beam_ms / args.steps, 4)})
+    if scan_ms > 0 and scan_bytes > 0:
+        nl = max(1, ktimes["scan"]["launches"])
+        ach = scan_bytes / (scan_ms / 1000.0) / 1e9
+        t, tn = traffic_of("ws_scan_warp_kernel")
+        cands.append({"bound": "hbm", "kernel": "ws_scan_warp_kernel / ws_prefilter_direct_kernel", "achieved": round(ach, 1),
+                      "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": t, "traffic_note": tn,
+                      "peak_source": peak_src + "; windows of one batch overlap, so rows are shared through L2 and the "
+                                                "no-reuse byte count can exceed the HBM peak (SURVEY.md §8d)",
+                      "bytes_per_launch": int(scan_bytes / nl), "ms_per_launch": round(scan_ms / nl, 4),
+                      "ms_per_step": round(scan_ms / args.steps, 4)})
+    if gemm_info:
+        nl = max(1, ktimes["gemm_sweep"]["launches"])
+        t, tn = traffic_of("ws_gemm_topk_kernel")
+        g = dict(gemm_info)
+        g.update({"traffic": t, "traffic_note": tn, "flops_per_launch": gemm_flops / nl, "ms_per_launch": round(gemm_ms / nl, 4)})
+        cands.append(g)
+    cands.sort(key=lambda c: -c["ms_per_step"])
+    roofline = dict(cands[0]) if cands else {"bound": "hbm", "achieved": 0.0, "peak": peak, "unit": "GB/s", "frac": 0.0, "traffic": None}
+    roofline["dominant_by"] = "kernel time per step (CUDA events)"
+    roofline["other_kernels"] = cands[1:]
+    roofline["kernel_ms_per_step"] = {kname: round(v["ms"] / args.steps, 4) for kname, v in ktimes.items()}
 
     cpu = cpu_baseline(args, cfg, data, queries, labels, windows, gts, table, ops) if not args.no_cpu else None
 

@@ -28,17 +28,19 @@ def main():
     h.h2d(dq, queries)
     h.set_option("gemm_prefilter", 1)
     powers = [int(p) for p in os.environ.get("POWERS", "-10,-8,-6,-4,-2,0").split(",")]
-    items = [0, 444, 592, 888, 1480, 2960]
-    chunks = [32, 16, 8, 4]
+    items = [int(x) for x in os.environ.get("ITEMS", "0,444,592,888,1480,2960").split(",")]
+    chunks = [int(x) for x in os.environ.get("CHUNKS", "32,16,8,4").split(",")]
+    dyns = [int(x) for x in os.environ.get("DYN", "1").split(",")]
     base_ids = {}
     for p in powers:
         w = synth.make_windows(labels, p, nq, seed=1000 + p)
         dw = h.dalloc(w.nbytes)
         h.h2d(dw, w)
         rows = []
-        for it, ch in itertools.product(items, chunks):
+        for it, ch, dyn in itertools.product(items, chunks, dyns):
             h.set_option("gemm_items", it)
             h.set_option("gemm_chunk_mb", ch)
+            h.set_option("gemm_dynamic", dyn)
             best = 1e9
             for _ in range(4):
                 h.timer_start()
@@ -54,11 +56,11 @@ def main():
             h.prefilter_batch(dq, dw, nq, 10, di, dd, device_ptrs=True)
             kt = h.kernel_times(reset=True)
             h.set_option("profile_kernels", 0)
-            rows.append((best, it, ch, kt.get("gemm_sweep", {}).get("ms", 0.0), same))
+            rows.append((best, it, ch, dyn, kt.get("gemm_sweep", {}).get("ms", 0.0), same))
         rows.sort()
-        print(f"== 2^{p}: default (items 0, chunk 32) = {[r for r in rows if r[1] == 0 and r[2] == 32][0][0]:.3f} ms")
-        for best, it, ch, sweep, same in rows[:6]:
-            print(f"   {best:.3f} ms  items={it} chunk_mb={ch} sweep={sweep:.3f} ms rows_identical={same}")
+        print(f"== 2^{p}")
+        for best, it, ch, dyn, sweep, same in rows[:int(os.environ.get("TOP", "8"))]:
+            print(f"   {best:.3f} ms  items={it} chunk_mb={ch} dynamic={dyn} sweep={sweep:.3f} ms rows_identical={same}")
         sys.stdout.flush()
 
 

@@ -342,7 +342,10 @@ __global__ void __launch_bounds__(WSG_PLAN_THREADS) ws_gemm_plan_kernel(WsGemmPl
   if (tid == 0) {
     unsigned long long per = (s_total + A.target_items - 1) / A.target_items;
     if (per < A.min_tiles) per = A.min_tiles;
-    if (per > A.max_tiles) per = A.max_tiles;  // the slices swept concurrently must stay L2-resident
+    // the slices swept concurrently must stay L2-resident; when the whole batch is huge (every group
+    // sweeps most of the axis) twice the chunk measured better: fewer items, same sharing
+    const unsigned long long cap_tiles = s_total >= 300000ull ? 2ull * A.max_tiles : A.max_tiles;
+    if (per > cap_tiles) per = cap_tiles;
     unsigned long long pts = per * WSG_TILE_N;
     const unsigned long long floor_pts = (A.n + WSG_MAX_SPLITS - 1) / WSG_MAX_SPLITS;
     if (pts < floor_pts) pts = floor_pts;
@@ -365,6 +368,7 @@ __global__ void __launch_bounds__(WSG_PLAN_THREADS) ws_gemm_plan_kernel(WsGemmPl
     uint32_t off = 0;
     for (uint32_t c = 0; c < s_nchunks; c++) { s_chunk_off[c] = off; off += s_chunk_cnt[c]; s_chunk_cnt[c] = 0; }
     *A.nitems = off <= A.max_items ? off : 0;
+    *A.sched_ctr = 0;
     if (off > A.max_items) atomicExch(A.overflow, 1u);
   }
   __syncthreads();
@@ -475,8 +479,32 @@ struct WsGemmSmem {
   uint32_t warps_done;                           // epilogue warps that finished an item (monotonic)
   uint32_t pad2_[3];
   uint32_t ring[WSG_RING][WSG_TILE_M];           // fresh scores (float bits), consumed by the owner thread
+  // The CTA's item sequence: entry i & (WSG_SCHED-1) = (i + 1) << 32 | item id (WSG_SENT: no more items),
+  // written by the TMA warp — the role that runs ahead of all others — and polled by the other roles.
+  // No hand-back is needed: the TMA warp is at most WSG_B_STAGES tiles, hence items, ahead of the MMA
+  // warp, which is at most one item ahead of the epilogue and threshold warps.
+  unsigned long long sched[WSG_SCHED];
 };
 #define WSG_SENT 0xFFFFFFFFu
+static_assert(WSG_SCHED >= 2 * (WSG_B_STAGES + WSG_ACC_STAGES + 2), "item ring too short for the pipeline depth");
+
+// item number `seq` of this CTA, as published by the TMA warp (warp-uniform)
+__device__ __forceinline__ uint32_t wsg_take_item(WsGemmSmem* S, uint32_t seq) {
+  volatile unsigned long long* p = &S->sched[seq & (WSG_SCHED - 1)];
+  unsigned long long v = *p;
+  long long t0 = 0;
+  uint32_t polls = 0;
+  while ((uint32_t)(v >> 32) != seq + 1) {
+    __nanosleep(32);
+    if ((++polls & 1023u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
+    v = *p;
+  }
+  return (uint32_t)v;
+}
 
 // Tiles of an item may be swept in any order.  The groups that sweep the same slice of the label
 // axis at the same time share its points through L2, so they must stay CLOSE to each other (a
@@ -549,6 +577,7 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   if (warp == 1) wsg_tmem_alloc(&S->tmem_base, 512);
   if (threadIdx.x == 64) S->warps_done = 0;
+  if (threadIdx.x >= 96 && threadIdx.x < 96 + WSG_SCHED) S->sched[threadIdx.x - 96] = 0ull;
   wsg_tc_fence_before();
   __syncthreads();
   wsg_tc_fence_after();
@@ -561,8 +590,22 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     // ===== TMA producer (whole warp walks the loop, one elected lane issues) =====
     uint32_t stage = 0, phase = 0;
-    for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+    uint32_t it = blockIdx.x;
+    for (uint32_t iseq = 0;; iseq++) {
+      // publish the CTA's next item to the other roles, then fetch its points
+      if (it >= nitems) it = WSG_SENT;
+      if (lane == 0) *(volatile unsigned long long*)&S->sched[iseq & (WSG_SCHED - 1)] = ((unsigned long long)(iseq + 1) << 32) | it;
+      if (it == WSG_SENT) break;
       const WsGemmItem item = A.items[it];
+      // items are ordered chunk-major: drawing them from one counter keeps the CTAs that run at the same
+      // time on neighbouring items (same slice of the label axis) and ends every CTA within one item of
+      // the others, whatever the item sizes
+      uint32_t nx = it + gridDim.x;
+      if (A.dyn) {
+        if (lane == 0) nx = gridDim.x + atomicAdd(A.sched_ctr, 1u);
+        nx = __shfl_sync(0xffffffffu, nx, 0);
+      }
+      it = nx;
       const uint32_t rot = wsg_rotation(item);
       for (uint32_t t = 0; t < item.ntiles; t++) {
         const int p = (int)(item.p0 + wsg_tile(t, rot, item.ntiles) * WSG_TILE_N);
@@ -591,7 +634,9 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t tmem_acc0 = tmem_base + WSG_TILE_N;  // columns [0,128) hold the queries
     const uint32_t nmma = nkb * 4, half = nmma / 2;
     uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
-    for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+    for (uint32_t iseq = 0;; iseq++) {
+      const uint32_t it = wsg_take_item(S, iseq);
+      if (it == WSG_SENT) break;
       const uint32_t ntiles = A.items[it].ntiles;
       wsg_mbar_wait(&S->a_full, a_phase);
       a_phase ^= 1;
@@ -638,7 +683,9 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const float INF = __int_as_float(0x7f800000);
     float* my_norm = S->wnorm[e];
     uint32_t acc = 0, acc_phase = 0, a_phase = 0;
-    for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+    for (uint32_t iseq = 0;; iseq++) {
+      const uint32_t it = wsg_take_item(S, iseq);
+      if (it == WSG_SENT) break;
       const WsGemmItem item = A.items[it];
       const uint32_t row = item.row0 + lrow;
       uint64_t* cand = A.cand + (size_t)it * WSG_CAND_CAP * WSG_TILE_M + lrow;
@@ -736,7 +783,9 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const float INF = __int_as_float(0x7f800000);
     const int k = (int)A.k;
     uint32_t seq = 0;
-    for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+    for (uint32_t iseq = 0;; iseq++) {
+      const uint32_t it = wsg_take_item(S, iseq);
+      if (it == WSG_SENT) break;
       const uint32_t row = A.items[it].row0 + lrow;
       const float slack = A.slack[row];
       // A threshold reached by ANY work item of the query (k-th best of a subset + slack) bounds the

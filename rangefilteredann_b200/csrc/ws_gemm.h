@@ -13,6 +13,7 @@
 #define WSG_ACC_STAGES 3     // 3 x 128 accumulator columns + 128 columns holding the query operand = 512
 #define WSG_KTOP 16          // k <= 16 on this path
 #define WSG_CAND_CAP 512     // survivors kept per (item, query)
+#define WSG_SCHED 64         // per-CTA ring of item ids (see WsGemmSmem::sched)
 #define WSG_RING 16          // per-query ring of fresh scores waiting to be folded into the running top-k
 #define WSG_EPI_WARPS 16     // 4 per TMEM lane quarter: each takes 32 of a tile's 128 columns
 #define WSG_THREADS 704      // warp 0: TMA producer, warp 1: MMA issuer, warps 2-17: epilogue, 18-21: thresholds
@@ -51,6 +52,7 @@ struct WsGemmPlanArgs {
   uint32_t* row_b;        // [rows_pad]
   WsGemmItem* items;
   uint32_t* nitems;       // out
+  uint32_t* sched_ctr;    // out: zeroed here, the sweep kernel's dynamic item counter
   uint32_t max_items;
   uint32_t* group_items;  // [groups][WSG_MAX_SPLITS] item indices of each group
   uint32_t* group_cnt;    // [groups]
@@ -87,6 +89,8 @@ struct WsGemmSeedArgs {
 struct WsGemmArgs {
   const WsGemmItem* items;
   const uint32_t* nitems;
+  uint32_t* sched_ctr;  // items beyond the first gridDim.x are drawn from this counter (dyn != 0)
+  uint32_t dyn;         // 0: item i of CTA b is b + i*gridDim.x (static striping)
   const uint32_t* row_a;
   const uint32_t* row_b;
   const float* slack;

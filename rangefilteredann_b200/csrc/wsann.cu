@@ -137,10 +137,11 @@ struct ws_index {
   int64_t opt_direct = 2;        // one-launch prefilter (K1d): 0 never, 1 always, 2 auto (host-sampled mean window <= scan_chunk)
   int64_t opt_gemm = 2;          // 0 never, 1 whenever eligible, 2 auto (host-sampled mean window >= opt_gemm_min_window)
   int64_t opt_gemm_min_window = 2048;
+  int64_t opt_gemm_dynamic = 1;  // sweep kernel draws work items from a device counter (0: static striping)
   int64_t opt_gemm_items = 0;    // target work items per plan (0: 2 per SM)
   int64_t opt_gemm_min_tiles = 8;
   int64_t opt_gemm_debug = 0;     // timing experiments (ws_gemm.h WsGemmArgs::dbg); results are invalid when set
-  int64_t opt_gemm_chunk_mb = 32; // largest slice of the label axis one work item sweeps
+  int64_t opt_gemm_chunk_mb = 8;  // largest slice of the label axis one work item sweeps
   bool gemm_ready = false;
   WsDevBuf g_norms, g_ctrl, g_perm, g_row_a, g_row_b, g_items, g_group_items, g_group_cnt, g_qpack, g_slack, g_cand,
       g_cand_cnt, g_cand_thr, g_res_keys, g_res_cnt, g_thr0, g_qnorm, g_qa, g_qb;
@@ -757,7 +758,7 @@ static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw
     pa.windows = dw + 2 * q0; pa.labels = idx->d_labels; pa.n = idx->n; pa.nq = sn; pa.rows_pad = rows_pad;
     pa.qa = (uint32_t*)idx->g_qa.p; pa.qb = (uint32_t*)idx->g_qb.p; pa.max_tiles = max_tiles;
     pa.perm = (uint32_t*)idx->g_perm.p; pa.row_a = (uint32_t*)idx->g_row_a.p; pa.row_b = (uint32_t*)idx->g_row_b.p;
-    pa.items = (WsGemmItem*)idx->g_items.p; pa.nitems = gctrl32 + 10; pa.max_items = max_items;
+    pa.items = (WsGemmItem*)idx->g_items.p; pa.nitems = gctrl32 + 10; pa.sched_ctr = gctrl32 + 12; pa.max_items = max_items;
     pa.group_items = (uint32_t*)idx->g_group_items.p; pa.group_cnt = (uint32_t*)idx->g_group_cnt.p;
     pa.target_items = target; pa.min_tiles = (uint32_t)std::max<int64_t>(1, idx->opt_gemm_min_tiles);
     pa.overflow = overflow_flag;
@@ -779,7 +780,7 @@ static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw
       WS_CUDA(wsg_launch_seed(kq, idx->metric, exact_rows, st, sa));
     }
     WsGemmArgs ga;
-    ga.items = pa.items; ga.nitems = pa.nitems; ga.row_a = pa.row_a; ga.row_b = pa.row_b; ga.slack = ka.slack; ga.gthr = sa.thr0;
+    ga.items = pa.items; ga.nitems = pa.nitems; ga.sched_ctr = pa.sched_ctr; ga.dyn = idx->opt_gemm_dynamic ? 1u : 0u; ga.row_a = pa.row_a; ga.row_b = pa.row_b; ga.slack = ka.slack; ga.gthr = sa.thr0;
     ga.norms = (const float*)idx->g_norms.p; ga.cand = (uint64_t*)idx->g_cand.p; ga.cand_cnt = (uint32_t*)idx->g_cand_cnt.p;
     ga.cand_thr = (float*)idx->g_cand_thr.p; ga.nkb = (idx->dpad + WSG_KBLK - 1) / WSG_KBLK; ga.k = k; ga.dbg = (uint32_t)idx->opt_gemm_debug; ga.qpack = ka.qpack; ga.dpad = idx->dpad;
     {
@@ -1557,6 +1558,8 @@ int ws_index_set_option(ws_index* idx, const char* name, int64_t value) {
     idx->opt_gemm = value;
   } else if (s == "gemm_min_window") {
     idx->opt_gemm_min_window = value < 0 ? 0 : value;
+  } else if (s == "gemm_dynamic") {
+    idx->opt_gemm_dynamic = value != 0;
   } else if (s == "gemm_items") {
     if (value < 0 || value > 65536) return ws_fail(WS_ERR_BADARG, "gemm_items must be 0..65536");
     idx->opt_gemm_items = value;

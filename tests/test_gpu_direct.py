@@ -89,7 +89,7 @@ def test_auto_routing_with_host_buffers(engine):
     h.set_option("prefilter_direct", 2)
     h.set_option("gemm_prefilter", 2)
     for power, expect_direct in ((-8, True), (-1, False)):
-        w = synth.make_windows(labels, power, 512, seed=5 + power)
+        w = synth.make_windows(labels, power, 512, seed=50 + power)
         ids, dists = np.empty((512, 10), np.uint32), np.empty((512, 10), np.float32)
         l0 = h.launches()
         h.prefilter_batch(queries, w, 512, 10, ids, dists)
