@@ -15,6 +15,16 @@ def main():
     b = json.load(open(sys.argv[1]))
     r = json.load(open(sys.argv[2]))
     rf = b["roofline"]
+    # DRAM traffic per launch: the committed ncu captures (the bench line carries the copy it was run with)
+    import os
+    try:
+        tr = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "r01_traffic.json")))
+        for c in [rf] + list(rf.get("other_kernels", [])):
+            for key, ent in tr.items():
+                if isinstance(ent, dict) and key.split("_kernel")[0] in c["kernel"]:
+                    c["traffic"] = ent["traffic_bytes"]
+    except Exception:
+        pass
     cpu = b["cpu_baseline"]
     out = []
     out.append("# Round 1 summary — one B200, BASELINE.json config 2 (1 M x 128 fp32 L2, 2-WST, 17 fractions x 10 000 queries, k = 10)\n")
