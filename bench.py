@@ -82,6 +82,29 @@ def load_ref():
     return _load_ext(path)
 
 
+def validate_cache(cdir: str, data, labels):
+    """Graph files are named after (L, R, alpha, min label, max label, count) only
+    (postfilter_vamana.h:126-132), so a cache left by a different dataset with the same label VALUES
+    would be loaded silently.  A fingerprint of the points and labels guards the directory: on a
+    mismatch (or a cache of unknown origin) the files are dropped and rebuilt."""
+    import hashlib
+    os.makedirs(cdir, exist_ok=True)
+    h = hashlib.sha1()
+    h.update(np.ascontiguousarray(labels).tobytes())
+    h.update(np.ascontiguousarray(data[::1009]).tobytes())
+    fp = h.hexdigest()
+    path = os.path.join(cdir, "FINGERPRINT")
+    old = open(path).read().strip() if os.path.exists(path) else None
+    bins = [f for f in os.listdir(cdir) if f.endswith(".bin")]
+    if old != fp and bins:
+        log(f"graph cache {cdir} belongs to another dataset (fingerprint {old} != {fp}): dropping {len(bins)} files")
+        for f in bins:
+            os.remove(os.path.join(cdir, f))
+    if old != fp:
+        with open(path, "w") as f:
+            f.write(fp + "\n")
+
+
 def ensure_graphs(cfg_name: str, cfg: dict, data, labels, rank: int):
     """Both arms search the same reference-format graph files under data_cache/<cfg>/wst/.
     A missing cache is produced once, untimed: by this engine's device-side builder when a
@@ -344,12 +367,17 @@ def run_engine(args, rank, world, local_rank):
     cfg = CONFIGS[args.config]
     os.environ["WSANN_DEVICE"] = str(local_rank)
     t_setup = time.time()
-    data, queries_all, labels = synth.make_dataset(cfg["n"], cfg["d"], cfg["nq"] * world, cfg["seed"])
+    # data and labels are the same on every rank, for every world size and in the reference arm (the graph
+    # cache is keyed by them); each rank answers its own batch of queries (weak scaling)
+    data, queries, labels = synth.make_dataset(cfg["n"], cfg["d"], cfg["nq"], cfg["seed"])
+    if rank > 0:
+        queries = synth.make_rank_queries(cfg["d"], cfg["nq"], cfg["seed"], rank)
     from rangefilteredann_b200 import sharding
-    queries = sharding.weak_batch(queries_all, cfg["nq"], rank)
     windows = {p: synth.make_windows(labels, p, cfg["nq"], seed=1000 + 17 * rank + p) for p in POWERS}
     cdir = cache_dir(args.config)
     os.makedirs(cdir, exist_ok=True)
+    if rank == 0:
+        validate_cache(cdir, data, labels)
     if world > 1:  # rank 0 fills the cache (its constructor builds + saves what is missing), the others load it
         import torch.distributed as dist
         if rank == 0:
@@ -644,6 +672,7 @@ def run_reference(args, rank, world):
         return
     data, queries, labels = synth.make_dataset(cfg["n"], cfg["d"], cfg["nq"], cfg["seed"])
     windows = {p: synth.make_windows(labels, p, cfg["nq"], seed=1000 + p) for p in POWERS}
+    validate_cache(cache_dir(args.config), data, labels)
     cdir = ensure_graphs(args.config, cfg, data, labels, 0)
     tree, pre = ref_indices(ref, cfg, cdir, data, labels)
     ns = args.ref_sample

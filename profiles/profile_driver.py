@@ -34,6 +34,8 @@ def main():
     data, queries, labels = synth.make_dataset(cfg["n"], cfg["d"], a.nq, cfg["seed"])
     cdir = bench.cache_dir(a.config)
     os.makedirs(cdir, exist_ok=True)
+    if a.index == "tree":
+        bench.validate_cache(cdir, data, labels)
     t0 = time.time()
     if a.index == "prefilter":
         tree = eng.PrefilterIndexFloatEuclidian(data, labels)

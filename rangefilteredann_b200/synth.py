@@ -56,6 +56,16 @@ def make_dataset(n: int, d: int, nq: int, seed: int = 0, angular: bool = False,
     return data, queries, labels
 
 
+def make_rank_queries(d: int, nq: int, data_seed: int, rank: int, angular: bool = False) -> np.ndarray:
+    """Queries of rank `rank` (> 0) of a query-sharded run: drawn from the same mixture as
+    make_dataset(..., seed=data_seed) — the centres are the first draw of that stream — but from their
+    own stream, so that data and labels (and with them the graph cache) do not depend on how many
+    ranks there are.  Rank 0 keeps make_dataset's own queries."""
+    centers = np.random.default_rng(data_seed).standard_normal((256, d)).astype(np.float32)
+    rng = np.random.default_rng([int(data_seed), 7919, int(rank)])
+    return make_vectors(nq, d, rng, centers, normalize=angular)
+
+
 def make_windows(labels: np.ndarray, power: int, nq: int, seed: int) -> np.ndarray:
     """Window recipe of filter_generation_utils.py:9-52 for fraction 2**power.
 

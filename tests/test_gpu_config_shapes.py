@@ -5,6 +5,8 @@ beam width across all 17 filter fractions"):
   C3 shape  d = 100 angular (rows padded to 112 floats), super-postfilter tree
   C5 shape  d = 96  L2, 2-WST (fenwick + optimized postfilter)
   C2 shape  d = 128 L2, 2-WST
+  C4 shape  d = 512 angular (CLIP-like), timestamp-style labels with many duplicates
+            (generate_redcaps_data.py:77-80), 2-WST
 
 65 536 points, graphs built on the device and saved in the reference's format; the oracle (pinned to
 the reference bit for bit, tests/test_oracle_golden.py) loads the same files.  Per fraction: ids and
@@ -28,10 +30,11 @@ def recall(ids, gt):
     return float(np.mean(hit / np.maximum(valid.sum(1), 1)))
 
 
-@pytest.mark.parametrize("d,angular,kind", [(100, True, "super"), (96, False, "wst"), (128, False, "wst")])
-def test_all_17_fractions(engine, tmp_path, d, angular, kind):
+@pytest.mark.parametrize("d,angular,kind,label_kind", [(100, True, "super", "unique"), (96, False, "wst", "unique"),
+                                                       (128, False, "wst", "unique"), (512, True, "wst", "timestamp")])
+def test_all_17_fractions(engine, tmp_path, d, angular, kind, label_kind):
     assert engine.device_count() > 0, "no CUDA device: the engine has no CPU fallback"
-    data, queries, labels = synth.make_dataset(N, d, NQ, 31 + d, angular)
+    data, queries, labels = synth.make_dataset(N, d, NQ, 31 + d, angular, label_kind=label_kind)
     cache = str(tmp_path / kind) + "/"
     sfx = "FloatMips" if angular else "FloatEuclidian"
     bp = engine.BuildParams(64, 500, 1.0, cache)
