@@ -54,6 +54,26 @@ def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
 
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    banner on stdout at init, the reference prints one line per loaded graph), so file descriptor 1 is
+    pointed at stderr for the whole run and the result line goes to a private copy of the original."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 # ------------------------------------------------------------------------------------------
 # data, graphs, ground truth
 # ------------------------------------------------------------------------------------------
@@ -592,7 +612,7 @@ def run_engine(args, rank, world, local_rank):
         "counters_per_step": {kname: int(v / args.steps) for kname, v in stats.items()},
         "per_fraction": per_fraction,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -668,7 +688,7 @@ def run_reference(args, rank, world):
     cfg = CONFIGS[args.config]
     ref = load_ref()
     if ref is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built in this snapshot"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref not built in this snapshot"})
         return
     data, queries, labels = synth.make_dataset(cfg["n"], cfg["d"], cfg["nq"], cfg["seed"])
     windows = {p: synth.make_windows(labels, p, cfg["nq"], seed=1000 + p) for p in POWERS}
@@ -725,7 +745,7 @@ def run_reference(args, rank, world):
             "e2e": {"value": round(value, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "per_fraction": {f"2^{p}": {"method": ops[p][0], "beam": ops[p][1], "qps_estimate": round(est_qps[p])}
                              for p in POWERS}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -741,6 +761,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=200)
     ap.add_argument("--ops-file", default=None, help="save / reuse the swept operating points (profiling runs)")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
