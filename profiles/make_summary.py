@@ -67,6 +67,21 @@ def main():
             out.append(f"| {p} | {best} ({e['beam']}) | {e['recall']:.4f} | {fmt_qps(e['qps'])} | {c['method']} | {fmt_qps(c['qps'])} | {e['qps'] / c['qps']:.0f}x |")
         else:
             out.append(f"| {p} | {best} ({e['beam']}) | {e['recall']:.4f} | {fmt_qps(e['qps'])} | - | - | - |")
+    out.append("""
+Other measurements of the final round-1 build:
+
+* 2 GPUs, query-sharded (torchrun, one rank per GPU, index replicated, no data-path collective, weak scaling):
+  27.68 M queries/s (12.29 ms per 340 000-query step; e2e 21.31 M) vs 14.12 M on one GPU — 1.96x (r01_bench_n2.json).
+* label-range sharded mode on 2 GPUs (NCCL all-gather of the per-shard top-k rows + `ws_merge_partial_topk`):
+  200 K x 96, recall@10 1.00 / 0.999 / 0.971 at 2^-8 / 2^-3 / 2^0, identical rows on both ranks (r01_label_shard_n2.log).
+* launch list of one bench step under ncu and its per-kernel shares: r01_launches_c2_final.csv / _summary.txt.
+* ncu `--set full` captures: tensor-core sweep before / after dynamic work items (r01_gemm_prefilter.md), one-launch
+  prefilter kernel, warp beam kernel (r01_beam_warp_kernel_ncu.md), scan kernel; raw metric tables r01_ncu_*_raw.csv.
+* device-side graph build of the 2047 graphs of config 2 (11 M node-rows): about 45 s (reference builder: 2408 s on
+  5 cores of the build container).
+* GPU tests: 88 passed, 1 skipped (`pytest -m gpu`): golden vectors of the reference for every index class, bit-exact ids +
+  distances against the device-order oracle for every method, beam tier and k, all 17 fractions at the C2 / C3 / C4 / C5
+  shapes, tensor-core and one-launch prefilter paths bit-identical to the scan path, 8-bit variants, device builder.""")
     print("\n".join(out))
 
 
