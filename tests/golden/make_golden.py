@@ -9,8 +9,9 @@ container where /root/reference exists.  Committed outputs:
   tiny_pretree_ref_outputs.npz  the same windows through RangeFilterTreeIndexFloatEuclidian (the tree over
                                 PrefilterIndex sub-indices, python_bindings.cpp:119-127); `--only pretree`
                                 regenerates just this file
-  tiny_u8_ref_outputs.npz       the UInt8Euclidian / Int8Mips prefilter and prefilter-bucket tree classes on
-                                quantised data (1200 x 64; `--only u8`)
+  tiny_u8/wst/*.bin, tiny_u8_ref_outputs.npz   the UInt8Euclidian (prefilter, prefilter-bucket tree, Vamana-bucket
+                                tree) and Int8Mips (prefilter, prefilter-bucket tree) classes on quantised data
+                                (1200 x 64; `--only u8`)
 
 Run: python tests/golden/make_golden.py      (after `make -C oracle ref`)
 """
@@ -49,14 +50,20 @@ def pretree(ref):
 
 
 def eight_bit(ref):
-    """UInt8Euclidian and Int8Mips: PrefilterIndex and the tree over prefilter buckets.  The graph classes
-    are not covered: the reference's own 8-bit Vamana build segfaults (observed with oracle/_ref on this
-    data, 1 and 8 threads, right after its first "beam search time" print), so it cannot produce vectors."""
+    """UInt8Euclidian: PrefilterIndex, the tree over prefilter buckets, and the tree over Vamana buckets
+    (3 reference-built graphs under tiny_u8/wst/); Int8Mips: PrefilterIndex and the tree over prefilter
+    buckets."""
     out = {}
+    udir = os.path.join(HERE, "tiny_u8", "wst")
+    os.makedirs(udir, exist_ok=True)
     for sfx, signed in (("UInt8Euclidian", False), ("Int8Mips", True)):
         data, queries, labels = tiny_u8_dataset(signed)
         pre = getattr(ref, "PrefilterIndex" + sfx)(data, labels)
         ptree = getattr(ref, "RangeFilterTreeIndex" + sfx)(data, labels, TINY_U8["cutoff"], 2, ref.BuildParams(64, 500, 1.0, ""))
+        vtree = None
+        if not signed:
+            vtree = getattr(ref, "VamanaRangeFilterTreeIndex" + sfx)(data, labels, TINY_U8["cutoff"], 2,
+                                                                     ref.BuildParams(64, 500, 1.0, udir + "/"))
         for name, windows, qkw in tiny_u8_cases(labels):
             nq = len(windows)
             qp = ref.QueryParams(10, qkw["beam"], 1.35, 10_000_000, 10_000, qkw["mult"], qkw["max_beam"], None, False)
@@ -66,6 +73,9 @@ def eight_bit(ref):
             for method in ("fenwick", "optimized_postfilter", "three_split"):
                 ids, d = ptree.batch_search(queries[:nq], windows, nq, method, qp)
                 out[f"{sfx}/{name}/pretree_{method}/ids"], out[f"{sfx}/{name}/pretree_{method}/dists"] = ids, d
+                if vtree is not None:
+                    ids, d = vtree.batch_search(queries[:nq], windows, nq, method, qp)
+                    out[f"{sfx}/{name}/{method}/ids"], out[f"{sfx}/{name}/{method}/dists"] = ids, d
     np.savez_compressed(os.path.join(HERE, "tiny_u8_ref_outputs.npz"), **out)
     print("wrote", len(out), "8-bit arrays")
 

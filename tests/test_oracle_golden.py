@@ -125,3 +125,23 @@ def test_oracle_matches_reference_8bit(sfx, signed, metric, dist_mode):
             assert np.array_equal(d, rd), f"{sfx}/{name}/{key}"
             for i, j in zip(*np.nonzero(ids != rids)):  # integer distances tie often; the reference's sort is unstable
                 assert (rd[i] == rd[i, j]).sum() > 1 or rd[i, j] == rd[i, -1], f"{sfx}/{name}/{key} row {i} col {j}"
+
+
+@pytest.mark.parametrize("dist_mode", [0, 1])
+def test_oracle_matches_reference_8bit_graph_tree(dist_mode):
+    """VamanaRangeFilterTreeIndexUInt8Euclidian on the reference-built graphs under tests/golden/tiny_u8/wst/:
+    the beam search sees integer-valued distances with many exact ties, broken by id in the reference
+    (beamSearch.h:59-61) and here alike — ids and distances must match bit for bit in both summation orders."""
+    data, queries, labels = tiny_u8_dataset(False)
+    gold = np.load(os.path.join(GOLDEN, "tiny_u8_ref_outputs.npz"))
+    fdata, fq = data.astype(np.float32), queries.astype(np.float32)
+    tree = Oracle("wst", fdata, labels, os.path.join(GOLDEN, "tiny_u8", "wst") + "/", dist_mode=dist_mode,
+                  cutoff=TINY_U8["cutoff"])
+    for name, windows, qkw in tiny_u8_cases(labels):
+        nq = len(windows)
+        for m in ("fenwick", "optimized_postfilter", "three_split"):
+            ids, d = tree.batch(m, fq[:nq], windows, k=10, beam=qkw["beam"], mult=qkw["mult"], max_beam=qkw["max_beam"], pad_id=0)
+            rids, rd = gold[f"UInt8Euclidian/{name}/{m}/ids"], gold[f"UInt8Euclidian/{name}/{m}/dists"]
+            assert np.array_equal(d, rd), f"{name}/{m}"
+            for i, j in zip(*np.nonzero(ids != rids)):
+                assert (rd[i] == rd[i, j]).sum() > 1 or rd[i, j] == rd[i, -1], f"{name}/{m} row {i} col {j}"
