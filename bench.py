@@ -612,6 +612,13 @@ def run_engine(args, rank, world, local_rank):
         "counters_per_step": {kname: int(v / args.steps) for kname, v in stats.items()},
         "per_fraction": per_fraction,
     }
+    if args.results_csv:
+        # the sweep in the reference driver's own results format (experiments/run_our_method.py:538-567),
+        # readable by its experiments/plot.py
+        from rangefilteredann_b200 import results as res
+        rows = [(res.filter_width_name(p), res.method_name(m, v["op"][1], max(1, v["op"][2])), v["recall"], v["ms"] / 1000.0)
+                for p in POWERS for m, v in table[p].items()]
+        res.save_results(rows, args.results_csv, cfg["nq"], f"B200x{world}")
     emit(line)
 
 
@@ -759,6 +766,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=5000)
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     ap.add_argument("--ref-sample", type=int, default=200)
+    ap.add_argument("--results-csv", default=None, help="also append the operating-point sweep to this file in the "
+                    "reference driver's results format (filter_width,method,recall,average_time,qps,threads)")
     ap.add_argument("--ops-file", default=None, help="save / reuse the swept operating points (profiling runs)")
     args = ap.parse_args()
     claim_stdout()

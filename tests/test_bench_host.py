@@ -52,3 +52,36 @@ def test_cache_fingerprint(tmp_path):
 def test_expected_graph_count():
     assert bench.expected_graph_count(1_000_000, 1000) == 2047   # 11 rows
     assert bench.expected_graph_count(3000, 500) == 15
+
+
+def test_results_csv_matches_reference_driver_format(tmp_path):
+    """rangefilteredann_b200/results.py against the reference driver's conventions
+    (experiments/run_our_method.py:174-207,538-567)."""
+    from rangefilteredann_b200 import results as res
+    gt = np.array([[1, 2, 3, 4], [5, 6, 7, 8]])
+    out = np.array([[1, 2, 9, 9, 3], [8, 7, 6, 5, 0]])
+    assert res.compute_recall(gt, out, 4) == (2 / 4 + 4 / 4) / 2
+    assert res.method_name("prefilter_tc") == "prefiltering"
+    assert res.method_name("fenwick", 20) == "vamana-tree_1.000_2_20"
+    assert res.method_name("optimized_postfilter", 80, 2) == "optimized-postfiltering_1.000_2_80_2"
+    assert res.method_name("super", 10, 4) == "super-postfiltering_2_0.5_1.0_10_4"
+    assert res.filter_width_name(-8) == "2pow-8"
+    # should_break: recall ~ 1 stops; no improvement stops unless final multiply is 1; slower than prefiltering stops
+    assert not res.should_break([])
+    assert res.should_break([("2pow-8", "x_1", 0.9995, 1.0)])
+    assert not res.should_break([("2pow-8", "x_10_1", 0.9, 1.0)])
+    assert res.should_break([("w", "x_10_2", 0.9, 1.0), ("w", "x_20_2", 0.9, 1.0)])
+    assert not res.should_break([("w", "x_10_1", 0.9, 1.0), ("w", "x_20_1", 0.9, 1.0)])
+    assert res.should_break([("w", "prefiltering", 1.0 - 1e-3 - 1e-9, 0.5), ("w", "x_10_1", 0.8, 0.1), ("w", "x_20_1", 0.9, 0.7)])
+    path = str(tmp_path / "results" / "sift_results.csv")
+    res.save_results([("2pow-8", "prefiltering", 1.0, 2.0), ("2pow-8", "vamana-tree_1.000_2_10", 0.97, 0.5, 12.5, 2, 100)],
+                     path, 10000, "B200x1")
+    res.save_results([("2pow0", "prefiltering", 1.0, 4.0)], path, 10000, "B200x1")
+    lines = open(path).read().splitlines()
+    assert lines[0] == "filter_width,method,recall,average_time,qps,threads"
+    assert lines[1] == "2pow-8,prefiltering,1.0,0.0002,5000.0,B200x1,,,"
+    assert lines[2] == "2pow-8,vamana-tree_1.000_2_10,0.97,5e-05,20000.0,B200x1,12.5,2,100"
+    assert lines[3].startswith("2pow0,prefiltering,1.0,0.0004,2500.0") and len(lines) == 4
+    import pandas as pd  # the reference's plot.py reads the file with pandas
+    df = pd.read_csv(path, index_col=False, usecols=range(6))
+    assert list(df.columns) == ["filter_width", "method", "recall", "average_time", "qps", "threads"] and len(df) == 3
