@@ -3,8 +3,8 @@
 The reference computes their distances as int32 sums cast to float; this engine keeps one fp32 arena
 and is exact on it while dim * 255^2 < 2^24 (checked at construction).  Covered here:
   * golden vectors from the unmodified reference — PrefilterIndex*, RangeFilterTreeIndex* (prefilter
-    buckets) and VamanaRangeFilterTreeIndexUInt8Euclidian on the reference-built graphs under
-    tests/golden/tiny_u8/wst/: distances bit-identical, ids identical up to exact ties
+    buckets): distances bit-identical, ids identical up to exact ties
+    (VamanaRangeFilterTreeIndexUInt8Euclidian on reference-built graphs: tests/test_gpu_zz_8bit_reference_graphs.py)
   * every graph class of three 8-bit variants on graphs built on the device, saved in the reference's
     .bin format and re-loaded by the oracle: ids and distances bit-identical
 """
@@ -42,21 +42,6 @@ def test_golden_8bit(engine, sfx, signed):
         for m in ("fenwick", "optimized_postfilter", "three_split"):
             ids, d = tree.batch_search(queries[:nq], windows, nq, m, qp)
             _assert_rows(ids, d, gold[f"{sfx}/{name}/pretree_{m}/ids"], gold[f"{sfx}/{name}/pretree_{m}/dists"], f"{sfx}/{name}/pretree_{m}")
-
-
-def test_golden_8bit_graph_tree(engine):
-    """Same graphs as the reference (tests/golden/tiny_u8/wst/), same integer-valued distances, ties
-    broken by id on both sides (beamSearch.h:59-61)."""
-    data, queries, labels = tiny_u8_dataset(False)
-    gold = np.load(os.path.join(GOLDEN, "tiny_u8_ref_outputs.npz"))
-    cache = os.path.join(GOLDEN, "tiny_u8", "wst") + "/"
-    tree = engine.VamanaRangeFilterTreeIndexUInt8Euclidian(data, labels, TINY_U8["cutoff"], 2, engine.BuildParams(64, 500, 1.0, cache))
-    for name, windows, qkw in tiny_u8_cases(labels):
-        nq = len(windows)
-        qp = engine.QueryParams(10, qkw["beam"], 1.35, 10_000_000, 10_000, qkw["mult"], qkw["max_beam"], None, False)
-        for m in ("fenwick", "optimized_postfilter", "three_split"):
-            ids, d = tree.batch_search(queries[:nq], windows, nq, m, qp)
-            _assert_rows(ids, d, gold[f"UInt8Euclidian/{name}/{m}/ids"], gold[f"UInt8Euclidian/{name}/{m}/dists"], f"{name}/{m}")
 
 
 @pytest.mark.parametrize("sfx,signed,metric", [("UInt8Euclidian", False, 0), ("Int8Euclidian", True, 0), ("UInt8Mips", False, 1)])
