@@ -9,6 +9,8 @@ container where /root/reference exists.  Committed outputs:
   tiny_pretree_ref_outputs.npz  the same windows through RangeFilterTreeIndexFloatEuclidian (the tree over
                                 PrefilterIndex sub-indices, python_bindings.cpp:119-127); `--only pretree`
                                 regenerates just this file
+  tiny_pretree_splits_ref_outputs.npz   RangeFilterTreeIndexFloatEuclidian with split factors 3 and 4, cutoff 300
+                                (`--only splits`)
   tiny_u8/wst/*.bin, tiny_u8_ref_outputs.npz   the UInt8Euclidian (prefilter, prefilter-bucket tree, Vamana-bucket
                                 tree) and Int8Mips (prefilter, prefilter-bucket tree) classes on quantised data
                                 (1200 x 64; `--only u8`)
@@ -49,6 +51,31 @@ def pretree(ref):
     print("wrote", len(out), "pretree arrays")
 
 
+def pretree_splits(ref):
+    """Split factors 3 and 4 (the driver only uses 2): the tree over PrefilterIndex buckets needs no
+    graphs, so the whole window -> bucket decomposition of range_filter_tree.h (fenwick cover, optimized
+    descent, three_split) is pinned for B != 2 by result vectors alone.  A case on which the reference
+    throws (its out-of-range .at(), SURVEY.md §A-12, aborts the whole batch) is recorded as such."""
+    data, queries, labels = synth.make_dataset(TINY["n"], TINY["d"], TINY["nq"], TINY["seed"])
+    out = {}
+    for split in (3, 4):
+        tree = ref.RangeFilterTreeIndexFloatEuclidian(data, labels, 300, split, ref.BuildParams(64, 500, 1.0, ""))
+        for name, windows, qkw in tiny_cases(labels):
+            nq = len(windows)
+            qp = ref.QueryParams(10, qkw["beam"], 1.35, 10_000_000, 10_000, qkw["mult"], qkw["max_beam"], qkw.get("ratio"), False)
+            for method in ("fenwick", "optimized_postfilter", "three_split"):
+                key = f"b{split}/{name}/{method}"
+                try:
+                    ids, d = tree.batch_search(queries[:nq], windows, nq, method, qp)
+                except Exception as e:  # noqa: BLE001
+                    print("reference throws on", key, "->", str(e)[:80])
+                    out[key + "/throws"] = np.array([1])
+                    continue
+                out[key + "/ids"], out[key + "/dists"] = ids, d
+    np.savez_compressed(os.path.join(HERE, "tiny_pretree_splits_ref_outputs.npz"), **out)
+    print("wrote", len(out), "split-factor arrays")
+
+
 def eight_bit(ref):
     """UInt8Euclidian: PrefilterIndex, the tree over prefilter buckets, and the tree over Vamana buckets
     (3 reference-built graphs under tiny_u8/wst/); Int8Mips: PrefilterIndex and the tree over prefilter
@@ -87,6 +114,8 @@ def main():
         pretree(ref)
     if only in (None, "u8"):
         eight_bit(ref)
+    if only in (None, "splits"):
+        pretree_splits(ref)
     if only is not None:
         return
     data, queries, labels = synth.make_dataset(TINY["n"], TINY["d"], TINY["nq"], TINY["seed"])

@@ -159,3 +159,25 @@ def test_decompose_c2_geometry(method):
         hi = (0.5 * (s[b - 1] + s[b])) if b < n else s[-1] + 1.0
         edges.append((lo, hi))
     check_against_oracle(idx, orc, method, np.array(edges, np.float32))
+
+
+@pytest.mark.parametrize("split", [3, 4, 7])
+@pytest.mark.parametrize("prefilter_nodes", [False, True])
+def test_decompose_other_split_factors(split, prefilter_nodes):
+    """Split factors other than the driver's 2: the device decomposition (evaluated on the host) against the
+    oracle's trace, tiny tree (cutoff 300) and a 200 000-point tree (cutoff 1000)."""
+    data, queries, labels = synth.make_dataset(TINY["n"], TINY["d"], TINY["nq"], TINY["seed"])
+    kind = "pretree" if prefilter_nodes else "wst"
+    idx = build_host_tree(np.sort(labels), 300, split=split, prefilter_nodes=prefilter_nodes)
+    orc = Oracle(kind, data, labels, None, cutoff=300, split=float(split))
+    for method in ("fenwick", "optimized_postfilter", "three_split"):
+        for name, windows, qkw in tiny_cases(labels):
+            check_against_oracle(idx, orc, method, windows, ratio=qkw.get("ratio"))
+    n = 200_000
+    rng = np.random.default_rng(9)
+    labels = (rng.permutation(n).astype(np.float64) / n).astype(np.float32)
+    idx = build_host_tree(np.sort(labels), 1000, split=split, prefilter_nodes=prefilter_nodes)
+    orc = Oracle(kind, np.zeros((n, 1), np.float32), labels, None, cutoff=1000, split=float(split))
+    for method in ("fenwick", "optimized_postfilter", "three_split"):
+        for power in (-14, -9, -5, -2, 0):
+            check_against_oracle(idx, orc, method, synth.make_windows(labels, power, 24, seed=power + 90), join=True)

@@ -1,0 +1,67 @@
+"""GPU parity for B-WST split factors other than the driver's 2 (range_filter_tree.h:129-189):
+
+  * RangeFilterTreeIndexFloatEuclidian (prefilter buckets), split 3 and 4, against golden vectors of the
+    unmodified reference (tests/golden/tiny_pretree_splits_ref_outputs.npz) and, bit for bit, against the
+    device-order oracle
+  * VamanaRangeFilterTreeIndexFloatEuclidian, split 3, graphs built on the device and re-loaded by the oracle:
+    ids and distances bit-identical for every query method
+
+The CPU halves (oracle vs the same golden vectors; the device decomposition evaluated on the host vs the
+oracle's trace for split 3 / 4 / 7) are tests/test_oracle_golden.py and tests/test_decompose_cpu.py.
+
+(Sorted last on purpose: written after the round's GPU budget was spent; its first GPU run is the round-end one.)"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from golden_cases import TINY, tiny_cases
+from oracle_api import Oracle
+from rangefilteredann_b200 import synth
+from test_gpu_golden import rows_equal_up_to_ties
+
+pytestmark = pytest.mark.gpu
+METHODS = ("fenwick", "optimized_postfilter", "three_split")
+
+
+def _qp(engine, qkw):
+    return engine.QueryParams(10, qkw["beam"], 1.35, 10_000_000, 10_000, qkw["mult"], qkw["max_beam"], qkw.get("ratio"), False)
+
+
+@pytest.mark.parametrize("split", [3, 4])
+def test_prefilter_bucket_tree_other_splits(engine, split):
+    assert engine.device_count() > 0, "no CUDA device: the engine has no CPU fallback"
+    data, queries, labels = synth.make_dataset(TINY["n"], TINY["d"], TINY["nq"], TINY["seed"])
+    gold = np.load(os.path.join(GOLDEN, "tiny_pretree_splits_ref_outputs.npz"))
+    tree = engine.RangeFilterTreeIndexFloatEuclidian(data, labels, 300, split, engine.BuildParams(64, 500, 1.0, ""))
+    orc = Oracle("pretree", data, labels, None, dist_mode=1, cutoff=300, split=float(split))
+    for name, windows, qkw in tiny_cases(labels):
+        nq = len(windows)
+        q = queries[:nq]
+        for m in METHODS:
+            ids, d = tree.batch_search(q, windows, nq, m, _qp(engine, qkw))
+            oids, od = orc.batch(m, q, windows, k=10, beam=qkw["beam"], mult=qkw["mult"], max_beam=qkw["max_beam"],
+                                 ratio=qkw.get("ratio"), pad_id=0)
+            assert np.array_equal(d.view(np.uint32), od.view(np.uint32)) and np.array_equal(ids, oids), f"b{split}/{name}/{m} vs oracle"
+            key = f"b{split}/{name}/{m}"
+            ok = rows_equal_up_to_ties(ids, d, gold[key + "/ids"], gold[key + "/dists"])
+            assert ok.all(), f"{key}: rows {np.nonzero(~ok)[0][:8]} differ from the reference"
+
+
+def test_vamana_bucket_tree_split_3(engine, tmp_path):
+    data, queries, labels = synth.make_dataset(TINY["n"], TINY["d"], TINY["nq"], TINY["seed"])
+    cache = str(tmp_path / "wst3") + "/"
+    # cutoff 400: rows of 1, 3 and 9 buckets (3000 -> 1000 -> 334 / 333 points)
+    tree = engine.VamanaRangeFilterTreeIndexFloatEuclidian(data, labels, 400, 3, engine.BuildParams(64, 500, 1.0, cache))
+    assert len([f for f in os.listdir(cache) if f.endswith(".bin")]) == 1 + 3 + 9
+    orc = Oracle("wst", data, labels, cache, dist_mode=1, cutoff=400, split=3.0)
+    for name, windows, qkw in tiny_cases(labels):
+        nq = len(windows)
+        q = queries[:nq]
+        for m in METHODS:
+            ids, d = tree.batch_search(q, windows, nq, m, _qp(engine, qkw))
+            oids, od = orc.batch(m, q, windows, k=10, beam=qkw["beam"], mult=qkw["mult"], max_beam=qkw["max_beam"],
+                                 ratio=qkw.get("ratio"), pad_id=0)
+            assert np.array_equal(d.view(np.uint32), od.view(np.uint32)), f"{name}/{m}: distances differ"
+            assert np.array_equal(ids, oids), f"{name}/{m}: ids differ"

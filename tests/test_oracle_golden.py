@@ -145,3 +145,26 @@ def test_oracle_matches_reference_8bit_graph_tree(dist_mode):
             assert np.array_equal(d, rd), f"{name}/{m}"
             for i, j in zip(*np.nonzero(ids != rids)):
                 assert (rd[i] == rd[i, j]).sum() > 1 or rd[i, j] == rd[i, -1], f"{name}/{m} row {i} col {j}"
+
+
+@pytest.mark.parametrize("split", [3, 4])
+@pytest.mark.parametrize("method", ["fenwick", "optimized_postfilter", "three_split"])
+def test_oracle_matches_reference_other_split_factors(tiny, split, method):
+    """B-WST with split factor 3 / 4 (range_filter_tree.h:129-189; the driver only uses 2): the tree over
+    PrefilterIndex buckets answers every bucket exactly, so result vectors pin the decomposition itself."""
+    data, queries, labels = synth.make_dataset(TINY["n"], TINY["d"], TINY["nq"], TINY["seed"])
+    gold = np.load(os.path.join(GOLDEN, "tiny_pretree_splits_ref_outputs.npz"))
+    orc = Oracle("pretree", data, labels, None, cutoff=300, split=float(split))
+    checked = 0
+    for name, windows, qkw in tiny["cases"]:
+        key = f"b{split}/{name}/{method}"
+        if key + "/ids" not in gold:
+            continue
+        rids, rd = gold[key + "/ids"], gold[key + "/dists"]
+        ids, d = orc.batch(method, queries[: len(windows)], windows, k=10, beam=qkw["beam"], mult=qkw["mult"],
+                           max_beam=qkw["max_beam"], ratio=qkw.get("ratio"), pad_id=0)
+        assert np.array_equal(d, rd), key
+        for i, j in zip(*np.nonzero(ids != rids)):
+            assert (rd[i] == rd[i, j]).sum() > 1 or rd[i, j] == rd[i, -1], f"{key} row {i} col {j}"
+        checked += 1
+    assert checked > 0
