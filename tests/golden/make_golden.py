@@ -11,6 +11,7 @@ container where /root/reference exists.  Committed outputs:
                                 regenerates just this file
   tiny_pretree_splits_ref_outputs.npz   RangeFilterTreeIndexFloatEuclidian with split factors 3 and 4, cutoff 300
                                 (`--only splits`)
+  tiny_super/*.bin, tiny_super_ref_outputs.npz   super-postfilter tree with split 2.5 / shift 0.4 (`--only super`)
   tiny_u8/wst/*.bin, tiny_u8_ref_outputs.npz   the UInt8Euclidian (prefilter, prefilter-bucket tree, Vamana-bucket
                                 tree) and Int8Mips (prefilter, prefilter-bucket tree) classes on quantised data
                                 (1200 x 64; `--only u8`)
@@ -31,7 +32,8 @@ os.environ["PARLAY_NUM_THREADS"] = "8"
 
 from conftest import _load_ext, find_ext  # noqa: E402
 from rangefilteredann_b200 import synth  # noqa: E402
-from golden_cases import tiny_cases, tiny_mips_cases, tiny_u8_cases, tiny_u8_dataset, TINY, TINY_MIPS, TINY_U8  # noqa: E402
+from golden_cases import (tiny_cases, tiny_mips_cases, tiny_super_cases, tiny_u8_cases, tiny_u8_dataset,  # noqa: E402
+                          TINY, TINY_MIPS, TINY_SUPER, TINY_U8)
 
 
 def pretree(ref):
@@ -76,6 +78,25 @@ def pretree_splits(ref):
     print("wrote", len(out), "split-factor arrays")
 
 
+def super_fractional(ref):
+    """SuperOptimizedPostfilterTreeIndexFloatEuclidian with split 2.5 / shift 0.4 on 800 points: graphs under
+    tiny_super/ and result vectors."""
+    c = TINY_SUPER
+    data, queries, labels = synth.make_dataset(c["n"], c["d"], c["nq"], c["seed"])
+    sdir = os.path.join(HERE, "tiny_super")
+    os.makedirs(sdir, exist_ok=True)
+    sup = ref.SuperOptimizedPostfilterTreeIndexFloatEuclidian(data, labels, c["cutoff"], c["split"], c["shift"],
+                                                              ref.BuildParams(64, 500, 1.0, sdir + "/"))
+    out = {}
+    for name, windows, qkw in tiny_super_cases(labels):
+        nq = len(windows)
+        qp = ref.QueryParams(10, qkw["beam"], 1.35, 10_000_000, 10_000, qkw["mult"], qkw["max_beam"], None, False)
+        ids, d = sup.batch_search(queries[:nq], windows, nq, qp)
+        out[f"{name}/super/ids"], out[f"{name}/super/dists"] = ids, d
+    np.savez_compressed(os.path.join(HERE, "tiny_super_ref_outputs.npz"), **out)
+    print("wrote", len(out), "super arrays,", len(os.listdir(sdir)), "graphs")
+
+
 def eight_bit(ref):
     """UInt8Euclidian: PrefilterIndex, the tree over prefilter buckets, and the tree over Vamana buckets
     (3 reference-built graphs under tiny_u8/wst/); Int8Mips: PrefilterIndex and the tree over prefilter
@@ -116,6 +137,8 @@ def main():
         eight_bit(ref)
     if only in (None, "splits"):
         pretree_splits(ref)
+    if only in (None, "super"):
+        super_fractional(ref)
     if only is not None:
         return
     data, queries, labels = synth.make_dataset(TINY["n"], TINY["d"], TINY["nq"], TINY["seed"])

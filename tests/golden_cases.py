@@ -68,3 +68,16 @@ def tiny_u8_cases(labels):
         w = synth.make_windows(labels, power, TINY_U8["nq"], seed=400 + power)
         cases.append((f"u8_pow{power}", w, dict(beam=20, mult=2, max_beam=10000)))
     return cases
+
+
+# ---- super-postfilter tree with a fractional split factor and a non-default shift
+# (super_optimized_postfilter_tree.h:145-170 evaluates the bucket size in float)
+TINY_SUPER = dict(n=800, d=16, nq=48, seed=13, cutoff=200, split=2.5, shift=0.4)
+
+
+def tiny_super_cases(labels):
+    cases = []
+    for power in (-6, -3, -1, 0):
+        w = synth.make_windows(labels, power, TINY_SUPER["nq"], seed=600 + power)
+        cases.append((f"sup_pow{power}", w, dict(beam=10, mult=2, max_beam=10000)))
+    return cases

@@ -65,3 +65,28 @@ def test_vamana_bucket_tree_split_3(engine, tmp_path):
                                  ratio=qkw.get("ratio"), pad_id=0)
             assert np.array_equal(d.view(np.uint32), od.view(np.uint32)), f"{name}/{m}: distances differ"
             assert np.array_equal(ids, oids), f"{name}/{m}: ids differ"
+
+
+def test_super_tree_fractional_split(engine):
+    """SuperOptimizedPostfilterTreeIndexFloatEuclidian with split 2.5 / shift 0.4 on the 20 reference-built
+    graphs of tests/golden/tiny_super/: the host geometry (bucket sizes evaluated in float, as
+    super_optimized_postfilter_tree.h:145-170 does) must name exactly those files — a mismatch would show up
+    as a device-side build of new files — and the rows must match the oracle bit for bit and the reference's
+    golden vectors."""
+    from golden_cases import TINY_SUPER, tiny_super_cases
+    c = TINY_SUPER
+    data, queries, labels = synth.make_dataset(c["n"], c["d"], c["nq"], c["seed"])
+    cache = os.path.join(GOLDEN, "tiny_super") + "/"
+    before = sorted(os.listdir(cache))
+    sup = engine.SuperOptimizedPostfilterTreeIndexFloatEuclidian(data, labels, c["cutoff"], c["split"], c["shift"],
+                                                                 engine.BuildParams(64, 500, 1.0, cache))
+    assert sorted(os.listdir(cache)) == before and len(before) == 20, "the engine's geometry named other graph files"
+    gold = np.load(os.path.join(GOLDEN, "tiny_super_ref_outputs.npz"))
+    orc = Oracle("super", data, labels, cache, dist_mode=1, cutoff=c["cutoff"], split=c["split"], shift=c["shift"])
+    for name, windows, qkw in tiny_super_cases(labels):
+        nq = len(windows)
+        ids, d = sup.batch_search(queries[:nq], windows, nq, _qp(engine, qkw))
+        oids, od = orc.batch("super", queries[:nq], windows, k=10, beam=qkw["beam"], mult=qkw["mult"], max_beam=qkw["max_beam"], pad_id=0)
+        assert np.array_equal(d.view(np.uint32), od.view(np.uint32)) and np.array_equal(ids, oids), f"{name} vs oracle"
+        ok = rows_equal_up_to_ties(ids, d, gold[f"{name}/super/ids"], gold[f"{name}/super/dists"])
+        assert ok.mean() >= 0.95, f"{name}: only {ok.sum()}/{len(ok)} rows match the reference"

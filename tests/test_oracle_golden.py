@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN
-from golden_cases import TINY, TINY_MIPS, TINY_U8, tiny_cases, tiny_mips_cases, tiny_u8_cases, tiny_u8_dataset
+from golden_cases import (TINY, TINY_MIPS, TINY_SUPER, TINY_U8, tiny_cases, tiny_mips_cases, tiny_super_cases,
+                          tiny_u8_cases, tiny_u8_dataset)
 from oracle_api import Oracle
 from rangefilteredann_b200 import synth
 
@@ -168,3 +169,19 @@ def test_oracle_matches_reference_other_split_factors(tiny, split, method):
             assert (rd[i] == rd[i, j]).sum() > 1 or rd[i, j] == rd[i, -1], f"{key} row {i} col {j}"
         checked += 1
     assert checked > 0
+
+
+def test_oracle_matches_reference_super_fractional_split():
+    """Super-postfilter tree with split 2.5 / shift 0.4: the reference evaluates bucket sizes in float
+    (super_optimized_postfilter_tree.h:145-170); graphs under tests/golden/tiny_super/."""
+    c = TINY_SUPER
+    data, queries, labels = synth.make_dataset(c["n"], c["d"], c["nq"], c["seed"])
+    gold = np.load(os.path.join(GOLDEN, "tiny_super_ref_outputs.npz"))
+    orc = Oracle("super", data, labels, os.path.join(GOLDEN, "tiny_super") + "/", cutoff=c["cutoff"], split=c["split"], shift=c["shift"])
+    for name, windows, qkw in tiny_super_cases(labels):
+        ids, d = orc.batch("super", queries[: len(windows)], windows, k=10, beam=qkw["beam"], mult=qkw["mult"],
+                           max_beam=qkw["max_beam"], pad_id=0)
+        rids, rd = gold[f"{name}/super/ids"], gold[f"{name}/super/dists"]
+        assert np.array_equal(d, rd), name
+        for i, j in zip(*np.nonzero(ids != rids)):
+            assert (rd[i] == rd[i, j]).sum() > 1 or rd[i, j] == rd[i, -1], f"{name} row {i} col {j}"
