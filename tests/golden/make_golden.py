@@ -11,6 +11,7 @@ container where /root/reference exists.  Committed outputs:
                                 regenerates just this file
   tiny_pretree_splits_ref_outputs.npz   RangeFilterTreeIndexFloatEuclidian with split factors 3 and 4, cutoff 300
                                 (`--only splits`)
+  tiny_dup_ref_outputs.npz      PrefilterIndex on duplicate labels, windows ending on label values (`--only dup`)
   tiny_super/*.bin, tiny_super_ref_outputs.npz   super-postfilter tree with split 2.5 / shift 0.4 (`--only super`)
   tiny_u8/wst/*.bin, tiny_u8_ref_outputs.npz   the UInt8Euclidian (prefilter, prefilter-bucket tree, Vamana-bucket
                                 tree) and Int8Mips (prefilter, prefilter-bucket tree) classes on quantised data
@@ -32,7 +33,8 @@ os.environ["PARLAY_NUM_THREADS"] = "8"
 
 from conftest import _load_ext, find_ext  # noqa: E402
 from rangefilteredann_b200 import synth  # noqa: E402
-from golden_cases import (tiny_cases, tiny_mips_cases, tiny_super_cases, tiny_u8_cases, tiny_u8_dataset,  # noqa: E402
+from golden_cases import (tiny_cases, tiny_dup_dataset, tiny_dup_windows, tiny_mips_cases, tiny_super_cases,  # noqa: E402
+                          tiny_u8_cases, tiny_u8_dataset,
                           TINY, TINY_MIPS, TINY_SUPER, TINY_U8)
 
 
@@ -97,6 +99,20 @@ def super_fractional(ref):
     print("wrote", len(out), "super arrays,", len(os.listdir(sdir)), "graphs")
 
 
+def duplicate_labels(ref):
+    """PrefilterIndexFloatEuclidian on data with ~12 points per label value, windows ending on label values."""
+    data, queries, labels = tiny_dup_dataset()
+    w = tiny_dup_windows()
+    pre = ref.PrefilterIndexFloatEuclidian(data, labels)
+    out = {"windows": w}
+    for k in (1, 5):
+        qp = ref.QueryParams(k, 10, 1.35, 10_000_000, 10_000, 1, 10000, None, False)
+        ids, d = pre.batch_search(queries, w, len(w), qp)
+        out[f"k{k}/ids"], out[f"k{k}/dists"] = ids, d
+    np.savez_compressed(os.path.join(HERE, "tiny_dup_ref_outputs.npz"), **out)
+    print("wrote", len(out), "duplicate-label arrays")
+
+
 def eight_bit(ref):
     """UInt8Euclidian: PrefilterIndex, the tree over prefilter buckets, and the tree over Vamana buckets
     (3 reference-built graphs under tiny_u8/wst/); Int8Mips: PrefilterIndex and the tree over prefilter
@@ -139,6 +155,8 @@ def main():
         pretree_splits(ref)
     if only in (None, "super"):
         super_fractional(ref)
+    if only in (None, "dup"):
+        duplicate_labels(ref)
     if only is not None:
         return
     data, queries, labels = synth.make_dataset(TINY["n"], TINY["d"], TINY["nq"], TINY["seed"])

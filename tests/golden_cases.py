@@ -81,3 +81,33 @@ def tiny_super_cases(labels):
         w = synth.make_windows(labels, power, TINY_SUPER["nq"], seed=600 + power)
         cases.append((f"sup_pow{power}", w, dict(beam=10, mult=2, max_beam=10000)))
     return cases
+
+
+# ---- duplicate labels (timestamp-style data) through PrefilterIndex: the set of in-window
+# points does not depend on how equal labels are ordered, so the reference's rows are well defined
+TINY_DUP = dict(n=3000, d=16, nq=64, seed=17, levels=250)
+
+
+def tiny_dup_dataset():
+    data, queries, _ = synth.make_dataset(TINY_DUP["n"], TINY_DUP["d"], TINY_DUP["nq"], TINY_DUP["seed"])
+    rng = np.random.default_rng(TINY_DUP["seed"] + 1)
+    labels = rng.integers(0, TINY_DUP["levels"], size=TINY_DUP["n"]).astype(np.float32)   # ~12 points per value
+    return data, queries, labels
+
+
+def tiny_dup_windows():
+    """Windows whose ends sit exactly ON label values, between them, and outside the range."""
+    rng = np.random.default_rng(TINY_DUP["seed"] + 2)
+    nq, L = TINY_DUP["nq"], TINY_DUP["levels"]
+    lo = rng.integers(0, L - 20, size=nq).astype(np.float64)
+    width = rng.integers(1, 20, size=nq)
+    hi = lo + width
+    kind = np.arange(nq) % 4
+    lo = np.where(kind == 1, lo - 0.5, lo)          # between two values
+    hi = np.where(kind == 2, hi + 0.5, hi)
+    w = np.stack([lo, hi], axis=1)
+    w[0] = [-5.0, 3.0]                              # starts below every label
+    w[1] = [L - 4.0, L + 10.0]                      # ends above every label (r = n-1 rule: last point dropped)
+    w[2] = [0.0, float(L)]                          # everything
+    w[3] = [7.0, 7.0]                               # empty: lo == hi on a label value
+    return w.astype(np.float32)

@@ -6,8 +6,8 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN
-from golden_cases import (TINY, TINY_MIPS, TINY_SUPER, TINY_U8, tiny_cases, tiny_mips_cases, tiny_super_cases,
-                          tiny_u8_cases, tiny_u8_dataset)
+from golden_cases import (TINY, TINY_MIPS, TINY_SUPER, TINY_U8, tiny_cases, tiny_dup_dataset, tiny_dup_windows,
+                          tiny_mips_cases, tiny_super_cases, tiny_u8_cases, tiny_u8_dataset)
 from oracle_api import Oracle
 from rangefilteredann_b200 import synth
 
@@ -185,3 +185,40 @@ def test_oracle_matches_reference_super_fractional_split():
         assert np.array_equal(d, rd), name
         for i, j in zip(*np.nonzero(ids != rids)):
             assert (rd[i] == rd[i, j]).sum() > 1 or rd[i, j] == rd[i, -1], f"{name} row {i} col {j}"
+
+
+def dup_window_sizes(labels, w):
+    """Points PrefilterIndex::query_knn scans: [lb(lo), lb(hi)) with both searches capped at n-1
+    (prefiltering.h:159-184)."""
+    sl = np.sort(labels)
+    n = len(sl)
+    a = np.minimum(np.searchsorted(sl, w[:, 0], side="left"), n - 1)
+    b = np.minimum(np.searchsorted(sl, w[:, 1], side="left"), n - 1)
+    return np.maximum(b - a, 0)
+
+
+@pytest.mark.parametrize("k", [1, 5])
+def test_oracle_matches_reference_duplicate_labels(k):
+    """~12 points per label value, windows that end exactly on label values: lo is inclusive, hi exclusive,
+    and a window reaching past the largest label loses the last sorted point.  Rows whose
+    window holds fewer than k points are undefined in the reference (it reads past its frontier) and skipped."""
+    data, queries, labels = tiny_dup_dataset()
+    w = tiny_dup_windows()
+    gold = np.load(os.path.join(GOLDEN, "tiny_dup_ref_outputs.npz"))
+    assert np.array_equal(gold["windows"], w)
+    sizes = dup_window_sizes(labels, w)
+    defined = sizes >= k
+    # a window reaching past the largest label drops the LAST sorted point; with several points on the largest
+    # value, which one is last depends on the reference's unstable sort (SURVEY.md §A-9): not comparable row by row
+    defined &= w[:, 1] <= labels.max()
+    assert defined.sum() >= len(w) - 3 and not defined[3] and not defined[1]
+    orc = Oracle("prefilter", data, labels, None)
+    ids, d = orc.batch("prefilter", queries, w, k=k, pad_id=0xFFFFFFFF)
+    rids, rd = gold[f"k{k}/ids"], gold[f"k{k}/dists"]
+    assert np.array_equal(d[defined], rd[defined])
+    for i, j in zip(*np.nonzero(ids != rids)):
+        if defined[i]:
+            assert (rd[i] == rd[i, j]).sum() > 1 or rd[i, j] == rd[i, -1], f"row {i} col {j}"
+    # the semantics, stated independently: every returned point has lo <= label < hi
+    lab = labels[ids[defined].astype(np.int64)]
+    assert (lab >= w[defined, 0:1]).all() and (lab < w[defined, 1:2]).all()
