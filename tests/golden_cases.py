@@ -85,7 +85,7 @@ def tiny_super_cases(labels):
 
 # ---- duplicate labels (timestamp-style data) through PrefilterIndex: the set of in-window
 # points does not depend on how equal labels are ordered, so the reference's rows are well defined
-TINY_DUP = dict(n=3000, d=16, nq=64, seed=17, levels=250)
+TINY_DUP = dict(n=3000, d=32, nq=64, seed=17, levels=250)
 
 
 def tiny_dup_dataset():
