@@ -1,15 +1,18 @@
-"""GPU parity for B-WST split factors other than the driver's 2 (range_filter_tree.h:129-189):
+"""More GPU parity against vectors of the unmodified reference, for behaviours the experiment driver does
+not exercise:
 
-  * RangeFilterTreeIndexFloatEuclidian (prefilter buckets), split 3 and 4, against golden vectors of the
-    unmodified reference (tests/golden/tiny_pretree_splits_ref_outputs.npz) and, bit for bit, against the
-    device-order oracle
-  * VamanaRangeFilterTreeIndexFloatEuclidian, split 3, graphs built on the device and re-loaded by the oracle:
-    ids and distances bit-identical for every query method
+  * B-WST split factors 3 and 4 (range_filter_tree.h:129-189): RangeFilterTreeIndexFloatEuclidian (prefilter
+    buckets) against tests/golden/tiny_pretree_splits_ref_outputs.npz and, bit for bit, the device-order oracle;
+    VamanaRangeFilterTreeIndexFloatEuclidian with split 3 on device-built graphs against the oracle
+  * super-postfilter tree with split 2.5 / shift 0.4 (float-evaluated bucket sizes) on the reference-built
+    graphs of tests/golden/tiny_super/
+  * PrefilterIndex on duplicate labels with windows ending on label values (tests/golden/tiny_dup_ref_outputs.npz)
 
-The CPU halves (oracle vs the same golden vectors; the device decomposition evaluated on the host vs the
-oracle's trace for split 3 / 4 / 7) are tests/test_oracle_golden.py and tests/test_decompose_cpu.py.
+The CPU halves (oracle vs the same vectors; the device decomposition evaluated on the host vs the oracle's
+trace for split 3 / 4 / 7) are tests/test_oracle_golden.py and tests/test_decompose_cpu.py.
 
-(Sorted last on purpose: written after the round's GPU budget was spent; its first GPU run is the round-end one.)"""
+(Sorted last on purpose: written after the round's GPU budget was spent; the first GPU run of this file is the
+round-end one.)"""
 import os
 
 import numpy as np
