@@ -215,10 +215,10 @@ int ws_index_set_option(ws_index* idx, const char* name, int64_t value);
 int ws_index_hbm_bytes(const ws_index* idx, uint64_t* out);
 /* With option "profile_kernels" = 1 every kernel launch is bracketed by CUDA events on the
  * index stream.  Returns accumulated milliseconds / launch counts per kernel kind:
- * 0 decompose, 1..3 beam search warp-per-task tiers (beam <= 64 / 128 / 256), 4 beam search
- * CTA-per-task tier (1024), 5 beam search large tier, 6 scan, 7 merge, 8 tensor-core prefilter
- * sweep, 9 its bounds + plan + pack kernels, 10 its re-rank kernel, 11 its seed-threshold kernel.
- * ms_out / launches_out are [12]. */
+ * 0 decompose, 1..5 beam search warp-per-task tiers (beam <= 64 / 128 / 256 / 512 / 1024), 6 beam search
+ * CTA-per-task large tier (<= 12288, global visited bitmap), 7 scan, 8 merge, 9 tensor-core prefilter
+ * sweep, 10 its bounds + plan + pack kernels, 11 its re-rank kernel, 12 its seed-threshold kernel.
+ * ms_out / launches_out are [13]. */
 int ws_index_kernel_times(ws_index* idx, double* ms_out, uint64_t* launches_out, int reset);
 
 /* Host-side evaluation of the window→task decomposition, same code the device runs

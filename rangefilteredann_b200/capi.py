@@ -156,8 +156,8 @@ class Handle:
     def set_option(self, name: str, value: int):
         check(lib().ws_index_set_option(self.raw, name.encode(), int(value)), "ws_index_set_option")
 
-    KERNEL_KINDS = ("decompose", "beam_warp64", "beam_warp128", "beam_warp256", "beam1024", "beam_large", "scan", "merge",
-                    "gemm_sweep", "gemm_plan_pack", "gemm_rerank", "gemm_seed")
+    KERNEL_KINDS = ("decompose", "beam_warp64", "beam_warp128", "beam_warp256", "beam_warp512", "beam_warp1024", "beam_large",
+                    "scan", "merge", "gemm_sweep", "gemm_plan_pack", "gemm_rerank", "gemm_seed")
 
     def kernel_times(self, reset=True) -> dict:
         ms = np.zeros(len(self.KERNEL_KINDS), np.float64)

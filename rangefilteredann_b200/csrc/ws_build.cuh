@@ -16,36 +16,6 @@
 #pragma once
 #include "ws_kernels.cuh"
 
-#define WS_BUILD_VCAP 2048  // candidate capacity of one prune (visited list + current neighbours)
-
-struct WsBuildGraph {
-  uint32_t start;     // first arena rank
-  uint32_t count;     // points in the graph
-  uint32_t row_off;   // first row in the build adjacency
-  uint32_t floor;     // this round inserts perm[floor .. ceil)
-  uint32_t ceil;
-  uint32_t task_off;  // first task index of this graph in the round
-};
-
-struct WsBuildArgs {
-  const float* vecs;
-  uint32_t dim, dpad, R;
-  int32_t* adj;            // [rows][R]
-  int32_t* deg;            // [rows]
-  const int32_t* perm;     // [rows] local ids in insertion order
-  const WsBuildGraph* graphs;
-  uint32_t ngraphs;
-  uint32_t ntasks;
-  uint32_t* head;          // task counter
-  int32_t* new_out;        // [ntasks][R]
-  int32_t* new_cnt;        // [ntasks]
-  uint64_t* pairs;         // reverse edges: (target row << 32) | source local id
-  uint32_t* pair_count;
-  uint32_t L;              // build beam
-  uint32_t beam_cap, hash_mask, cand_cap, expand;
-  double alpha;
-  unsigned long long* stats;
-};
 
 __device__ __forceinline__ uint32_t ws_build_find_graph_by_task(const WsBuildGraph* g, uint32_t n, uint32_t t) {
   uint32_t lo = 0, hi = n;  // last graph with task_off <= t
@@ -216,21 +186,6 @@ __global__ void ws_build_heads_kernel(const uint64_t* pairs, uint32_t n, uint32_
 }
 
 // ---- round kernel 4: add reverse edges; re-prune rows that overflow (index.h:285-297) --------
-struct WsBuildRevArgs {
-  const float* vecs;
-  uint32_t dim, dpad, R;
-  int32_t* adj;
-  int32_t* deg;
-  const WsBuildGraph* graphs;
-  uint32_t ngraphs;
-  const uint64_t* pairs;
-  uint32_t npairs;
-  const uint32_t* heads;
-  uint32_t nheads;
-  uint32_t* head;  // work counter
-  double alpha;
-  unsigned long long* stats;
-};
 
 template <int KQ, int METRIC>
 __global__ void __launch_bounds__(WS_CTA_THREADS) ws_build_reverse_kernel(WsBuildRevArgs A) {
@@ -290,15 +245,6 @@ __global__ void __launch_bounds__(WS_CTA_THREADS) ws_build_reverse_kernel(WsBuil
 }
 
 // ---- final: sort every adjacency list by distance to its node (index.h:131-134) ---------------
-struct WsBuildSortArgs {
-  const float* vecs;
-  uint32_t dim, dpad, R;
-  int32_t* adj;
-  const int32_t* deg;
-  const WsBuildGraph* graphs;
-  uint32_t ngraphs;
-  uint32_t rows;
-};
 
 template <int KQ, int METRIC>
 __global__ void __launch_bounds__(WS_CTA_THREADS) ws_build_sortadj_kernel(WsBuildSortArgs A) {

@@ -4,8 +4,7 @@
 #include <stdint.h>
 
 #define WS_KEY_MAX 0xFFFFFFFFFFFFFFFFull
-#define WS_TEAM 8           // lanes cooperating on one vector (128-bit loads, 128 B per team pass)
-#define WS_CTA_THREADS 128  // every search/scan/merge kernel runs 4 warps = 16 teams
+#include "ws_args.h"        // WS_TEAM, WS_CTA_THREADS, WS_TOPK_BUF
 
 // ---- (distance, id) keys ---------------------------------------------------------------
 // fp32 distance mapped to an order-preserving uint32 in the high word, id in the low word:
@@ -141,7 +140,6 @@ __device__ __forceinline__ int ws_pow2ceil(int x) {
 // ---- streaming top-k in shared memory ----------------------------------------------------
 // buf holds [0,nbest) = best keys so far (sorted) followed by `cnt` appended keys.
 // Compaction sorts everything and keeps k.  Capacity WS_TOPK_BUF keys; k <= WS_TOPK_BUF/2.
-#define WS_TOPK_BUF 2048
 struct WsTopk {
   uint64_t* buf;   // [WS_TOPK_BUF]
   int* cnt;        // appended since last compaction (shared)

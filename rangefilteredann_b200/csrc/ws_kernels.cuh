@@ -1,49 +1,21 @@
 // ws_kernels.cuh — the sm_100a kernels of the window-search hot path.
 //
 //   K3  ws_decompose_kernel   window -> (query,node)/(query,slice) work items   (ws_decompose.h)
-//   K2  ws_beam_kernel        one CTA per graph task: Vamana beam search + label
-//                             predicate + exponential doubling, all on device
+//   K2  ws_beam_warp_kernel   one warp per graph task (beams <= 1024): Vamana beam search + label
+//       ws_beam_cta2_kernel   predicate + exponential doubling, all on device; one CTA per task above
 //   K1  ws_scan_kernel        one CTA per slice task: streaming fp32 distances + top-k
 //   K4  ws_merge_kernel       per query: merge partial top-k lists, decode ids, pad
 //
 // All four are HBM-bound integer/gather work: 128-bit coalesced loads by
 // teams of 8 lanes, state in shared memory, persistent grids sized from the SM count.
 #pragma once
-#include "ws_decompose.h"
+#include "ws_args.h"
 #include "ws_device.cuh"
 
-struct WsNode {
-  const int32_t* adj;  // [count][R] local neighbour ids, -1 padded
-  uint32_t start;      // first arena rank of the node
-  uint32_t count;
-};
-
-enum { WS_MODE_PREFILTER = 10, WS_MODE_POSTFILTER = 11 };
-
-// stats slots (unsigned long long[8]) — order of ws_stats
-enum { WS_ST_SEARCHES = 0, WS_ST_VISITED, WS_ST_DISTCMPS, WS_ST_SCANPTS, WS_ST_GTASKS, WS_ST_STASKS,
-       WS_ST_ESCALATED, WS_ST_BEAMSUM };
 
 // ------------------------------------------------------------------------------------------
 // K3: decomposition
 // ------------------------------------------------------------------------------------------
-struct WsDecompArgs {
-  WsGeom g;
-  WsDecompParams p;
-  int mode;
-  int32_t node;            // WS_MODE_POSTFILTER
-  const float* windows;    // [nq][2]
-  uint32_t nq;
-  uint32_t cap;
-  WsTask* tasks;           // [nq][cap]
-  uint32_t* counts;        // [nq]
-  uint32_t* gq;            // graph-task queue (slot indices)
-  uint32_t* gq_count;
-  uint32_t* sq;            // scan-task queue
-  uint32_t* sq_count;
-  uint32_t* overflow;
-  unsigned long long* stats;
-};
 
 __global__ void __launch_bounds__(128) ws_decompose_kernel(WsDecompArgs A) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -84,43 +56,6 @@ __global__ void __launch_bounds__(128) ws_decompose_kernel(WsDecompArgs A) {
 // ------------------------------------------------------------------------------------------
 // K2: beam search
 // ------------------------------------------------------------------------------------------
-struct WsBeamArgs {
-  const float* vecs;       // [n][dpad]
-  const float* labels;     // [n]
-  const WsNode* nodes;
-  const float* queries;    // [nq][dim]
-  uint32_t dim, dpad, R;
-  WsTask* tasks;
-  uint64_t* res_keys;      // [slots][k]
-  uint32_t* res_cnt;       // [slots]
-  uint32_t k;
-  const uint32_t* q_in;
-  const uint32_t* q_in_count;
-  uint32_t* q_head;
-  uint32_t* q_out;         // next tier (may be null on the last tier)
-  uint32_t* q_out_count;
-  uint32_t beam_cap;       // largest beam this launch can hold in shared memory
-  uint32_t hash_mask;      // smem visited table entries - 1 (GLOBAL_SEEN == false)
-  uint32_t cand_cap;       // power of two >= expand * R
-  uint32_t expand;         // nodes expanded per step (1 = reference order)
-  int32_t skip_query_id;   // emulate `a == p.id()` (beamSearch.h:128)
-  long long max_beam, final_mult, limit, degree_limit;
-  uint32_t* bitmap;        // GLOBAL_SEEN: [gridDim.x][bitmap_words]
-  uint64_t bitmap_words;
-  unsigned long long* stats;
-  uint32_t hash16;         // warp tiers: visited table holds 16-bit tags (ws_seen_warp2_h16)
-  uint32_t min_tasks;      // warp tiers fed by escalation: below this many queued tasks, hand them all to q_out
-  // optional: brute-force scan tasks of the same batch, drained by the same warps once the graph
-  // queue is empty (warp tiers only; null otherwise)
-  const uint32_t* sq_in;
-  const uint32_t* sq_count;
-  uint32_t* sq_head;
-  // final result rows (written directly for WS_TF_SOLO tasks; K4 handles the rest)
-  uint32_t* out_ids;
-  float* out_dists;
-  const uint32_t* decode;
-  uint32_t pad_id;
-};
 
 __device__ __forceinline__ int ws_lb_shift1(const uint64_t* a, int n, uint64_t v) {
   int lo = 0, hi = n;
@@ -348,143 +283,10 @@ __device__ __forceinline__ float* ws_carve_beam_smem(unsigned char* base, uint32
   return qs;
 }
 
-template <int KQ, int METRIC, bool GLOBAL_SEEN>
-__global__ void __launch_bounds__(WS_CTA_THREADS) ws_beam_kernel(WsBeamArgs A) {
-  extern __shared__ __align__(16) unsigned char ws_smem[];
-  WsBeamSmem S;
-  float* qs = ws_carve_beam_smem(ws_smem, A.beam_cap, A.cand_cap, A.dpad, S);
-
-  __shared__ uint32_t s_task;
-  __shared__ int s_m, s_npick, s_have;
-  __shared__ int s_pick[8];
-  __shared__ int s_wc[WS_CTA_THREADS / 32];
-  S.s_m = &s_m; S.s_npick = &s_npick; S.s_pick = s_pick; S.s_wc = s_wc;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tl = lane & (WS_TEAM - 1);
-  const int dpad4 = A.dpad >> 2;
-  const int K = (int)A.k;
-  WsSearchCfg C;
-  C.R = (int)A.R; C.E = (int)A.expand; C.dpad4 = dpad4; C.hash_mask = A.hash_mask;
-  C.limit = A.limit; C.degree_limit = A.degree_limit;
-  C.bitmap = GLOBAL_SEEN ? A.bitmap + (size_t)blockIdx.x * A.bitmap_words : nullptr;
-
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) s_task = atomicAdd(A.q_head, 1u);
-    __syncthreads();
-    const uint32_t t = s_task;
-    if (t >= *A.q_in_count) break;
-    const uint32_t slot = A.q_in[t];
-    const WsTask task = A.tasks[slot];
-    const WsNode node = A.nodes[task.node];
-
-    for (int i = tid; i < (int)A.dpad; i += WS_CTA_THREADS)
-      qs[i] = (i < (int)A.dim) ? A.queries[(size_t)task.query * A.dim + i] : 0.f;
-    __syncthreads();
-    float4 q[KQ];
-    ws_load_query<KQ>(qs, q, tl, dpad4);
-    const float4* vbase = reinterpret_cast<const float4*>(A.vecs + (size_t)node.start * A.dpad);
-    const int skip_id = A.skip_query_id ? (int)task.query : -1;
-
-    long long beam = task.beam;
-    int phase = (task.flags & WS_TF_FINAL) ? 1 : 0;
-    const long long mult = (task.flags & WS_TF_MULT1) ? 1 : A.final_mult;
-    int have = 0;
-    bool escalate = false;
-    if (!(task.flags & WS_TF_RESUMED) && tid == 0) A.res_cnt[slot] = 0;
-
-    // PostfilterVamanaIndex::query (postfilter_vamana.h:141-188)
-    for (;;) {
-      if (phase == 0) {
-        if (!(have < K && beam < A.max_beam)) {
-          long long fin = beam * mult;
-          if (fin > A.max_beam) fin = A.max_beam;
-          if (fin > beam) { beam = fin; phase = 1; } else break;
-        }
-      }
-      if (beam > (long long)A.beam_cap) { escalate = true; break; }
-
-      const int B = (int)beam;
-      uint64_t* cur;
-      unsigned long long nvis, ncmp;
-      const int n = ws_beam_search<KQ, METRIC, GLOBAL_SEEN>(S, C, node, vbase, q, B, skip_id, &cur, &nvis, &ncmp,
-                                                            nullptr, 0);
-
-      // ---- raw_query's label predicate, closed interval (postfilter_vamana.h:234-251)
-      if (tid == 0) s_have = 0;
-      __syncthreads();
-      for (int base = 0; base < n && s_have < K; base += WS_CTA_THREADS) {
-        int i = base + tid;
-        bool in = false;
-        uint64_t key = 0;
-        uint32_t rank = 0;
-        if (i < n) {
-          key = cur[i];
-          rank = node.start + ((uint32_t)(key & 0xFFFFFFFFull) >> 1);
-          float lab = __ldg(A.labels + rank);
-          in = (lab >= task.lo) && (lab <= task.hi);
-        }
-        int tot;
-        int prev = s_have;
-        int r = prev + ws_cta_rank(in, s_wc, lane, warp, &tot);
-        if (in && r < K) {
-          const uint64_t okey = (key & 0xFFFFFFFF00000000ull) | rank;
-          A.res_keys[(size_t)slot * K + r] = okey;
-          if (task.flags & WS_TF_SOLO) ws_write_result(A.out_ids, A.out_dists, A.decode, task.query, K, r, okey);
-        }
-        __syncthreads();
-        if (tid == 0) s_have = prev + tot;
-        __syncthreads();
-      }
-      have = s_have;
-      if (tid == 0) {
-        A.res_cnt[slot] = (uint32_t)min(have, K);
-        atomicAdd(A.stats + WS_ST_SEARCHES, 1ull);
-        atomicAdd(A.stats + WS_ST_VISITED, nvis);
-        atomicAdd(A.stats + WS_ST_DISTCMPS, ncmp);
-        atomicAdd(A.stats + WS_ST_BEAMSUM, (unsigned long long)B);
-      }
-      __syncthreads();
-      if (phase == 1) break;
-      if (have < K) beam *= 2;
-    }
-
-    if (!escalate && (task.flags & WS_TF_SOLO))
-      for (int j = min(have, K) + tid; j < K; j += WS_CTA_THREADS) ws_write_pad(A.out_ids, A.out_dists, A.pad_id, task.query, K, j);
-    if (escalate && tid == 0) {
-      if (A.q_out != nullptr) {
-        A.tasks[slot].beam = (uint32_t)beam;
-        A.tasks[slot].flags = task.flags | WS_TF_RESUMED | (phase ? WS_TF_FINAL : 0u);
-        uint32_t pos = atomicAdd(A.q_out_count, 1u);
-        A.q_out[pos] = slot;
-        atomicAdd(A.stats + WS_ST_ESCALATED, 1ull);
-      }
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 // K1: brute-force scan of a contiguous slice (prefiltering.h:154-204 hot loop 2,
 //     range_filter_tree.h:386-397 edge scans)
 // ------------------------------------------------------------------------------------------
-struct WsScanArgs {
-  const float* vecs;
-  const float* queries;
-  uint32_t dim, dpad;
-  const WsTask* tasks;
-  uint64_t* res_keys;
-  uint32_t* res_cnt;
-  uint32_t k;
-  const uint32_t* q_in;
-  const uint32_t* q_in_count;
-  uint32_t* q_head;
-  unsigned long long* stats;
-  uint32_t* out_ids;
-  float* out_dists;
-  const uint32_t* decode;
-  uint32_t pad_id;
-};
 
 #define WS_SCAN_UNROLL 2
 
@@ -564,18 +366,6 @@ __global__ void __launch_bounds__(WS_CTA_THREADS) ws_scan_kernel(WsScanArgs A) {
 // K4: per-query merge (sort_and_truncate, range_filter_tree.h:542-549), decode
 //     (range_filter_tree.h:84-92) and padding
 // ------------------------------------------------------------------------------------------
-struct WsMergeArgs {
-  const uint32_t* counts;   // tasks per query
-  uint32_t cap;
-  const uint64_t* res_keys;
-  const uint32_t* res_cnt;
-  uint32_t k;
-  const uint32_t* decode;   // may be null
-  uint32_t pad_id;
-  uint32_t nq;
-  uint32_t* ids;            // [nq][k]
-  float* dists;             // [nq][k]
-};
 
 __global__ void __launch_bounds__(WS_CTA_THREADS) ws_merge_kernel(WsMergeArgs A) {
   __shared__ uint64_t buf[WS_TOPK_BUF];
@@ -639,12 +429,14 @@ __global__ void ws_fill_kernel(uint4* p, size_t n16) {
 // sorted in registers.  Many more searches are resident per SM (each needs ~10 KB of shared
 // memory), which is what hides the two dependent HBM latencies of every expansion.
 // ------------------------------------------------------------------------------------------
-#define WS_WARPS_PER_CTA 4
 #ifndef WS_BEAM_ROWS
 #define WS_BEAM_ROWS 2  // candidate rows each team of 8 lanes keeps in flight (x4 teams per warp)
 #endif
 #ifndef WS_BEAM_PREFETCH
 #define WS_BEAM_PREFETCH 1  // 1: L2-prefetch the candidate rows beyond the first register batch; 2: also survivors' adjacency rows
+#endif
+#ifndef WS_BEAM_PREFETCH_NEXT
+#define WS_BEAM_PREFETCH_NEXT 1  // L2-prefetch the adjacency row of the entry that will most likely be expanded next
 #endif
 #ifndef WS_WARP_MINBLOCKS
 #define WS_WARP_MINBLOCKS 7  // resident CTAs per SM the warp kernels are register-budgeted for
@@ -796,10 +588,6 @@ __device__ __forceinline__ void ws_warp_sort32(uint64_t& k0, int lane) {
   }
 }
 
-// shared memory one warp needs (bytes)
-__host__ __device__ inline size_t ws_warp_smem_bytes(uint32_t cap, uint32_t hash_entries, uint32_t hash16) {
-  return (size_t)cap * 8 + 64 * 8 * 2 + 64 * 4 * 2 + (size_t)hash_entries * (hash16 ? 2 : 4);
-}
 
 template <int STEPS>
 __device__ __forceinline__ int ws_lb_fixed_raw(const uint64_t* a, int n, uint64_t v) {
@@ -939,7 +727,13 @@ __device__ __forceinline__ void ws_scan_task(const WsScanOut& A, const WsTask& t
   __syncwarp();
 }
 
-// CS = log2 of the largest beam the instantiation can hold (7 -> 128, 8 -> 256)
+// CS = log2 of the largest beam the instantiation can hold (7 -> 128, 8 -> 256, 9 -> 512, 10 -> 1024).
+// CS <= 8: the merge holds the whole frontier tail in registers; above, the tail is shifted in place from the end,
+// 32 entries at a time.  The 512 / 1024 instantiations serve the doubling tail of optimized postfiltering
+// (postfilter_vamana.h:161-172): those tasks are few and long, i.e. bound by the latency of one expansion, not by
+// bytes (an expansion adds ~7 unseen neighbours at these beams), so a warp per task — thousands of searches in
+// flight, no CTA barrier on the dependent chain — beats a CTA per task (round 1: one 256-thread CTA per SM, 3 % of
+// SM-time active, profiles/r01_ncu_beam_cta2_kernel_raw.csv).
 template <int KQ, int METRIC, bool EXACT, int CS>
 __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, (CS <= 7 ? WS_WARP_MINBLOCKS : 2)) ws_beam_warp_kernel(WsBeamArgs A) {
   extern __shared__ __align__(16) unsigned char ws_smem[];
@@ -1038,6 +832,22 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, (CS <= 7 ? WS_WARP_MINB
         __syncwarp();
         if (lane == 0) fr[pick] = pkey | 1ull;  // visited (beamSearch.h:114-117)
         nvis++;
+        if (WS_BEAM_PREFETCH_NEXT) {
+          // The entry expanded NEXT is, unless this expansion inserts something in front of it, the next
+          // unvisited one: pull its adjacency row (2 x 128 B) into L2 now, so that the first of the two
+          // dependent loads of the next expansion is an L2 hit.  A hint only: a wrong guess costs 256 B.
+          int nxt = -1;
+          for (int b0 = pick + 1; b0 < n && b0 < pick + 65; b0 += 32) {
+            const int i = b0 + lane;
+            const bool unv = i < n && !(fr[i] & 1ull);
+            const unsigned bal = __ballot_sync(0xffffffffu, unv);
+            if (bal) { nxt = b0 + __ffs(bal) - 1; break; }
+          }
+          if (nxt >= 0 && lane < 2) {
+            const uint32_t nid = (uint32_t)(fr[nxt] & 0xFFFFFFFFull) >> 1;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(node.adj + (size_t)nid * R) + 128 * lane));
+          }
+        }
 
         // neighbours not seen before (beamSearch.h:123-131); two per lane
         int nb0 = -1, nb1 = -1;
@@ -1127,24 +937,43 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, (CS <= 7 ? WS_WARP_MINB
         // merge in place, trim to the beam (beamSearch.h:151-172): entries before the first
         // insertion point stay where they are
         const int first_new = cpos[0];
-        constexpr int NE = (1 << CS) / 32;  // frontier entries per lane
-        uint64_t e[NE];
-        int np[NE];
-#pragma unroll
-        for (int r = 0; r < NE; r++) {
-          const int i = lane + 32 * r;
-          const bool mv = i >= first_new && i < n;
-          e[r] = fr[min(i, (int)CAP - 1)];
-          const int c = ws_lb_fixed<6>(sk2, mc2, e[r] >> 1);
-          np[r] = mv ? i + c : B;
-        }
         const int j1 = lane + 32;
         const uint64_t c0 = sk2[lane], c1 = sk2[j1];
         const int q0 = lane < mc2 ? cpos[lane] + lane : B, q1 = j1 < mc2 ? cpos[j1] + j1 : B;
-        __syncwarp();
+        if constexpr (CS <= 8) {
+          constexpr int NE = (1 << CS) / 32;  // frontier entries per lane
+          uint64_t e[NE];
+          int np[NE];
 #pragma unroll
-        for (int r = 0; r < NE; r++)
-          if (np[r] < B) fr[np[r]] = e[r];
+          for (int r = 0; r < NE; r++) {
+            const int i = lane + 32 * r;
+            const bool mv = i >= first_new && i < n;
+            e[r] = fr[min(i, (int)CAP - 1)];
+            const int c = ws_lb_fixed<6>(sk2, mc2, e[r] >> 1);
+            np[r] = mv ? i + c : B;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int r = 0; r < NE; r++)
+            if (np[r] < B) fr[np[r]] = e[r];
+        } else {
+          // Shift the tail [first_new, n) right, from the end, 32 entries at a time.  Entry i moves to
+          // i + (survivors below it) >= i, so a chunk never writes below its own start: the chunks still to come
+          // (lower indices) read untouched entries, and one barrier per chunk (reads before writes) suffices.
+          for (int hi = n; hi > first_new; hi -= 32) {
+            const int i = hi - 1 - lane;
+            const bool valid = i >= first_new;
+            uint64_t key = 0;
+            int c = 0;
+            if (valid) {
+              key = fr[i];
+              c = ws_lb_fixed<6>(sk2, mc2, key >> 1);
+            }
+            __syncwarp();
+            if (valid && i + c < B) fr[i + c] = key;
+          }
+          __syncwarp();
+        }
         if (q0 < B) fr[q0] = c0;
         if (q1 < B) fr[q1] = c1;
         n = min(n + mc2, B);
@@ -1188,12 +1017,16 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, (CS <= 7 ? WS_WARP_MINB
 
     if (!escalate && (task.flags & WS_TF_SOLO))
       for (int j = min(have, K) + lane; j < K; j += 32) ws_write_pad(A.out_ids, A.out_dists, A.pad_id, task.query, K, j);
-    if (escalate && lane == 0 && A.q_out != nullptr) {
-      A.tasks[slot].beam = (uint32_t)beam;
-      A.tasks[slot].flags = task.flags | WS_TF_RESUMED | (phase ? WS_TF_FINAL : 0u);
-      const uint32_t pos = atomicAdd(A.q_out_count, 1u);
-      A.q_out[pos] = slot;
-      atomicAdd(A.stats + WS_ST_ESCALATED, 1ull);
+    if (escalate && lane == 0) {
+      if (A.q_out != nullptr) {
+        A.tasks[slot].beam = (uint32_t)beam;
+        A.tasks[slot].flags = task.flags | WS_TF_RESUMED | (phase ? WS_TF_FINAL : 0u);
+        const uint32_t pos = atomicAdd(A.q_out_count, 1u);
+        A.q_out[pos] = slot;
+        atomicAdd(A.stats + WS_ST_ESCALATED, 1ull);
+      } else if (A.sticky != nullptr) {
+        atomicOr(A.sticky, 2u);  // no tier left: the host reports it (ws_index_sync / end of a host-buffer batch)
+      }
     }
   }
 
@@ -1273,13 +1106,6 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_SCAN_MINBLOCKS) ws_s
 //      slots, no queues, no control words.  Any window size is answered correctly (the warp
 //      streams the whole window); the host only routes batches here when windows are small.
 // ------------------------------------------------------------------------------------------
-struct WsPrefilterDirectArgs {
-  WsScanArgs s;            // tasks / q_in* unused
-  const float* labels;     // [n] sorted
-  uint64_t n;
-  const float* windows;    // [nq][2]
-  uint32_t nq;
-};
 
 template <int KQ, int METRIC, bool EXACT>
 __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_SCAN_MINBLOCKS) ws_prefilter_direct_kernel(WsPrefilterDirectArgs A) {
@@ -1312,13 +1138,6 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, WS_SCAN_MINBLOCKS) ws_p
 //      (SURVEY.md §8e-2): parts x [nq][k] (id, dist) rows -> [nq][k], ascending (dist, id);
 //      pad rows (dist == FLT_MAX) are ignored and re-created at the tail.
 // ------------------------------------------------------------------------------------------
-struct WsMergePartsArgs {
-  const uint32_t* ids;    // [parts][nq][k]
-  const float* dists;     // [parts][nq][k]
-  uint32_t parts, k, nq, pad_id;
-  uint32_t* out_ids;      // [nq][k]
-  float* out_dists;
-};
 
 __global__ void __launch_bounds__(WS_CTA_THREADS) ws_merge_parts_kernel(WsMergePartsArgs A) {
   __shared__ uint64_t buf[WS_TOPK_BUF];
@@ -1375,7 +1194,6 @@ __global__ void __launch_bounds__(WS_CTA_THREADS) ws_merge_parts_kernel(WsMergeP
 // an expansion is in flight at once; the frontier is one array updated in place by all
 // threads.  Same algorithm and same results as the warp kernel / ws_beam_kernel.
 // ------------------------------------------------------------------------------------------
-#define WS_CTA2_THREADS 256
 
 template <int KQ, int METRIC, bool EXACT, bool GLOBAL_SEEN, int CS>
 __global__ void __launch_bounds__(WS_CTA2_THREADS, 1) ws_beam_cta2_kernel(WsBeamArgs A) {
@@ -1472,8 +1290,30 @@ __global__ void __launch_bounds__(WS_CTA2_THREADS, 1) ws_beam_cta2_kernel(WsBeam
             const int* arow = node.adj + (size_t)cur_id * R;
             if (lane < R && (long long)lane < A.degree_limit) nb0 = __ldg(arow + lane);
             if (lane + 32 < R && (long long)(lane + 32) < A.degree_limit) nb1 = __ldg(arow + lane + 32);
+            if (WS_BEAM_PREFETCH_NEXT) {  // adjacency row of the entry most likely expanded next -> L2 (see the warp kernel)
+              int nxt = -1;
+              for (int b0 = pick + 1; b0 < n && b0 < pick + 65; b0 += 32) {
+                const int i = b0 + lane;
+                const bool unv = i < n && !(fr[i] & 1ull);
+                const unsigned bal = __ballot_sync(0xffffffffu, unv);
+                if (bal) { nxt = b0 + __ffs(bal) - 1; break; }
+              }
+              if (nxt >= 0 && lane < 2) {
+                const uint32_t nid = (uint32_t)(fr[nxt] & 0xFFFFFFFFull) >> 1;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(node.adj + (size_t)nid * R) + 128 * lane));
+              }
+            }
             bool keep0 = nb0 >= 0 && nb0 != skip_id;
             bool keep1 = nb1 >= 0 && nb1 != skip_id;
+            if (GLOBAL_SEEN && WS_BEAM_PREFETCH_NEXT) {
+              // The visited bitmap lives in global memory, so the probe below is a second dependent memory round trip
+              // before the gathers can start.  The large tier is latency-bound (a handful of very long tasks), not
+              // bandwidth-bound: pull every listed neighbour's row towards L2 while the bitmap answers.
+              const int lines = ((int)A.dpad * 4 + 127) >> 7;
+              const char* vb = reinterpret_cast<const char*>(vbase_tl - tl);
+              if (keep0) for (int l = 0; l < lines; l++) asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + (size_t)nb0 * A.dpad * 4 + 128 * l));
+              if (keep1) for (int l = 0; l < lines; l++) asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + (size_t)nb1 * A.dpad * 4 + 128 * l));
+            }
             if (!GLOBAL_SEEN) {
               ws_seen_warp2(hash, A.hash_mask, nb0, keep0, nb1, keep1);
             } else {
@@ -1558,7 +1398,15 @@ __global__ void __launch_bounds__(WS_CTA2_THREADS, 1) ws_beam_cta2_kernel(WsBeam
           int c = 0;
           if (valid) {
             key = fr[i];
-            c = ws_lb_fixed<6>(sk2, mc2, key >> 1);
+            if (mc2 <= 4) {  // the common case at large beams: a few broadcast compares instead of a binary search
+              const uint64_t kk = key >> 1;
+              c = (int)((sk2[0] >> 1) < kk);
+              if (mc2 > 1) c += (int)((sk2[1] >> 1) < kk);
+              if (mc2 > 2) c += (int)((sk2[2] >> 1) < kk);
+              if (mc2 > 3) c += (int)((sk2[3] >> 1) < kk);
+            } else {
+              c = ws_lb_fixed<6>(sk2, mc2, key >> 1);
+            }
           }
           __syncthreads();
           if (valid && i + c < B) fr[i + c] = key;
@@ -1613,12 +1461,16 @@ __global__ void __launch_bounds__(WS_CTA2_THREADS, 1) ws_beam_cta2_kernel(WsBeam
 
     if (!escalate && (task.flags & WS_TF_SOLO))
       for (int j = min(have, K) + tid; j < K; j += WS_CTA2_THREADS) ws_write_pad(A.out_ids, A.out_dists, A.pad_id, task.query, K, j);
-    if (escalate && tid == 0 && A.q_out != nullptr) {
-      A.tasks[slot].beam = (uint32_t)beam;
-      A.tasks[slot].flags = task.flags | WS_TF_RESUMED | (phase ? WS_TF_FINAL : 0u);
-      const uint32_t pos = atomicAdd(A.q_out_count, 1u);
-      A.q_out[pos] = slot;
-      atomicAdd(A.stats + WS_ST_ESCALATED, 1ull);
+    if (escalate && tid == 0) {
+      if (A.q_out != nullptr) {
+        A.tasks[slot].beam = (uint32_t)beam;
+        A.tasks[slot].flags = task.flags | WS_TF_RESUMED | (phase ? WS_TF_FINAL : 0u);
+        const uint32_t pos = atomicAdd(A.q_out_count, 1u);
+        A.q_out[pos] = slot;
+        atomicAdd(A.stats + WS_ST_ESCALATED, 1ull);
+      } else if (A.sticky != nullptr) {
+        atomicOr(A.sticky, 2u);
+      }
     }
   }
 }

@@ -8,15 +8,15 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/wsann.h"
-#include "ws_kernels.cuh"
-#include "ws_build.cuh"
+#include "ws_launch.h"
 #include "ws_gemm.h"
 
-#include <cub/device/device_radix_sort.cuh>
+#include <cmath>
 #include <random>
 
 // ------------------------------------------------------------------------------------------
@@ -52,16 +52,17 @@ static int ws_fail(int code, const char* fmt, ...) {
 // ------------------------------------------------------------------------------------------
 // index object
 // ------------------------------------------------------------------------------------------
-// beam tiers: 0,1,2 = warp-per-task kernels (cap 64 / 128 / 256), 3 = CTA-per-task with a
-// shared-memory visited table (cap 1024), 4 = CTA-per-task with a global visited bitmap
-static const uint32_t kBeamTierCaps[4] = {64, 128, 256, 1024};
-#define WS_NUM_WARP_TIERS 3
-#define WS_NUM_TIERS 5
+// beam tiers: 0..4 = warp-per-task kernels (cap 64 / 128 / 256 / 512 / 1024, visited table in shared memory),
+// 5 = CTA-per-task with a global visited bitmap (cap 12288)
+static const uint32_t kBeamTierCaps[5] = {64, 128, 256, 512, 1024};
+static const int kBeamTierCS[5] = {7, 7, 8, 9, 10};
+#define WS_NUM_WARP_TIERS 5
+#define WS_NUM_TIERS 6
 static const uint32_t kBeamCapLarge = 12288;                // global-bitmap tier
 static const uint32_t kMaxK = WS_TOPK_BUF / 2;
 static const size_t kAdjSlabBytes = 256ull << 20;
-#define WS_NUM_KERNEL_KINDS 12  // 0 decompose, 1-3 warp beam tiers 64/128/256, 4 CTA beam tier 1024, 5 beam large, 6 scan, 7 merge,
-                                // 8 tensor-core prefilter sweep, 9 its bounds+plan+pack, 10 its re-rank, 11 its seed thresholds
+#define WS_NUM_KERNEL_KINDS 13  // 0 decompose, 1-5 warp beam tiers 64/128/256/512/1024, 6 beam large, 7 scan, 8 merge,
+                                // 9 tensor-core prefilter sweep, 10 its bounds+plan+pack, 11 its re-rank, 12 its seed thresholds
 
 struct WsDevBuf {
   void* p = nullptr;
@@ -69,6 +70,10 @@ struct WsDevBuf {
 };
 
 struct ws_index {
+  // One batch at a time per index: the *_batch / build / merge entry points mutate per-index scratch
+  // (task slots, queues, control words, one stream), so they serialise here.  The reference's Python
+  // callers hold the GIL for a whole batch_search; this engine's bindings release it.
+  std::recursive_mutex mu;
   int device = -1;  // -1: host-only geometry index (decomposition tests)
   int metric = 0;
   uint64_t n = 0;
@@ -131,6 +136,10 @@ struct ws_index {
   WsDevBuf tasks, res_keys, res_cnt, counts, queues, ctrl, d_queries, d_windows, d_ids, d_dists,
       bitmap, flush;
   unsigned long long* d_stats = nullptr;
+  // sticky error word, never cleared by a batch: bit 0 = task-slot capacity overflow (tasks dropped), bit 1 = a task
+  // outgrew the last beam tier and was dropped.  Read (and cleared) by host-buffer batches before they return and by
+  // ws_index_sync for device-pointer batches, which only enqueue work.
+  uint32_t* d_sticky = nullptr;
   uint64_t launches = 0;
 
   // tensor-core prefilter (ws_gemm.cuh)
@@ -299,6 +308,8 @@ int ws_index_create(int device, int metric, uint64_t n, uint32_t dim, const floa
   }
   WS_CREATE_CUDA(cudaMalloc(&idx->d_stats, 8 * sizeof(unsigned long long)));
   WS_CREATE_CUDA(cudaMemset(idx->d_stats, 0, 8 * sizeof(unsigned long long)));
+  WS_CREATE_CUDA(cudaMalloc(&idx->d_sticky, 4 * sizeof(uint32_t)));
+  WS_CREATE_CUDA(cudaMemset(idx->d_sticky, 0, 4 * sizeof(uint32_t)));
 #undef WS_CREATE_CUDA
   *out = idx;
   return WS_OK;
@@ -313,6 +324,7 @@ void ws_index_destroy(ws_index* idx) {
     cudaFree(idx->d_labels);
     cudaFree(idx->d_decode);
     cudaFree(idx->d_stats);
+    cudaFree(idx->d_sticky);
     for (void* p : idx->adj_slabs) cudaFree(p);
     for (void* p : idx->build_allocs) cudaFree(p);
     for (void* p : idx->geom_dev_allocs) cudaFree(p);
@@ -529,112 +541,6 @@ static uint32_t ws_task_capacity(const ws_index* idx, int mode) {
   return (uint32_t)fen;
 }
 
-// CTA-per-task tiers (beams > 256): ws_beam_cta2_kernel, shared-memory visited table (cap 1024)
-// or global bitmap (cap 12288)
-template <int KQ, int METRIC, bool EXACT, bool GS, int CS>
-static cudaError_t ws_launch_beam_cta_tt(int grid, size_t smem, cudaStream_t s, const WsBeamArgs& a) {
-  cudaError_t e = cudaFuncSetAttribute(ws_beam_cta2_kernel<KQ, METRIC, EXACT, GS, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  ws_beam_cta2_kernel<KQ, METRIC, EXACT, GS, CS><<<grid, WS_CTA2_THREADS, smem, s>>>(a);
-  return cudaGetLastError();
-}
-template <int KQ, int METRIC>
-static cudaError_t ws_launch_beam_t(bool exact, bool global_seen, int grid, size_t smem, cudaStream_t s, const WsBeamArgs& a) {
-  if (global_seen) return exact ? ws_launch_beam_cta_tt<KQ, METRIC, true, true, 14>(grid, smem, s, a) : ws_launch_beam_cta_tt<KQ, METRIC, false, true, 14>(grid, smem, s, a);
-  return exact ? ws_launch_beam_cta_tt<KQ, METRIC, true, false, 10>(grid, smem, s, a) : ws_launch_beam_cta_tt<KQ, METRIC, false, false, 10>(grid, smem, s, a);
-}
-template <int KQ, int METRIC, bool EXACT, bool GS, int CS>
-static cudaError_t ws_beam_cta_occupancy_tt(size_t smem, int* blocks) {
-  cudaError_t e = cudaFuncSetAttribute(ws_beam_cta2_kernel<KQ, METRIC, EXACT, GS, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_beam_cta2_kernel<KQ, METRIC, EXACT, GS, CS>, WS_CTA2_THREADS, smem);
-}
-template <int KQ, int METRIC>
-static cudaError_t ws_beam_occupancy_t(bool exact, bool global_seen, size_t smem, int* blocks) {
-  if (global_seen) return exact ? ws_beam_cta_occupancy_tt<KQ, METRIC, true, true, 14>(smem, blocks) : ws_beam_cta_occupancy_tt<KQ, METRIC, false, true, 14>(smem, blocks);
-  return exact ? ws_beam_cta_occupancy_tt<KQ, METRIC, true, false, 10>(smem, blocks) : ws_beam_cta_occupancy_tt<KQ, METRIC, false, false, 10>(smem, blocks);
-}
-
-template <int KQ, int METRIC, bool EXACT, int CS>
-static cudaError_t ws_launch_beam_warp_tt(int grid, size_t smem, cudaStream_t s, const WsBeamArgs& a) {
-  cudaError_t e = cudaFuncSetAttribute(ws_beam_warp_kernel<KQ, METRIC, EXACT, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  ws_beam_warp_kernel<KQ, METRIC, EXACT, CS><<<grid, WS_WARPS_PER_CTA * 32, smem, s>>>(a);
-  return cudaGetLastError();
-}
-template <int KQ, int METRIC>
-static cudaError_t ws_launch_beam_warp_t(bool exact, bool wide, int grid, size_t smem, cudaStream_t s, const WsBeamArgs& a) {
-  if (exact) return wide ? ws_launch_beam_warp_tt<KQ, METRIC, true, 8>(grid, smem, s, a) : ws_launch_beam_warp_tt<KQ, METRIC, true, 7>(grid, smem, s, a);
-  return wide ? ws_launch_beam_warp_tt<KQ, METRIC, false, 8>(grid, smem, s, a) : ws_launch_beam_warp_tt<KQ, METRIC, false, 7>(grid, smem, s, a);
-}
-template <int KQ, int METRIC, bool EXACT, int CS>
-static cudaError_t ws_beam_warp_occupancy_tt(size_t smem, int* blocks) {
-  cudaError_t e = cudaFuncSetAttribute(ws_beam_warp_kernel<KQ, METRIC, EXACT, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_beam_warp_kernel<KQ, METRIC, EXACT, CS>, WS_WARPS_PER_CTA * 32, smem);
-}
-template <int KQ, int METRIC>
-static cudaError_t ws_beam_warp_occupancy_t(bool exact, bool wide, size_t smem, int* blocks) {
-  if (exact) return wide ? ws_beam_warp_occupancy_tt<KQ, METRIC, true, 8>(smem, blocks) : ws_beam_warp_occupancy_tt<KQ, METRIC, true, 7>(smem, blocks);
-  return wide ? ws_beam_warp_occupancy_tt<KQ, METRIC, false, 8>(smem, blocks) : ws_beam_warp_occupancy_tt<KQ, METRIC, false, 7>(smem, blocks);
-}
-
-template <int KQ, int METRIC>
-static cudaError_t ws_launch_scan_t(int grid, size_t smem, cudaStream_t s, const WsScanArgs& a) {
-  cudaError_t e = cudaFuncSetAttribute(ws_scan_kernel<KQ, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  ws_scan_kernel<KQ, METRIC><<<grid, WS_CTA_THREADS, smem, s>>>(a);
-  return cudaGetLastError();
-}
-
-template <int KQ, int METRIC>
-static cudaError_t ws_launch_scan_warp_t(bool exact, int grid, cudaStream_t s, const WsScanArgs& a) {
-  if (exact) ws_scan_warp_kernel<KQ, METRIC, true><<<grid, WS_WARPS_PER_CTA * 32, 0, s>>>(a);
-  else ws_scan_warp_kernel<KQ, METRIC, false><<<grid, WS_WARPS_PER_CTA * 32, 0, s>>>(a);
-  return cudaGetLastError();
-}
-template <int KQ, int METRIC>
-static cudaError_t ws_launch_prefilter_direct_t(bool exact, int grid, cudaStream_t s, const WsPrefilterDirectArgs& a) {
-  if (exact) ws_prefilter_direct_kernel<KQ, METRIC, true><<<grid, WS_WARPS_PER_CTA * 32, 0, s>>>(a);
-  else ws_prefilter_direct_kernel<KQ, METRIC, false><<<grid, WS_WARPS_PER_CTA * 32, 0, s>>>(a);
-  return cudaGetLastError();
-}
-template <int KQ, int METRIC>
-static cudaError_t ws_prefilter_direct_occupancy_t(bool exact, int* blocks) {
-  if (exact) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_prefilter_direct_kernel<KQ, METRIC, true>, WS_WARPS_PER_CTA * 32, 0);
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_prefilter_direct_kernel<KQ, METRIC, false>, WS_WARPS_PER_CTA * 32, 0);
-}
-template <int KQ, int METRIC>
-static cudaError_t ws_scan_warp_occupancy_t(bool exact, int* blocks) {
-  if (exact) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_scan_warp_kernel<KQ, METRIC, true>, WS_WARPS_PER_CTA * 32, 0);
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_scan_warp_kernel<KQ, METRIC, false>, WS_WARPS_PER_CTA * 32, 0);
-}
-
-#define WS_DISPATCH_KQ(KQV, METRICV, CALL)                                    \
-  do {                                                                        \
-    if ((METRICV) == 0) {                                                     \
-      switch (KQV) {                                                          \
-        case 1: CALL(1, 0); break;                                            \
-        case 2: CALL(2, 0); break;                                            \
-        case 3: CALL(3, 0); break;                                            \
-        case 4: CALL(4, 0); break;                                            \
-        case 8: CALL(8, 0); break;                                            \
-        case 16: CALL(16, 0); break;                                          \
-        default: CALL(32, 0); break;                                          \
-      }                                                                       \
-    } else {                                                                  \
-      switch (KQV) {                                                          \
-        case 1: CALL(1, 1); break;                                            \
-        case 2: CALL(2, 1); break;                                            \
-        case 3: CALL(3, 1); break;                                            \
-        case 4: CALL(4, 1); break;                                            \
-        case 8: CALL(8, 1); break;                                            \
-        case 16: CALL(16, 1); break;                                          \
-        default: CALL(32, 1); break;                                          \
-      }                                                                       \
-    }                                                                         \
-  } while (0)
-
 static int ws_pick_kq(uint32_t dpad) {
   uint32_t need = (dpad / 4 + WS_TEAM - 1) / WS_TEAM;
   const int opts[] = {1, 2, 3, 4, 8, 16, 32};
@@ -770,13 +676,13 @@ static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw
     sa.vecs = idx->d_vecs; sa.queries = ka.queries; sa.dim = idx->dim; sa.dpad = idx->dpad; sa.rows_pad = rows_pad; sa.k = k;
     sa.perm = pa.perm; sa.row_a = pa.row_a; sa.row_b = pa.row_b; sa.slack = ka.slack; sa.qnorm = ka.qnorm; sa.thr0 = (uint32_t*)idx->g_thr0.p;
     {
-      WsKernelScope ks(idx, 9);
+      WsKernelScope ks(idx, 10);
       WS_CUDA(wsg_launch_plan(nsort, st, pa));
       WS_CUDA(wsg_launch_pack(st, ka));
       idx->launches += 2;
     }
     {
-      WsKernelScope ks(idx, 11);
+      WsKernelScope ks(idx, 12);
       WS_CUDA(wsg_launch_seed(kq, idx->metric, exact_rows, st, sa));
     }
     WsGemmArgs ga;
@@ -784,7 +690,7 @@ static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw
     ga.norms = (const float*)idx->g_norms.p; ga.cand = (uint64_t*)idx->g_cand.p; ga.cand_cnt = (uint32_t*)idx->g_cand_cnt.p;
     ga.cand_thr = (float*)idx->g_cand_thr.p; ga.nkb = (idx->dpad + WSG_KBLK - 1) / WSG_KBLK; ga.k = k; ga.dbg = (uint32_t)idx->opt_gemm_debug; ga.qpack = ka.qpack; ga.dpad = idx->dpad;
     {
-      WsKernelScope ks(idx, 8);
+      WsKernelScope ks(idx, 9);
       WS_CUDA(wsg_launch_topk(idx->num_sms, st, idx->g_tm_a, idx->g_tm_b, ga));
     }
     WsGemmRerankArgs ra;
@@ -794,11 +700,19 @@ static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw
     ra.out_ids = dids + q0 * k; ra.out_dists = ddists + q0 * k; ra.decode = decode; ra.pad_id = pad_id;
     ra.res_keys = (uint64_t*)idx->g_res_keys.p; ra.res_cnt = (uint32_t*)idx->g_res_cnt.p; ra.stats = idx->d_stats; ra.gstats = gctrl;
     {
-      WsKernelScope ks(idx, 10);
+      WsKernelScope ks(idx, 11);
       WS_CUDA(wsg_launch_rerank(kq, idx->metric, exact_rows, st, ra));
     }
   }
   return WS_OK;
+}
+
+// turns the device-side sticky error word into a status (and clears it)
+static int ws_report_sticky(ws_index* idx, uint32_t bits) {
+  cudaMemsetAsync(idx->d_sticky, 0, sizeof(uint32_t), idx->stream);
+  cudaStreamSynchronize(idx->stream);
+  if (bits & 1u) return ws_fail(WS_ERR_STATE, "task slot capacity overflowed: tasks were dropped (internal bound too small)");
+  return ws_fail(WS_ERR_STATE, "a graph task outgrew the last beam tier and was dropped (sticky bits 0x%x)", bits);
 }
 
 struct WsBatchPlan {
@@ -813,6 +727,7 @@ struct WsBatchPlan {
 static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* queries, const float* windows,
                         uint64_t nq, uint32_t* ids, float* dists, uint32_t flags) {
   if (!idx) return ws_fail(WS_ERR_BADARG, "null index");
+  std::lock_guard<std::recursive_mutex> lock(idx->mu);
   if (idx->device < 0) return ws_fail(WS_ERR_CUDA, "host-only geometry index: no CUDA device, and this engine has no CPU fallback");
   if (!idx->finalized) return ws_fail(WS_ERR_STATE, "ws_index_finalize has not been called");
   if (nq == 0) return WS_OK;
@@ -893,16 +808,22 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
     if (idx->opt_direct == 1) use_direct = true;
     else use_direct = mean_window >= 0.0 && mean_window <= (double)idx->opt_scan_chunk;
   }
-  // ctrl layout: [0..5] queue counts (beam tiers 0..4, scan = 5), [8..13] queue heads, [16] overflow
+  // ctrl layout: [0..6] queue counts (beam tiers 0..5, scan = 6), [8..14] queue heads
   uint32_t* ctrl = (uint32_t*)idx->ctrl.p;
   if (!use_direct) WS_CUDA(cudaMemsetAsync(ctrl, 0, 64 * sizeof(uint32_t), st));
   uint32_t* queues = (uint32_t*)idx->queues.p;
+  const int kq = ws_pick_kq(idx->dpad);
+  const int metric = idx->metric;
+  const bool exact_rows = (uint32_t)kq * WS_TEAM * 4 == idx->dpad;  // padded row = 8*KQ float4s: no column predicate
+#define WS_LAUNCH(what, expr)                                                                               \
+  do {                                                                                                      \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "%s: %s", what, cudaGetErrorString(_e));             \
+  } while (0)
 
   if (use_gemm) {
-    WS_TRY(ws_run_prefilter_gemm(idx, dq, dw, nq, k, dids, ddists, plan.use_decode ? idx->d_decode : nullptr, plan.pad_id, ctrl + 16));
+    WS_TRY(ws_run_prefilter_gemm(idx, dq, dw, nq, k, dids, ddists, plan.use_decode ? idx->d_decode : nullptr, plan.pad_id, idx->d_sticky));
   } else if (use_direct) {
-    const int kq = ws_pick_kq(idx->dpad);
-    const bool exact_rows = (uint32_t)kq * WS_TEAM * 4 == idx->dpad;
     WsPrefilterDirectArgs pa;
     pa.s.vecs = idx->d_vecs; pa.s.queries = dq; pa.s.dim = idx->dim; pa.s.dpad = idx->dpad;
     pa.s.tasks = nullptr; pa.s.res_keys = (uint64_t*)idx->res_keys.p; pa.s.res_cnt = (uint32_t*)idx->res_cnt.p;
@@ -910,22 +831,16 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
     pa.s.out_ids = dids; pa.s.out_dists = ddists; pa.s.decode = plan.use_decode ? idx->d_decode : nullptr; pa.s.pad_id = plan.pad_id;
     pa.labels = idx->d_labels; pa.n = idx->n; pa.windows = dw; pa.nq = (uint32_t)nq;
     int occ = 0;
-#define WS_OCD(KQ_, M_) { cudaError_t _e = ws_prefilter_direct_occupancy_t<KQ_, M_>(exact_rows, &occ); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(_e)); }
-    WS_DISPATCH_KQ(kq, idx->metric, WS_OCD);
-#undef WS_OCD
+    WS_LAUNCH("occupancy query", wsl_prefilter_direct_occ(kq, metric, exact_rows, &occ));
     if (occ < 1) return ws_fail(WS_ERR_CUDA, "prefilter kernel does not fit on an SM");
     const int grid = (int)std::min<uint64_t>((nq + WS_WARPS_PER_CTA - 1) / WS_WARPS_PER_CTA, (uint64_t)idx->num_sms * occ);
-#define WS_LPD(KQ_, M_) { cudaError_t _e = ws_launch_prefilter_direct_t<KQ_, M_>(exact_rows, grid, st, pa); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "prefilter kernel launch: %s", cudaGetErrorString(_e)); }
     {
-      WsKernelScope ks(idx, 6);
-      WS_DISPATCH_KQ(kq, idx->metric, WS_LPD);
+      WsKernelScope ks(idx, 7);
+      WS_LAUNCH("prefilter kernel launch", wsl_prefilter_direct(kq, metric, exact_rows, grid, st, pa));
     }
-#undef WS_LPD
   } else {
   // ---- tiers: which launch takes fresh graph tasks
-  const int kq = ws_pick_kq(idx->dpad);
   const int lowest_tier = idx->opt_warp_tiers ? 0 : WS_NUM_WARP_TIERS;
-  const bool exact_rows = (uint32_t)kq * WS_TEAM * 4 == idx->dpad;  // padded row = 8*KQ float4s: no column predicate
   int first_tier = WS_NUM_TIERS - 1;
   if (needs_graph) {
     for (int t = lowest_tier; t < WS_NUM_TIERS - 1; t++)
@@ -950,17 +865,16 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
   da.gq_count = ctrl + first_tier;
   da.sq = queues + (size_t)WS_NUM_TIERS * slots;
   da.sq_count = ctrl + WS_NUM_TIERS;
-  da.overflow = ctrl + 16;
+  da.overflow = idx->d_sticky;
   da.stats = idx->d_stats;
   {
     WsKernelScope ks(idx, 0);
-    ws_decompose_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(da);
+    WS_LAUNCH("decomposition kernel launch", wsl_decompose((int)((nq + 127) / 128), st, da));
   }
-  WS_CUDA(cudaGetLastError());
 
   // the first warp-tier launch can also take the batch's scan tasks (same warps, same smem)
   const bool has_scans = plan.mode != WS_MODE_POSTFILTER && plan.mode != WS_METHOD_SUPER_POSTFILTER;
-  const bool fuse_scan = needs_graph && has_scans && idx->opt_fuse_scan && first_tier < WS_NUM_WARP_TIERS &&
+  const bool fuse_scan = needs_graph && has_scans && idx->opt_fuse_scan && first_tier < 2 &&
                          k <= std::min<uint32_t>(128u, kBeamTierCaps[first_tier]);
 
   // ---- K2 beam search, one persistent launch per tier
@@ -972,7 +886,6 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
     int tiers[WS_NUM_TIERS];
     int ntiers = 0;
     for (int t = first_tier; t < WS_NUM_TIERS; t++) {
-      if (t == 2 && t != first_tier && !idx->opt_warp256) continue;  // escalate 128 -> CTA tier directly
       if (ntiers > 0 && (int64_t)kBeamTierCaps[tiers[ntiers - 1]] >= qp.postfiltering_max_beam) break;  // nothing can need more
       tiers[ntiers++] = t;
     }
@@ -980,32 +893,31 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
       const int t = tiers[ti];
       const int t_next = ti + 1 < ntiers ? tiers[ti + 1] : -1;
       const bool large = (t == WS_NUM_TIERS - 1);
-      const bool warp_tier = t < WS_NUM_WARP_TIERS;
-      const bool wide = t == 2;  // the 256-beam instantiation of the warp kernel
+      const bool warp_tier = !large;
       const uint32_t beam_cap = large ? kBeamCapLarge : kBeamTierCaps[t];
-      uint32_t hash_entries = 0;
-      // 16-bit visited tags need id < 2^(log2(entries) + 12)
-      uint32_t hash16 = 0;
+      const int cs = large ? 14 : kBeamTierCS[t];
+      // Visited table of the warp tiers: 2048 entries up to beam 128, then 16 per unit of beam capacity, 8 at 1024
+      // (a beam-B search sees ~7 B distinct nodes; the table only has to avoid most recomputation).
+      // 16-bit tags need id < 2^(log2(entries) + 12); larger nodes use 32-bit entries.
+      uint32_t hash_entries = 0, hash16 = 0;
       if (warp_tier) {
-        hash_entries = (uint32_t)idx->opt_warp_hash * (wide ? 2 : 1);
+        hash_entries = (uint32_t)idx->opt_warp_hash;
+        if (t == 2) hash_entries *= 2;
+        if (t >= 3) hash_entries *= 4;
         uint32_t hb = 0;
         while ((1u << hb) < hash_entries) hb++;
         hash16 = (idx->opt_hash16 && (uint64_t)idx->max_node_count <= (1ull << (hb + 12))) ? 1u : 0u;
-      } else if (!large) {
-        hash_entries = 1024;
-        while (hash_entries < (uint64_t)idx->opt_hash_factor * beam_cap) hash_entries <<= 1;
       }
-      if (!warp_tier && idx->R > 64) return ws_fail(WS_ERR_BADARG, "graphs with max_degree > 64 are not supported by the query kernels");
+      if (idx->R > 64) return ws_fail(WS_ERR_BADARG, "graphs with max_degree > 64 are not supported by the query kernels");
       size_t smem;
       if (warp_tier)
         smem = (size_t)WS_WARPS_PER_CTA * ws_warp_smem_bytes(beam_cap, hash_entries, hash16);
       else
-        smem = (size_t)beam_cap * 8 + 64 * 8 * 2 + 64 * 4 * 2 + (size_t)hash_entries * 4;
+        smem = (size_t)beam_cap * 8 + 64 * 8 * 2 + 64 * 4 * 2;
       if (smem > idx->smem_optin) return ws_fail(WS_ERR_BADARG, "beam tier %d needs %zu B of shared memory (> %zu)", t, smem, idx->smem_optin);
       int occ = 0;
-#define WS_OCC(KQ_, M_) { cudaError_t _e = warp_tier ? ws_beam_warp_occupancy_t<KQ_, M_>(exact_rows, wide, smem, &occ) : ws_beam_occupancy_t<KQ_, M_>(exact_rows, large, smem, &occ); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(_e)); }
-      WS_DISPATCH_KQ(kq, idx->metric, WS_OCC);
-#undef WS_OCC
+      WS_LAUNCH("occupancy query", warp_tier ? wsl_beam_warp_occ(kq, metric, exact_rows, cs, smem, &occ)
+                                            : wsl_beam_cta_occ(kq, metric, exact_rows, smem, &occ));
       if (occ < 1) return ws_fail(WS_ERR_CUDA, "beam kernel does not fit on an SM (smem %zu)", smem);
       int grid = idx->num_sms * occ;
       WsBeamArgs ba;
@@ -1029,19 +941,19 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
         ba.bitmap = (uint32_t*)idx->bitmap.p;
       }
       ba.stats = idx->d_stats;
+      ba.sticky = idx->d_sticky;
       ba.hash16 = hash16;
-      ba.min_tasks = (wide && t != first_tier) ? (uint32_t)idx->opt_warp256_min : 0u;
+      ba.min_tasks = 0u;
       ba.sq_in = nullptr; ba.sq_count = nullptr; ba.sq_head = nullptr;
       if (fuse_scan && t == first_tier) {  // this launch also drains the scan queue
         ba.sq_in = queues + (size_t)WS_NUM_TIERS * slots; ba.sq_count = ctrl + WS_NUM_TIERS; ba.sq_head = ctrl + 8 + WS_NUM_TIERS;
       }
       ba.out_ids = dids; ba.out_dists = ddists; ba.decode = plan.use_decode ? idx->d_decode : nullptr; ba.pad_id = plan.pad_id;
-#define WS_LB(KQ_, M_) { cudaError_t _e = warp_tier ? ws_launch_beam_warp_t<KQ_, M_>(exact_rows, wide, grid, smem, st, ba) : ws_launch_beam_t<KQ_, M_>(exact_rows, large, grid, smem, st, ba); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "beam kernel launch (tier %d): %s", t, cudaGetErrorString(_e)); }
       {
         WsKernelScope ks(idx, 1 + t);
-        WS_DISPATCH_KQ(kq, idx->metric, WS_LB);
+        WS_LAUNCH("beam kernel launch", warp_tier ? wsl_beam_warp(kq, metric, exact_rows, cs, grid, smem, st, ba)
+                                                  : wsl_beam_cta(kq, metric, exact_rows, grid, smem, st, ba));
       }
-#undef WS_LB
     }
   }
 
@@ -1056,26 +968,16 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
     sa.out_ids = dids; sa.out_dists = ddists; sa.decode = plan.use_decode ? idx->d_decode : nullptr; sa.pad_id = plan.pad_id;
     if (k <= 128 && idx->opt_warp_scan) {  // warp-per-task streaming scan
       int occ = 0;
-#define WS_OCS(KQ_, M_) { cudaError_t _e = ws_scan_warp_occupancy_t<KQ_, M_>(exact_rows, &occ); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(_e)); }
-      WS_DISPATCH_KQ(kq, idx->metric, WS_OCS);
-#undef WS_OCS
+      WS_LAUNCH("occupancy query", wsl_scan_warp_occ(kq, metric, exact_rows, &occ));
       if (occ < 1) return ws_fail(WS_ERR_CUDA, "scan kernel does not fit on an SM");
       int grid = idx->num_sms * occ;
-#define WS_LSW(KQ_, M_) { cudaError_t _e = ws_launch_scan_warp_t<KQ_, M_>(exact_rows, grid, st, sa); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "scan kernel launch: %s", cudaGetErrorString(_e)); }
-      {
-        WsKernelScope ks(idx, 6);
-        WS_DISPATCH_KQ(kq, idx->metric, WS_LSW);
-      }
-#undef WS_LSW
+      WsKernelScope ks(idx, 7);
+      WS_LAUNCH("scan kernel launch", wsl_scan_warp(kq, metric, exact_rows, grid, st, sa));
     } else {
       size_t smem = (size_t)WS_TOPK_BUF * 8 + (size_t)idx->dpad * 4;
       int grid = idx->num_sms * 8;
-#define WS_LS(KQ_, M_) { cudaError_t _e = ws_launch_scan_t<KQ_, M_>(grid, smem, st, sa); if (_e != cudaSuccess) return ws_fail(WS_ERR_CUDA, "scan kernel launch: %s", cudaGetErrorString(_e)); }
-      {
-        WsKernelScope ks(idx, 6);
-        WS_DISPATCH_KQ(kq, idx->metric, WS_LS);
-      }
-#undef WS_LS
+      WsKernelScope ks(idx, 7);
+      WS_LAUNCH("scan kernel launch", wsl_scan(kq, metric, grid, smem, st, sa));
     }
   }
 
@@ -1087,21 +989,18 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
     ma.k = k; ma.decode = plan.use_decode ? idx->d_decode : nullptr; ma.pad_id = plan.pad_id;
     ma.nq = (uint32_t)nq; ma.ids = dids; ma.dists = ddists;
     int grid = (int)std::min<uint64_t>(nq, (uint64_t)idx->num_sms * 16);
-    {
-      WsKernelScope ks(idx, 7);
-      ws_merge_kernel<<<grid, WS_CTA_THREADS, 0, st>>>(ma);
-    }
-    WS_CUDA(cudaGetLastError());
+    WsKernelScope ks(idx, 8);
+    WS_LAUNCH("merge kernel launch", wsl_merge(grid, st, ma));
   }
   }  // !use_gemm
 
   if (!dev_ptrs) {
-    uint32_t h_overflow = 0;
+    uint32_t h_sticky = 0;
     WS_CUDA(cudaMemcpyAsync(ids, dids, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     WS_CUDA(cudaMemcpyAsync(dists, ddists, nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (!use_direct) WS_CUDA(cudaMemcpyAsync(&h_overflow, ctrl + 16, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    WS_CUDA(cudaMemcpyAsync(&h_sticky, idx->d_sticky, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     WS_CUDA(cudaStreamSynchronize(st));
-    if (h_overflow) return ws_fail(WS_ERR_STATE, "task slot capacity %u overflowed (internal bound too small)", cap);
+    if (h_sticky) return ws_report_sticky(idx, h_sticky);
   }
   return WS_OK;
 }
@@ -1158,17 +1057,16 @@ int ws_index_device(const ws_index* idx, int* device) {
 }
 #define WS_NEED_DEVICE(idx)                                                     \
   if (!(idx)) return ws_fail(WS_ERR_BADARG, "null index");                      \
+  std::lock_guard<std::recursive_mutex> lock_((idx)->mu);                        \
   if ((idx)->device < 0) return ws_fail(WS_ERR_CUDA, "host-only geometry index"); \
   WS_CUDA(cudaSetDevice((idx)->device));
 
 int ws_index_sync(ws_index* idx) {
   WS_NEED_DEVICE(idx);
   WS_CUDA(cudaStreamSynchronize(idx->stream));
-  uint32_t h_overflow = 0;
-  if (idx->ctrl.p) {
-    WS_CUDA(cudaMemcpy(&h_overflow, (uint32_t*)idx->ctrl.p + 16, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    if (h_overflow) return ws_fail(WS_ERR_STATE, "task slot capacity overflowed in the last batch");
-  }
+  uint32_t h_sticky = 0;
+  WS_CUDA(cudaMemcpy(&h_sticky, idx->d_sticky, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (h_sticky) return ws_report_sticky(idx, h_sticky);
   return WS_OK;
 }
 int ws_device_alloc(ws_index* idx, size_t bytes, void** dptr) {
@@ -1221,8 +1119,7 @@ int ws_flush_l2(ws_index* idx) {
   WS_NEED_DEVICE(idx);
   const size_t bytes = 256ull << 20;  // 2x the 126 MB L2
   WS_TRY(ws_ensure(idx, idx->flush, bytes));
-  ws_fill_kernel<<<idx->num_sms * 8, 256, 0, idx->stream>>>((uint4*)idx->flush.p, bytes / 16);
-  WS_CUDA(cudaGetLastError());
+  WS_CUDA(wsl_fill(idx->num_sms * 8, idx->stream, (uint4*)idx->flush.p, bytes / 16));
   return WS_OK;
 }
 
@@ -1252,30 +1149,6 @@ static void ws_build_schedule(size_t n, std::vector<std::pair<uint32_t, uint32_t
     if (ceiling > floor) out.push_back({(uint32_t)floor, (uint32_t)ceiling});
     inc++;
   }
-}
-
-template <int KQ, int METRIC>
-static cudaError_t ws_launch_build_insert_t(int grid, size_t smem, cudaStream_t s, const WsBuildArgs& a) {
-  cudaError_t e = cudaFuncSetAttribute(ws_build_insert_kernel<KQ, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  ws_build_insert_kernel<KQ, METRIC><<<grid, WS_CTA_THREADS, smem, s>>>(a);
-  return cudaGetLastError();
-}
-template <int KQ, int METRIC>
-static cudaError_t ws_build_insert_occ_t(size_t smem, int* blocks) {
-  cudaError_t e = cudaFuncSetAttribute(ws_build_insert_kernel<KQ, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_build_insert_kernel<KQ, METRIC>, WS_CTA_THREADS, smem);
-}
-template <int KQ, int METRIC>
-static cudaError_t ws_launch_build_reverse_t(int grid, cudaStream_t s, const WsBuildRevArgs& a) {
-  ws_build_reverse_kernel<KQ, METRIC><<<grid, WS_CTA_THREADS, 0, s>>>(a);
-  return cudaGetLastError();
-}
-template <int KQ, int METRIC>
-static cudaError_t ws_launch_build_sort_t(int grid, cudaStream_t s, const WsBuildSortArgs& a) {
-  ws_build_sortadj_kernel<KQ, METRIC><<<grid, WS_CTA_THREADS, 0, s>>>(a);
-  return cudaGetLastError();
 }
 
 extern "C" {
@@ -1330,7 +1203,7 @@ int ws_build_graphs(ws_index* idx, uint32_t ngraphs, const uint64_t* starts, con
   size_t temp_bytes = 0;
   unsigned long long* d_bstats = nullptr;
   const size_t max_pairs = max_tasks * R;
-  cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, d_pairs, d_pairs2, (int)max_pairs, 0, 64, st);
+  wsl_sort_keys(nullptr, &temp_bytes, d_pairs, d_pairs2, (int)max_pairs, st);
   auto cleanup = [&]() {
     cudaFree(d_perm); cudaFree(d_new_out); cudaFree(d_new_cnt); cudaFree(d_graphs); cudaFree(d_pairs);
     cudaFree(d_pairs2); cudaFree(d_heads); cudaFree(d_ctrl); cudaFree(d_temp); cudaFree(d_bstats);
@@ -1358,7 +1231,7 @@ int ws_build_graphs(ws_index* idx, uint32_t ngraphs, const uint64_t* starts, con
   WS_B(cudaMalloc(&d_bstats, 8 * sizeof(unsigned long long)));
   WS_B(cudaMemsetAsync(d_bstats, 0, 8 * sizeof(unsigned long long), st));
   WS_B(cudaMemcpyAsync(d_perm, perm.data(), rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  ws_fill_i32_kernel<<<idx->num_sms * 8, 256, 0, st>>>(d_adj, rows * R, -1);
+  WS_B(wsl_fill_i32(idx->num_sms * 8, st, d_adj, rows * R, -1));
   WS_B(cudaMemsetAsync(d_deg, 0, rows * sizeof(int32_t), st));
 
   const int kq = ws_pick_kq(idx->dpad);
@@ -1371,9 +1244,7 @@ int ws_build_graphs(ws_index* idx, uint32_t ngraphs, const uint64_t* starts, con
   const size_t smem = (size_t)2 * beam_cap * 8 + (size_t)cand_cap * 24 + (size_t)idx->dpad * 4 + (size_t)hash_entries * 4 +
                       (size_t)WS_BUILD_VCAP * 8;
   int occ = 0;
-#define WS_OCCB(KQ_, M_) { WS_B((ws_build_insert_occ_t<KQ_, M_>(smem, &occ))); }
-  WS_DISPATCH_KQ(kq, idx->metric, WS_OCCB);
-#undef WS_OCCB
+  WS_B(wsl_build_insert_occ(kq, idx->metric, smem, &occ));
   if (occ < 1) { cleanup(); cudaFree(d_adj); cudaFree(d_deg); return ws_fail(WS_ERR_CUDA, "build kernel does not fit (smem %zu)", smem); }
 
   for (size_t r = 0; r < max_rounds; r++) {
@@ -1394,18 +1265,14 @@ int ws_build_graphs(ws_index* idx, uint32_t ngraphs, const uint64_t* starts, con
     a.L = beam_l; a.beam_cap = beam_cap; a.hash_mask = hash_entries - 1; a.cand_cap = cand_cap; a.expand = E;
     a.alpha = alpha; a.stats = d_bstats;
     const int grid = (int)std::min<uint64_t>(ntasks, (uint64_t)idx->num_sms * occ);
-#define WS_LBI(KQ_, M_) { WS_B((ws_launch_build_insert_t<KQ_, M_>(grid, smem, st, a))); }
-    WS_DISPATCH_KQ(kq, idx->metric, WS_LBI);
-#undef WS_LBI
-    ws_build_apply_kernel<<<(ntasks + 7) / 8, 256, 0, st>>>(a);
-    WS_B(cudaGetLastError());
+    WS_B(wsl_build_insert(kq, idx->metric, grid, smem, st, a));
+    WS_B(wsl_build_apply((int)((ntasks + 7) / 8), st, a));
     uint32_t npairs = 0;
     WS_B(cudaMemcpyAsync(&npairs, d_ctrl + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     WS_B(cudaStreamSynchronize(st));
     if (npairs == 0) continue;
-    WS_B(cub::DeviceRadixSort::SortKeys(d_temp, temp_bytes, d_pairs, d_pairs2, (int)npairs, 0, 64, st));
-    ws_build_heads_kernel<<<(npairs + 255) / 256, 256, 0, st>>>(d_pairs2, npairs, d_heads, d_ctrl + 2);
-    WS_B(cudaGetLastError());
+    WS_B(wsl_sort_keys(d_temp, &temp_bytes, d_pairs, d_pairs2, (int)npairs, st));
+    WS_B(wsl_build_heads((int)((npairs + 255) / 256), st, d_pairs2, npairs, d_heads, d_ctrl + 2));
     uint32_t nheads = 0;
     WS_B(cudaMemcpyAsync(&nheads, d_ctrl + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     WS_B(cudaStreamSynchronize(st));
@@ -1414,18 +1281,14 @@ int ws_build_graphs(ws_index* idx, uint32_t ngraphs, const uint64_t* starts, con
     ra.graphs = d_graphs; ra.ngraphs = ngraphs; ra.pairs = d_pairs2; ra.npairs = npairs; ra.heads = d_heads;
     ra.nheads = nheads; ra.head = d_ctrl + 3; ra.alpha = alpha; ra.stats = d_bstats;
     const int rgrid = (int)std::min<uint64_t>(nheads, (uint64_t)idx->num_sms * 8);
-#define WS_LBR(KQ_, M_) { WS_B((ws_launch_build_reverse_t<KQ_, M_>(rgrid, st, ra))); }
-    WS_DISPATCH_KQ(kq, idx->metric, WS_LBR);
-#undef WS_LBR
+    WS_B(wsl_build_reverse(kq, idx->metric, rgrid, st, ra));
   }
   {
     WsBuildSortArgs sa;
     sa.vecs = idx->d_vecs; sa.dim = idx->dim; sa.dpad = idx->dpad; sa.R = R; sa.adj = d_adj; sa.deg = d_deg;
     sa.graphs = d_graphs; sa.ngraphs = ngraphs; sa.rows = (uint32_t)rows;
     const int sgrid = (int)std::min<uint64_t>(rows, (uint64_t)idx->num_sms * 16);
-#define WS_LBS(KQ_, M_) { WS_B((ws_launch_build_sort_t<KQ_, M_>(sgrid, st, sa))); }
-    WS_DISPATCH_KQ(kq, idx->metric, WS_LBS);
-#undef WS_LBS
+    WS_B(wsl_build_sort(kq, idx->metric, sgrid, st, sa));
   }
   unsigned long long hs[8];
   WS_B(cudaMemcpyAsync(hs, d_bstats, sizeof(hs), cudaMemcpyDeviceToHost, st));
@@ -1488,8 +1351,7 @@ int ws_merge_partial_topk(ws_index* idx, const uint32_t* ids, const float* dists
   a.ids = ids; a.dists = dists; a.parts = parts; a.k = k; a.nq = (uint32_t)nq; a.pad_id = pad_id;
   a.out_ids = out_ids; a.out_dists = out_dists;
   int grid = (int)std::min<uint64_t>(nq, (uint64_t)idx->num_sms * 16);
-  ws_merge_parts_kernel<<<grid, WS_CTA_THREADS, 0, idx->stream>>>(a);
-  WS_CUDA(cudaGetLastError());
+  WS_CUDA(wsl_merge_parts(grid, idx->stream, a));
   idx->launches++;
   return WS_OK;
 }
@@ -1523,6 +1385,7 @@ int ws_index_launch_count(const ws_index* idx, uint64_t* out) {
 }
 int ws_index_set_option(ws_index* idx, const char* name, int64_t value) {
   if (!idx || !name) return ws_fail(WS_ERR_BADARG, "null argument");
+  std::lock_guard<std::recursive_mutex> lock(idx->mu);
   std::string s(name);
   if (s == "expand_width") {
     if (value < 1 || value > 8) return ws_fail(WS_ERR_BADARG, "expand_width must be 1..8");

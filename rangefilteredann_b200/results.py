@@ -4,7 +4,7 @@ here is on the query path.
 
 Mirrors experiments/run_our_method.py:
   compute_recall   :174-180   mean |GT ∩ top-k| / |GT| per query
-  should_break     :183-207   early exit of a beam sweep
+  sweep_finished   :183-207   early exit of a beam sweep (the driver's `should_break` rule)
   method names     :255,295,367,397,433,525  ("prefiltering", "postfiltering_<alpha>_<beam>_<mult>",
                    "vamana-tree_<alpha>_<split>_<beam>", "optimized-postfiltering_<alpha>_<split>_<beam>_<mult>",
                    "smart-combined_…", "three-split_…", "super-postfiltering_<split>_<shift>_<alpha>_<beam>_<mult>")
@@ -28,23 +28,22 @@ def compute_recall(gt_neighbors, results, top_k: int) -> float:
     return recall / len(gt_neighbors)
 
 
-def should_break(run_results) -> bool:
-    """run_our_method.py:183-207: stop a sweep when recall is ~1, when recall stopped improving (unless
-    final_beam_multiply == 1), or when the last run was slower than prefiltering."""
-    if len(run_results) == 0:
+def sweep_finished(rows) -> bool:
+    """When the reference driver stops widening the beam for one (filter width, method) sweep
+    (rule of run_our_method.py:183-207).  `rows` are the sweep's result tuples so far,
+    (filter_width, method_name, recall, seconds); method names end in "_<final_beam_multiply>"."""
+    if not rows:
         return False
-    if run_results[-1][2] > 0.999:
+    _, name, recall, seconds = rows[-1][:4]
+    if recall > 0.999:                      # saturated
         return True
-    if len(run_results) == 1:
+    if len(rows) < 2:
         return False
-    recall_not_better = run_results[-1][2] <= run_results[-2][2]
-    one_multiply = run_results[-1][1].split("_")[-1] == "1"
-    if recall_not_better and not one_multiply:
+    stalled = recall <= rows[-2][2]
+    if stalled and not name.endswith("_1"):  # with final_beam_multiply == 1 a stall is not conclusive
         return True
-    prefiltering_results = [x for x in run_results if x[1] == "prefiltering"]
-    if len(prefiltering_results) == 0:
-        return False
-    return run_results[-1][3] > prefiltering_results[-1][3]
+    brute_force = [r[3] for r in rows if r[1] == "prefiltering"]
+    return bool(brute_force) and seconds > brute_force[-1]
 
 
 def filter_width_name(power: int) -> str:

@@ -23,7 +23,17 @@ def _pick(base: str, metric: str, dtype: str):
     raise Exception("Invalid metric " + metric)
 
 
-def prefilter_index_constructor(metric, dtype):          # wrapper.py:218-242
+def range_filter_tree_index_constructor(metric, dtype):  # wrapper.py:219-239 — the one helper that spells the 8-bit
+    # classes the way the module registers them ("UInt8" / "Int8"), so all three dtypes are reachable through it
+    names = {"float": "Float", "uint8": "UInt8", "int8": "Int8"}
+    if metric not in ("Euclidian", "mips"):
+        raise Exception("Invalid metric " + metric)
+    if dtype not in names:
+        raise Exception("Invalid data type " + dtype)
+    return getattr(_eng, "RangeFilterTreeIndex" + names[dtype] + ("Euclidian" if metric == "Euclidian" else "Mips"))
+
+
+def prefilter_index_constructor(metric, dtype):          # wrapper.py:242-266
     return _pick("PrefilterIndex", metric, dtype)
 
 

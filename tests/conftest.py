@@ -1,3 +1,4 @@
+import contextlib
 import importlib.util
 import os
 import sys
@@ -11,6 +12,25 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 DATA_CACHE = os.path.join(ROOT, "data_cache")
+REF_CACHE = os.path.join(ROOT, "ref_cache")  # graph caches written by the UNMODIFIED reference builder (oracle/build_ref_cache.py)
+
+# A graph-cache miss must never be answered by the device-side builder behind a test's back: it would write
+# engine-built graphs into the committed golden directories under the reference's file names and turn "searched on
+# identical reference graphs" into self-comparison.  Tests that WANT a device build say so (device_graph_build()).
+os.environ["WSANN_GRAPH_BUILD"] = "0"
+
+
+@contextlib.contextmanager
+def device_graph_build():
+    old = os.environ.get("WSANN_GRAPH_BUILD")
+    os.environ["WSANN_GRAPH_BUILD"] = "1"
+    try:
+        yield
+    finally:
+        if old is None:
+            os.environ.pop("WSANN_GRAPH_BUILD", None)
+        else:
+            os.environ["WSANN_GRAPH_BUILD"] = old
 
 
 def pytest_configure(config):

@@ -66,13 +66,13 @@ def test_results_csv_matches_reference_driver_format(tmp_path):
     assert res.method_name("optimized_postfilter", 80, 2) == "optimized-postfiltering_1.000_2_80_2"
     assert res.method_name("super", 10, 4) == "super-postfiltering_2_0.5_1.0_10_4"
     assert res.filter_width_name(-8) == "2pow-8"
-    # should_break: recall ~ 1 stops; no improvement stops unless final multiply is 1; slower than prefiltering stops
-    assert not res.should_break([])
-    assert res.should_break([("2pow-8", "x_1", 0.9995, 1.0)])
-    assert not res.should_break([("2pow-8", "x_10_1", 0.9, 1.0)])
-    assert res.should_break([("w", "x_10_2", 0.9, 1.0), ("w", "x_20_2", 0.9, 1.0)])
-    assert not res.should_break([("w", "x_10_1", 0.9, 1.0), ("w", "x_20_1", 0.9, 1.0)])
-    assert res.should_break([("w", "prefiltering", 1.0 - 1e-3 - 1e-9, 0.5), ("w", "x_10_1", 0.8, 0.1), ("w", "x_20_1", 0.9, 0.7)])
+    # sweep_finished: recall ~ 1 stops; no improvement stops unless final multiply is 1; slower than prefiltering stops
+    assert not res.sweep_finished([])
+    assert res.sweep_finished([("2pow-8", "x_1", 0.9995, 1.0)])
+    assert not res.sweep_finished([("2pow-8", "x_10_1", 0.9, 1.0)])
+    assert res.sweep_finished([("w", "x_10_2", 0.9, 1.0), ("w", "x_20_2", 0.9, 1.0)])
+    assert not res.sweep_finished([("w", "x_10_1", 0.9, 1.0), ("w", "x_20_1", 0.9, 1.0)])
+    assert res.sweep_finished([("w", "prefiltering", 1.0 - 1e-3 - 1e-9, 0.5), ("w", "x_10_1", 0.8, 0.1), ("w", "x_20_1", 0.9, 0.7)])
     path = str(tmp_path / "results" / "sift_results.csv")
     res.save_results([("2pow-8", "prefiltering", 1.0, 2.0), ("2pow-8", "vamana-tree_1.000_2_10", 0.97, 0.5, 12.5, 2, 100)],
                      path, 10000, "B200x1")

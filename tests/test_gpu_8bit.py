@@ -13,7 +13,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, device_graph_build
 from golden_cases import TINY_U8, tiny_u8_cases, tiny_u8_dataset
 from oracle_api import Oracle
 
@@ -50,9 +50,10 @@ def test_graph_classes_vs_oracle(engine, tmp_path, sfx, signed, metric):
     fdata, fq = data.astype(np.float32), queries.astype(np.float32)
     wst, sup, flat = (str(tmp_path / k) + "/" for k in ("wst", "super", "flat"))
     bp = lambda path: engine.BuildParams(64, 500, 1.0, path)
-    tree = getattr(engine, "VamanaRangeFilterTreeIndex" + sfx)(data, labels, TINY_U8["cutoff"], 2, bp(wst))
-    supt = getattr(engine, "SuperOptimizedPostfilterTreeIndex" + sfx)(data, labels, TINY_U8["cutoff"], 2.0, 0.5, bp(sup))
-    flt = getattr(engine, "PostfilterVamanaIndex" + sfx)(data, labels, bp(flat))
+    with device_graph_build():
+        tree = getattr(engine, "VamanaRangeFilterTreeIndex" + sfx)(data, labels, TINY_U8["cutoff"], 2, bp(wst))
+        supt = getattr(engine, "SuperOptimizedPostfilterTreeIndex" + sfx)(data, labels, TINY_U8["cutoff"], 2.0, 0.5, bp(sup))
+        flt = getattr(engine, "PostfilterVamanaIndex" + sfx)(data, labels, bp(flat))
     o_tree = Oracle("wst", fdata, labels, wst, metric=metric, dist_mode=1, cutoff=TINY_U8["cutoff"])
     o_sup = Oracle("super", fdata, labels, sup, metric=metric, dist_mode=1, cutoff=TINY_U8["cutoff"])
     o_flat = Oracle("flat", fdata, labels, flat, metric=metric, dist_mode=1)

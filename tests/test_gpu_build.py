@@ -8,7 +8,7 @@ import struct
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, device_graph_build
 from golden_cases import TINY
 from oracle_api import Oracle
 from rangefilteredann_b200 import synth
@@ -30,8 +30,9 @@ def read_graph(path):
 def built(engine, tmp_path_factory):
     cache = str(tmp_path_factory.mktemp("gpu_built")) + "/"
     data, queries, labels = synth.make_dataset(TINY["n"], TINY["d"], TINY["nq"], TINY["seed"])
-    tree = engine.VamanaRangeFilterTreeIndexFloatEuclidian(data, labels, TINY["cutoff"], 2,
-                                                           engine.BuildParams(64, 500, 1.0, cache))
+    with device_graph_build():
+        tree = engine.VamanaRangeFilterTreeIndexFloatEuclidian(data, labels, TINY["cutoff"], 2,
+                                                               engine.BuildParams(64, 500, 1.0, cache))
     return dict(cache=cache, data=data, queries=queries, labels=labels, tree=tree)
 
 

@@ -16,6 +16,7 @@ asserted anyway, against an independent brute-force ground truth.
 import numpy as np
 import pytest
 
+from conftest import device_graph_build
 from oracle_api import Oracle
 from rangefilteredann_b200 import synth
 
@@ -40,11 +41,13 @@ def test_all_17_fractions(engine, tmp_path, d, angular, kind, label_kind):
     bp = engine.BuildParams(64, 500, 1.0, cache)
     metric = 1 if angular else 0
     if kind == "super":
-        idx = getattr(engine, "SuperOptimizedPostfilterTreeIndex" + sfx)(data, labels, 1000, 2.0, 0.5, bp)
+        with device_graph_build():
+            idx = getattr(engine, "SuperOptimizedPostfilterTreeIndex" + sfx)(data, labels, 1000, 2.0, 0.5, bp)
         orc = Oracle("super", data, labels, cache, metric=metric, dist_mode=1, cutoff=1000)
         methods = ["super"]
     else:
-        idx = getattr(engine, "VamanaRangeFilterTreeIndex" + sfx)(data, labels, 1000, 2, bp)
+        with device_graph_build():
+            idx = getattr(engine, "VamanaRangeFilterTreeIndex" + sfx)(data, labels, 1000, 2, bp)
         orc = Oracle("wst", data, labels, cache, metric=metric, dist_mode=1, cutoff=1000)
         methods = ["fenwick", "optimized_postfilter"]
     qp = engine.QueryParams(K, 20, 1.35, 10_000_000, 10_000, 2, 10000, None, False)

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, device_graph_build
 from golden_cases import TINY
 from rangefilteredann_b200 import capi, label_shard, synth
 
@@ -45,7 +45,8 @@ def test_two_label_shards_on_one_device(engine, tmp_path):
     data, queries, labels = synth.make_dataset(TINY["n"], TINY["d"], TINY["nq"], TINY["seed"])
     single = engine.VamanaRangeFilterTreeIndexFloatEuclidian(
         data, labels, TINY["cutoff"], 2, engine.BuildParams(64, 500, 1.0, os.path.join(GOLDEN, "tiny", "wst") + "/"))
-    shards = [label_shard.LabelShardedTree(data, labels, r, 2, str(tmp_path), cutoff=TINY["cutoff"]) for r in range(2)]
+    with device_graph_build():
+        shards = [label_shard.LabelShardedTree(data, labels, r, 2, str(tmp_path), cutoff=TINY["cutoff"]) for r in range(2)]
     qp = engine.QueryParams(10, 20, 1.35, 10_000_000, 10_000, 1, 10000, None, False)
     for power in (-4, -1, 0):
         w = synth.make_windows(labels, power, TINY["nq"], seed=400 + power)

@@ -214,12 +214,9 @@ def test_rejects_unsupported(tiny, engine):
         tiny.run_engine("optimized_postfilter", tiny.queries[:4], w, beam=10, max_beam=50000)
     with pytest.raises(RuntimeError):
         tiny.run_engine("fenwick", tiny.queries[:4], w, k=5000)
-    os.environ["WSANN_GRAPH_BUILD"] = "0"
-    try:
-        with pytest.raises(RuntimeError, match="graph cache miss"):
-            engine.PostfilterVamanaIndexFloatEuclidian(tiny.data, tiny.labels, engine.BuildParams(64, 500, 1.0, "/nonexistent/"))
-    finally:
-        del os.environ["WSANN_GRAPH_BUILD"]
+    assert os.environ.get("WSANN_GRAPH_BUILD") == "0"  # tests/conftest.py: no implicit device builds
+    with pytest.raises(RuntimeError, match="graph cache miss"):
+        engine.PostfilterVamanaIndexFloatEuclidian(tiny.data, tiny.labels, engine.BuildParams(64, 500, 1.0, "/nonexistent/"))
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(DATA_CACHE, "small", "wst")), reason="data_cache/small not present")
