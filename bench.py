@@ -48,6 +48,51 @@ BEAMS = [10, 20, 40, 80, 160, 320]
 MULTS = [1, 2, 4]
 RECALL_TARGET = 0.95
 PREFILTER_OPS = ("prefilter", "prefilter_direct", "prefilter_tc")
+# the engine's own routing of a PrefilterIndex batch (csrc/wsann.cu ws_run_batch, defaults of the options
+# gemm_min_window / scan_chunk): what `PrefilterIndex*.batch_search` does when nobody sets an option
+GEMM_MIN_WINDOW = 768
+SCAN_CHUNK = 8192
+
+
+def auto_prefilter_route(mean_window: float) -> str:
+    if mean_window >= GEMM_MIN_WINDOW:
+        return "prefilter_tc"
+    if mean_window <= SCAN_CHUNK:
+        return "prefilter_direct"
+    return "prefilter"
+
+
+def workload_string(cfg: dict) -> str:
+    """One string for both arms (the driver compares them)."""
+    return (f"{cfg['name']}, uniform unique labels, 2-WST (cutoff 1000, R=64 L=500 alpha=1, one set of reference-format "
+            f"graph files searched by both arms), prefilter / range-filter tree / optimized postfilter, "
+            f"17 fractions x {cfg['nq']} queries, k=10, per fraction the fastest method reaching recall@10 >= 0.95")
+
+
+def rows_equal_up_to_ties(ids, dists, rids, rdists, rtol=1e-5):
+    """Per row: ids equal position-wise, except among entries whose distances tie within rtol (BASELINE.json:
+    'prefilter top-k ids must match the reference exactly, except for distance ties within 1e-5 relative')."""
+    ok = np.zeros(len(ids), dtype=bool)
+    for i in range(len(ids)):
+        if not np.allclose(dists[i], rdists[i], rtol=rtol, atol=1e-30):
+            continue
+        if np.array_equal(ids[i], rids[i]):
+            ok[i] = True
+            continue
+        good = True
+        for j in np.nonzero(ids[i] != rids[i])[0]:
+            d = rdists[i, j]
+            tie = np.isclose(rdists[i], d, rtol=rtol, atol=1e-30)
+            if not (ids[i, j] in rids[i][tie] or np.isclose(rdists[i, -1], d, rtol=rtol, atol=1e-30)):
+                good = False
+                break
+        ok[i] = good
+    return ok
+
+
+# oracle/_ref is the reference compiled with its own flags (CMakeLists.txt:17-24) except that -march=native
+# becomes -march=x86-64-v3 (AVX2 + FMA; the build container's CPU is not the GPU box's)
+REF_MARCH = "x86-64-v3 (oracle/Makefile; the reference's CMake uses -march=native)"
 
 
 def log(*a):
@@ -305,12 +350,16 @@ class EngineRunner:
         self.dids = self.h.dalloc(nq * K * 4)
         self.ddists = self.h.dalloc(nq * K * 4)
         self.dwin = {}
+        self.mean_window = {}
 
-    def upload(self, queries, windows_by_power):
+    def upload(self, queries, windows_by_power, sorted_labels=None):
         self.h.h2d(self.dq, queries)
         for p, w in windows_by_power.items():
             self.dwin[p] = self.h.dalloc(w.nbytes)
             self.h.h2d(self.dwin[p], w)
+            if sorted_labels is not None:
+                rows = np.searchsorted(sorted_labels, w[:, 1]) - np.searchsorted(sorted_labels, w[:, 0])
+                self.mean_window[p] = float(np.mean(rows.clip(min=0)))
 
     def launch_dev(self, power, op):
         method, beam, mult = op
@@ -355,6 +404,9 @@ def choose_operating_points(runner: EngineRunner, gts, rank):
             r = recall_at_k(runner.fetch(), gts[p])
             ms = runner.time_dev(p, (alt, 0, 0))
             per_method[alt] = dict(op=(alt, 0, 0), recall=r, ms=ms)
+        # what PrefilterIndex.batch_search picks by itself for this fraction's windows (the step uses THIS, not the
+        # fastest of the three)
+        per_method["prefilter_auto"] = dict(per_method[auto_prefilter_route(runner.mean_window[p])])
         for method in ("fenwick", "optimized_postfilter"):
             best = None
             for mult in (MULTS if method == "optimized_postfilter" else [1]):
@@ -406,8 +458,10 @@ def run_engine(args, rank, world, local_rank):
     tree = eng.VamanaRangeFilterTreeIndexFloatEuclidian(data, labels, cfg["cutoff"], 2, eng.BuildParams(64, 500, 1.0, cdir))
     log(f"rank {rank}: data + index ready in {time.time() - t_setup:.1f}s")
     gts = ground_truth_torch(data, queries, labels, windows, f"cuda:{local_rank}")
+    pre = eng.PrefilterIndexFloatEuclidian(data, labels)  # the class run_our_method.py:249 calls for "prefiltering"
+    sorted_labels = np.sort(labels)
     runner = EngineRunner(tree, cfg["nq"], cfg["d"])
-    runner.upload(queries, windows)
+    runner.upload(queries, windows, sorted_labels)
     h = runner.h
     if args.ops_file and os.path.exists(args.ops_file):
         saved = json.load(open(args.ops_file))
@@ -418,7 +472,9 @@ def run_engine(args, rank, world, local_rank):
         if args.ops_file and rank == 0:
             json.dump({str(p): {m: dict(op=list(v["op"]), recall=v["recall"], ms=v["ms"]) for m, v in pm.items()}
                        for p, pm in table.items()}, open(args.ops_file, "w"))
-    ops = {p: min(table[p].values(), key=lambda v: v["ms"])["op"] for p in POWERS}
+    # per fraction: the fastest of {prefilter as the engine routes it by itself, range-filter tree, optimized postfilter}
+    step_methods = ("prefilter_auto", "fenwick", "optimized_postfilter")
+    ops = {p: min((table[p][m] for m in step_methods if m in table[p]), key=lambda v: v["ms"])["op"] for p in POWERS}
     nq_step = cfg["nq"] * len(POWERS)
 
     def barrier():
@@ -458,28 +514,37 @@ def run_engine(args, rank, world, local_rank):
     stats = h.stats()
     h.set_option("profile_kernels", 0)
 
-    # ---- end to end through the public API, pinned host buffers
-    hq = capi.pinned_array(queries.shape, np.float32)
-    hq[:] = queries
-    hw = {p: capi.pinned_array(windows[p].shape, np.float32) for p in POWERS}
-    for p in POWERS:
-        hw[p][:] = windows[p]
-    pre_handle_ops = {}
+    # ---- end to end through the public API: the pybind classes the reference driver calls (run_our_method.py:249,357,
+    # 387), ordinary pageable numpy arrays, default options (the engine routes prefilter batches by itself)
+    h.set_option("gemm_prefilter", 2)
+    h.set_option("prefilter_direct", 2)
+    hpre = capi.Handle.borrow(pre)
+    qps_by_op = {}
+
+    def e2e_call(p):
+        method, beam, mult = ops[p]
+        if method in PREFILTER_OPS:
+            return pre.batch_search(queries, windows[p], cfg["nq"], qps_by_op.setdefault((10, 1), eng.QueryParams(K, 10, 1.35, 10_000_000, 10_000, 1, 10000, None, False)))
+        qp = qps_by_op.setdefault((beam, mult), eng.QueryParams(K, beam, 1.35, 10_000_000, 10_000, mult, 10000, None, False))
+        return tree.batch_search(queries, windows[p], cfg["nq"], method, qp)
 
     def step_e2e():
         for p in POWERS:
-            method, beam, mult = ops[p]
-            if method in PREFILTER_OPS:
-                ids = np.empty((cfg["nq"], K), np.uint32)
-                dd = np.empty((cfg["nq"], K), np.float32)
-                h.set_option("gemm_prefilter", 1 if method == "prefilter_tc" else 0)
-                h.set_option("prefilter_direct", 1 if method == "prefilter_direct" else 0)
-                h.prefilter_batch(hq, hw[p], cfg["nq"], K, ids, dd)
-            else:
-                qp = eng.QueryParams(K, beam, 1.35, 10_000_000, 10_000, mult, 10000, None, False)
-                ids, dd = tree.batch_search(hq, hw[p], cfg["nq"], method, qp)
+            ids, _ = e2e_call(p)
         return ids
 
+    # which kernels the auto-routed prefilter calls actually launch (must be what the device-timed step runs)
+    routes = {}
+    hpre.set_option("profile_kernels", 1)
+    for p in POWERS:
+        if ops[p][0] in PREFILTER_OPS:
+            hpre.kernel_times(reset=True)
+            e2e_call(p)
+            kt = hpre.kernel_times(reset=True)
+            routes[f"2^{p}"] = "prefilter_tc" if "gemm_sweep" in kt else ("prefilter" if "decompose" in kt else "prefilter_direct")
+            if routes[f"2^{p}"] != ops[p][0]:
+                log(f"WARNING 2^{p}: auto routing took {routes[f'2^{p}']}, the device-timed step ran {ops[p][0]}")
+    hpre.set_option("profile_kernels", 0)
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
     barrier()
@@ -584,7 +649,9 @@ def run_engine(args, rank, world, local_rank):
     roofline["other_kernels"] = cands[1:]
     roofline["kernel_ms_per_step"] = {kname: round(v["ms"] / args.steps, 4) for kname, v in ktimes.items()}
 
-    cpu = cpu_baseline(args, cfg, data, queries, labels, windows, gts, table, ops) if not args.no_cpu else None
+    cpu, parity = (None, None)
+    if not args.no_cpu:
+        cpu, parity = cpu_baseline(args, cfg, data, queries, labels, windows, gts, table, ops, eng, tree, pre)
 
     per_fraction = {}
     for p in POWERS:
@@ -596,19 +663,21 @@ def run_engine(args, rank, world, local_rank):
         "value": round(value, 1), "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{cfg['name']}, uniform unique labels, 2-WST (cutoff 1000, R=64 L=500 alpha=1, "
-                               f"reference-format graphs) prefilter / range-filter tree / optimized postfilter, "
-                               f"17 fractions x {cfg['nq']} queries, k=10",
+        "config": {"workload": workload_string(cfg),
                    "name": args.config, "queries_per_step": nq_step * world,
                    "l2_policy": "working set (vectors + adjacency, >= 0.25 GB, random gathers) exceeds the 126 MB L2; no flush",
                    "parallelism": f"query-sharded dp{world}, index replicated"},
         "e2e": {"value": round(e2e_value, 1), "unit": "queries/s",
                 "h2d_bytes_per_step": int(len(POWERS) * cfg["nq"] * (cfg["d"] * 4 + 8)),
-                "d2h_bytes_per_step": int(len(POWERS) * cfg["nq"] * K * 8)},
+                "d2h_bytes_per_step": int(len(POWERS) * cfg["nq"] * K * 8),
+                "api": "pybind PrefilterIndexFloatEuclidian.batch_search / VamanaRangeFilterTreeIndexFloatEuclidian.batch_search, "
+                       "pageable numpy arrays, default engine options (prefilter batches routed by the engine)",
+                "prefilter_routes": routes},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "parity": parity,
         "counters_per_step": {kname: int(v / args.steps) for kname, v in stats.items()},
         "per_fraction": per_fraction,
     }
@@ -639,53 +708,94 @@ def ref_indices(ref, cfg, cdir, data, labels):
     return tree, pre
 
 
-def ref_time(ref, tree, pre, queries, w, op, nq):
+def ref_time(ref, tree, pre, queries, w, op, nq, want_dists=False):
     method, beam, mult = op
     qp = ref.QueryParams(K, max(beam, 1), 1.35, 10_000_000, 10_000, max(mult, 1), 10000, None, False)
     t0 = time.perf_counter()
     if method == "prefilter":
-        ids, _ = pre.batch_search(queries[:nq], w[:nq], nq, qp)
+        ids, dd = pre.batch_search(queries[:nq], w[:nq], nq, qp)
     else:
-        ids, _ = tree.batch_search(queries[:nq], w[:nq], nq, method, qp)
-    return time.perf_counter() - t0, ids
+        ids, dd = tree.batch_search(queries[:nq], w[:nq], nq, method, qp)
+    dt = time.perf_counter() - t0
+    return (dt, ids, dd) if want_dists else (dt, ids)
 
 
-def cpu_baseline(args, cfg, data, queries, labels, windows, gts, table, ops):
+def cpu_baseline(args, cfg, data, queries, labels, windows, gts, table, ops, eng, tree_e, pre_e):
     """The reference's own implementation (oracle/_ref), all host threads, timed exactly as
     run_our_method.py does (time around one batch_search incl. argument conversion), on a
     bounded sample of each fraction's batch, at each method's operating point; per fraction
-    the fastest method with recall >= 0.95 counts."""
+    the fastest method with recall >= 0.95 counts.
+
+    The reference's rows are kept and compared with this engine's rows for the SAME queries, windows, graph
+    files and (method, beam, final_multiply) — SURVEY.md App. G T1 / T5 at the BASELINE size, inside the bench:
+      prefilter              rows equal up to distance ties within 1e-5 relative (BASELINE.json north_star)
+      fenwick / opt. postf.  |recall_engine - recall_reference| <= 0.005 at equal beam
+    Returns (cpu_baseline, parity)."""
     ref = load_ref()
     if ref is None:
-        return {"value": None, "unit": "queries/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+        return {"value": None, "unit": "queries/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}, None
     assert not hasattr(ref, "__engine__"), "the reference module resolved to this engine"
     cores = int(os.environ.get("PARLAY_NUM_THREADS", os.cpu_count()))
     tree, pre = ref_indices(ref, cfg, cache_dir(args.config), data, labels)
     total_q, total_t, detail = 0, 0.0, {}
+    par = {"prefilter_rows_compared": 0, "prefilter_rows_equal_up_to_1e-5_ties": 0, "prefilter_rows_bit_identical_ids": 0,
+           "recall_gate": 0.005, "recall_points_compared": 0, "recall_points_within_gate": 0, "max_abs_recall_diff": 0.0,
+           "per_fraction": {}}
     ref_time(ref, tree, pre, queries, windows[-8], ("prefilter", 0, 0), 64)  # warm the pool
     for p in POWERS:
         best = None
+        pf = {}
         for method, v in table[p].items():
-            if method in ("prefilter_tc", "prefilter_direct"):  # the reference has one prefilter implementation (timed as "prefilter")
+            if method in ("prefilter_tc", "prefilter_direct", "prefilter_auto"):  # the reference has one prefilter implementation (timed as "prefilter")
                 continue
             ns = min(args.cpu_sample, cfg["nq"])
             t_probe, _ = ref_time(ref, tree, pre, queries, windows[p], v["op"], min(64, ns))
             per_q = t_probe / min(64, ns)
             ns = int(max(64, min(ns, args.cpu_budget_s / len(POWERS) / 3 / max(per_q, 1e-7))))
-            t, ids = ref_time(ref, tree, pre, queries, windows[p], v["op"], ns)
+            t, ids, rd = ref_time(ref, tree, pre, queries, windows[p], v["op"], ns, want_dists=True)
             r = recall_at_k(ids, gts[p][:ns])
             if r >= RECALL_TARGET - 0.02 and (best is None or t / ns < best[0]):  # sample recall is noisier
                 best = (t / ns, method, ns, r)
+            # ---- parity on the same sample, through the same pybind classes with default options
+            q_s, w_s = np.ascontiguousarray(queries[:ns]), np.ascontiguousarray(windows[p][:ns])
+            _, beam, mult = v["op"]
+            qp = eng.QueryParams(K, max(beam, 1), 1.35, 10_000_000, 10_000, max(mult, 1), 10000, None, False)
+            if method == "prefilter":
+                eids, ed = pre_e.batch_search(q_s, w_s, ns, qp)
+                ok = rows_equal_up_to_ties(eids, ed, ids, rd)
+                same = int((eids == ids).all(1).sum())
+                par["prefilter_rows_compared"] += ns
+                par["prefilter_rows_equal_up_to_1e-5_ties"] += int(ok.sum())
+                par["prefilter_rows_bit_identical_ids"] += same
+                pf["prefilter"] = {"rows": ns, "equal_up_to_ties": int(ok.sum()), "identical_ids": same}
+            else:
+                eids, _ = tree_e.batch_search(q_s, w_s, ns, method, qp)
+                r_e = recall_at_k(eids, gts[p][:ns])
+                diff = abs(r_e - r)
+                par["recall_points_compared"] += 1
+                par["recall_points_within_gate"] += int(diff <= par["recall_gate"])
+                par["max_abs_recall_diff"] = max(par["max_abs_recall_diff"], diff)
+                pf[method] = {"beam": beam, "final_multiply": mult, "queries": ns, "recall_engine": round(r_e, 4),
+                              "recall_reference": round(r, 4), "rows_identical_ids": int((eids == ids).all(1).sum())}
+        par["per_fraction"][f"2^{p}"] = pf
         if best is None:
             continue
         detail[f"2^{p}"] = {"method": best[1], "qps": round(1.0 / best[0]), "sample": best[2], "recall": round(best[3], 4)}
         total_q += 1
         total_t += best[0]
     value = total_q / total_t if total_t > 0 else None  # queries/s for one query of every fraction
-    return {"value": round(value, 1) if value else None, "unit": "queries/s", "cores": cores, "kind": "reference",
-            "sample": f"up to {args.cpu_sample} queries per fraction (time-bounded), same windows/graphs/operating points; "
-                      f"equal weight per fraction as in the GPU step",
-            "per_fraction": detail}
+    par["max_abs_recall_diff"] = round(par["max_abs_recall_diff"], 4)
+    par["ok"] = bool(par["prefilter_rows_compared"] == par["prefilter_rows_equal_up_to_1e-5_ties"] and
+                     par["recall_points_compared"] == par["recall_points_within_gate"])
+    par["against"] = "oracle/_ref (the unmodified reference) on the same queries, windows and graph files"
+    if not par["ok"]:
+        log("PARITY FAILURE against the reference: " + json.dumps({k2: v2 for k2, v2 in par.items() if k2 != "per_fraction"}))
+    cpu = {"value": round(value, 1) if value else None, "unit": "queries/s", "cores": cores, "kind": "reference",
+           "march": REF_MARCH,
+           "sample": f"up to {args.cpu_sample} queries per fraction (time-bounded), same windows/graphs/operating points; "
+                     f"equal weight per fraction as in the GPU step",
+           "per_fraction": detail}
+    return cpu, par
 
 
 def run_reference(args, rank, world):
@@ -744,10 +854,11 @@ def run_reference(args, rank, world):
             "value": round(value, 1), "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(dt / args.steps * 1000.0, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{cfg['name']} (same data, windows, graphs as the engine arm); each step = one "
-                                   f"batch per fraction x 17 fractions, batch = 0.25 s of work bounded to "
-                                   f"[{ns}, {cfg['nq']}] queries; value = 17 / sum of per-query times", "name": args.config},
+            "config": {"workload": workload_string(cfg), "name": args.config,
+                       "sampling": f"each step = one batch per fraction x 17 fractions, batch = 0.25 s of work bounded to "
+                                   f"[{ns}, {cfg['nq']}] queries; value = 17 / sum of per-query times"},
             "cpu_baseline": {"value": round(value, 1), "unit": "queries/s", "cores": cores, "kind": "reference",
+                             "march": REF_MARCH,
                              "sample": "per fraction: " + ", ".join(f"2^{p}:{ns_p[p]}" for p in POWERS)},
             "e2e": {"value": round(value, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "per_fraction": {f"2^{p}": {"method": ops[p][0], "beam": ops[p][1], "qps_estimate": round(est_qps[p])}

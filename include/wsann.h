@@ -90,7 +90,7 @@ typedef struct ws_stats {
   uint64_t beam_sum;           /* sum of beamSize over graph_searches (frontier bytes) */
 } ws_stats;
 
-typedef struct ws_index ws_index; /* opaque: one HBM arena on one device */
+typedef struct ws_index ws_index; /* opaque: one HBM arena on one device (several of them form a ws_group) */
 
 const char* ws_last_error(void);
 int ws_abi_version(void);
@@ -175,12 +175,63 @@ int ws_tree_batch(ws_index* idx, int method, const float* queries, const float* 
 
 /* Label-range sharded mode (datasets larger than one GPU's HBM): every rank
  * owns a contiguous label range with its own sub-tree, answers the whole batch locally, the
- * per-rank [nq][k] rows are all-gathered (NCCL over NVLink, done by the host plumbing) and this
- * kernel merges the `parts` lists per query — sort_and_truncate (range_filter_tree.h:542-549)
+ * per-rank [nq][k] rows are all-gathered (ws_allgather_merge / ws_group below do both steps; this entry point
+ * takes rows the host plumbing gathered by other means) and this kernel merges the `parts` lists per query — sort_and_truncate (range_filter_tree.h:542-549)
  * across shards.  All pointers are DEVICE pointers; rows with dist == FLT_MAX are pads.
  * Enqueues on the index stream. */
 int ws_merge_partial_topk(ws_index* idx, const uint32_t* ids, const float* dists, uint32_t parts, uint64_t nq,
                           uint32_t k, uint32_t pad_id, uint32_t* out_ids, float* out_dists);
+
+/* ---- multi-GPU inside the engine ------------------------------------------------------------
+ * The reference spreads one batch over the host's cores with `parlay::parallel_for` over the queries
+ * (range_filter_tree.h:70, prefiltering.h:131, postfilter_vamana.h:199, super_optimized_postfilter_tree.h:66).
+ * A ws_group spreads one batch over the GPUs of the box behind the same call (SURVEY.md §8b `ws_ctx`, §8e):
+ *
+ *   WS_GROUP_REPLICATED     every member holds the whole arena; the batch is cut into one contiguous slice per
+ *                           member (queries are independent units: no data-path collective)
+ *   WS_GROUP_LABEL_SHARDED  member g holds a contiguous range of the label-sorted points and its own tree; every
+ *                           member answers the whole batch on its shard, the [nq][k] partial rows are exchanged
+ *                           and merged per query (sort_and_truncate, range_filter_tree.h:542-549, across shards).
+ *                           Option "exchange": 0 = each member's merge kernel reads its peers' rows straight from
+ *                           their HBM over NVLink (peer access; default when available), 1 = ncclAllGather + merge.
+ *
+ * Host buffers only; the call returns when ids / dists are filled.  Members must be finalized and are not owned
+ * by the group.  Any other option name given to ws_group_set_option is forwarded to every member. */
+typedef struct ws_group ws_group;
+typedef enum ws_group_mode { WS_GROUP_REPLICATED = 0, WS_GROUP_LABEL_SHARDED = 1 } ws_group_mode;
+
+/* Clone of a finalized arena on another device (vectors, labels, decode, adjacency copied device to device). */
+int ws_index_replicate(ws_index* src, int device, ws_index** out);
+
+int ws_group_create(ws_index* const* members, int count, int mode, ws_group** out);
+void ws_group_destroy(ws_group* g);
+int ws_group_size(const ws_group* g, int* count);
+int ws_group_member(const ws_group* g, int i, ws_index** out);
+int ws_group_set_option(ws_group* g, const char* name, int64_t value);
+/* peer_access: all member pairs can read each other's HBM; exchange_in_use: 0 peer loads / 1 NCCL;
+ * last_ms3: device times of the last label-sharded batch, max over members: {search, exchange + merge, total} */
+int ws_group_info(ws_group* g, int* peer_access, int* exchange_in_use, double* last_ms3);
+/* PrefilterIndex::batch_search / PostfilterVamanaIndex::batch_search / RangeFilterTreeIndex::batch_search /
+ * SuperOptimizedPostfilterTree::batch_search over all members (same arguments as the ws_*_batch calls) */
+int ws_group_prefilter_batch(ws_group* g, const float* queries, const float* windows, uint64_t nq, uint32_t k,
+                             uint32_t* ids, float* dists);
+int ws_group_postfilter_batch(ws_group* g, int32_t node, const float* queries, const float* windows, uint64_t nq,
+                              const ws_query_params* qp, int pad, uint32_t* ids, float* dists);
+int ws_group_tree_batch(ws_group* g, int method, const float* queries, const float* windows, uint64_t nq,
+                        const ws_query_params* qp, uint32_t* ids, float* dists);
+
+/* One process per GPU (torchrun-style launch): the label-sharded exchange with NCCL inside this library.
+ * Rank 0 makes an id (ncclGetUniqueId) and hands the 128 bytes to the other ranks by whatever means the host
+ * program has; every rank then binds a communicator to its arena.  ws_allgather_merge all-gathers this rank's
+ * [nq][k] rows (DEVICE pointers, global ids, pads carry FLT_MAX) on the index stream and merges the ranks' lists
+ * per query into out_ids / out_dists (device pointers).  NCCL is loaded with dlopen("libnccl.so.2") on first use. */
+#define WS_NCCL_ID_BYTES 128
+int ws_nccl_unique_id(void* id_out);
+int ws_nccl_version(int* version);
+int ws_index_comm_init(ws_index* idx, int nranks, int rank, const void* id);
+int ws_index_comm_destroy(ws_index* idx);
+int ws_allgather_merge(ws_index* idx, const uint32_t* ids, const float* dists, uint64_t nq, uint32_t k, uint32_t pad_id,
+                       uint32_t* out_ids, float* out_dists);
 
 /* ---- device plumbing for callers that keep batches resident in HBM (bench `value`) --- */
 int ws_index_device(const ws_index* idx, int* device);
@@ -204,6 +255,8 @@ int ws_index_reset_stats(ws_index* idx);
 int ws_index_launch_count(const ws_index* idx, uint64_t* out);
 /* tuning knobs: "emulate_query_id_skip" (beamSearch.h:128 `a == p.id()`, default 1),
  * "scan_chunk" (rows per brute-force task), "profile_kernels", "warp_tiers", "warp_hash",
+ * "prefilter_open_tail" (1: prefilter windows may include the arena's last point — every label shard but the last;
+ * the reference's r = n-1 rule, SURVEY.md §A-2, then applies to the data set's last point only),
  * "prefilter_direct" (one-launch prefilter kernel for batches of small windows: 0 never, 1 always,
  * 2 auto = host-sampled mean window <= scan_chunk),
  * "gemm_prefilter" (tensor-core prefilter: 0 never, 1 whenever eligible, 2 auto = host-sampled mean

@@ -128,7 +128,8 @@ static void add_variant(py::module_& m, const std::string& sfx) {
              return run(b.nq, qp.k, [&](unsigned int* ids, float* dists) { self.batch_search(b.queries, b.filters, b.nq, qp, ids, dists); });
            },
            "queries"_a, "filters"_a, "num_queries"_a, "query_params"_a)
-      .def("_arena_handle", [](Prefilter& self) { return (uintptr_t)self.arena().get(); });
+      .def("_arena_handle", [](Prefilter& self) { return (uintptr_t)self.arena().get(); })
+      .def("_group_handle", [](Prefilter& self) { return (uintptr_t)self.group(); });
 
   py::class_<Postfilter>(m, ("PostfilterVamanaIndex" + sfx).c_str())
       .def(py::init([](TArray<T> points, FArray filters, BuildParams bp) {
@@ -142,7 +143,8 @@ static void add_variant(py::module_& m, const std::string& sfx) {
              return run(b.nq, qp.k, [&](unsigned int* ids, float* dists) { self.batch_search(b.queries, b.filters, b.nq, qp, ids, dists); });
            },
            "queries"_a, "filters"_a, "num_queries"_a, "query_params"_a)
-      .def("_arena_handle", [](Postfilter& self) { return (uintptr_t)self.arena().get(); });
+      .def("_arena_handle", [](Postfilter& self) { return (uintptr_t)self.arena().get(); })
+      .def("_group_handle", [](Postfilter& self) { return (uintptr_t)self.group(); });
 
   py::class_<Tree>(m, ("VamanaRangeFilterTreeIndex" + sfx).c_str())
       .def(py::init([](TArray<T> points, FArray filter_values, int32_t cutoff, size_t split_factor, BuildParams bp) {
@@ -161,6 +163,7 @@ static void add_variant(py::module_& m, const std::string& sfx) {
            },
            "queries"_a, "filters"_a, "num_queries"_a, "query_method"_a, "query_params"_a)
       .def("_arena_handle", [](Tree& self) { return (uintptr_t)self.arena().get(); })
+      .def("_group_handle", [](Tree& self) { return (uintptr_t)self.group(); })
       .def("_bucket_offsets", [](Tree& self) { return self.bucket_offsets(); });
 
   // python_bindings.cpp:119-127 — the tree over PrefilterIndex sub-indices
@@ -181,6 +184,7 @@ static void add_variant(py::module_& m, const std::string& sfx) {
            },
            "queries"_a, "filters"_a, "num_queries"_a, "query_method"_a, "query_params"_a)
       .def("_arena_handle", [](PreTree& self) { return (uintptr_t)self.arena().get(); })
+      .def("_group_handle", [](PreTree& self) { return (uintptr_t)self.group(); })
       .def("_bucket_offsets", [](PreTree& self) { return self.bucket_offsets(); });
 
   py::class_<Super>(m, ("SuperOptimizedPostfilterTreeIndex" + sfx).c_str())
@@ -197,7 +201,8 @@ static void add_variant(py::module_& m, const std::string& sfx) {
              return run(b.nq, qp.k, [&](unsigned int* ids, float* dists) { self.batch_search(b.queries, b.filters, b.nq, qp, ids, dists); });
            },
            "queries"_a, "filters"_a, "num_queries"_a, "query_params"_a)
-      .def("_arena_handle", [](Super& self) { return (uintptr_t)self.arena().get(); });
+      .def("_arena_handle", [](Super& self) { return (uintptr_t)self.arena().get(); })
+      .def("_group_handle", [](Super& self) { return (uintptr_t)self.group(); });
 
 }
 

@@ -33,6 +33,7 @@
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/wsann.h"
@@ -88,6 +89,47 @@ inline int default_device() {
   return 0;
 }
 
+// Which GPUs an index uses.  The reference spreads a batch over the host's cores (PARLAY_NUM_THREADS,
+// run_our_method.py:131); here the environment names the devices:
+//   WSANN_DEVICE=3            one GPU (default: 0) — what a one-process-per-GPU launcher sets per rank
+//   WSANN_DEVICES=0,1,2,3     several GPUs behind ONE batch_search call ("all" = every visible device)
+//   WSANN_SHARD_MODE=label    with several devices: contiguous label ranges instead of replicas (data sets beyond one
+//                             GPU's HBM; PrefilterIndex and the range-filter trees — the other classes replicate)
+struct DevicePlan {
+  std::vector<int> devices;
+  bool label_sharded = false;
+};
+
+inline DevicePlan device_plan() {
+  DevicePlan p;
+  if (const char* e = std::getenv("WSANN_DEVICES")) {
+    std::string v(e);
+    if (v == "all") {
+      int c = 0;
+      ws_device_count(&c);
+      for (int i = 0; i < c; i++) p.devices.push_back(i);
+    } else {
+      size_t pos = 0;
+      while (pos < v.size()) {
+        size_t comma = v.find(',', pos);
+        if (comma == std::string::npos) comma = v.size();
+        if (comma > pos) p.devices.push_back(std::atoi(v.substr(pos, comma - pos).c_str()));
+        pos = comma + 1;
+      }
+    }
+  }
+  if (p.devices.empty()) p.devices.push_back(default_device());
+  if (const char* m = std::getenv("WSANN_SHARD_MODE")) p.label_sharded = std::string(m) == "label" && p.devices.size() > 1;
+  return p;
+}
+
+// contiguous, balanced [lo, hi) slice `i` of `n` items cut into `parts` (sizes differ by at most one)
+inline std::pair<size_t, size_t> shard_bounds(size_t n, size_t i, size_t parts) {
+  const size_t base = n / parts, rem = n % parts;
+  const size_t lo = i * base + std::min(i, rem);
+  return {lo, lo + base + (i < rem ? 1 : 0)};
+}
+
 // ---- reference graph cache -----------------------------------------------------------------
 struct GraphFile {
   int32_t n = 0, max_degree = 0;
@@ -129,7 +171,11 @@ class Arena {
   Arena() = default;
   Arena(const Arena&) = delete;
   Arena& operator=(const Arena&) = delete;
-  ~Arena() { if (idx_) ws_index_destroy(idx_); }
+  ~Arena() {
+    if (group_) ws_group_destroy(group_);
+    for (ws_index* r : replicas_) ws_index_destroy(r);
+    if (idx_) ws_index_destroy(idx_);
+  }
 
   // tree_utils.h:39-98: argsort labels, physically permute, decode[sorted] = original.
   // Equal labels are ordered by original id (the reference's unstable parlay sort leaves
@@ -148,6 +194,33 @@ class Arena {
     check(ws_index_create(device, metric, n, (uint32_t)dim, sorted.data(), labels_.data(), order.data(), 1, &idx_),
           "ws_index_create");
   }
+
+  // one label shard: points already label-sorted, decode = the shard's ORIGINAL ids
+  void init_presorted(const float* sorted_points, const float* sorted_labels, const uint32_t* decode, size_t n, size_t dim,
+                      int metric, int device) {
+    n_ = n; dim_ = dim;
+    labels_.assign(sorted_labels, sorted_labels + n);
+    check(ws_index_create(device, metric, n, (uint32_t)dim, sorted_points, sorted_labels, decode, 1, &idx_), "ws_index_create");
+  }
+
+  // Upload the staged geometry; with several devices, clone the finished arena onto the others (device to device)
+  // and put the replicas behind one group: a batch is then cut into one slice per GPU.
+  void finalize(const std::vector<int>& devices = {}) {
+    check(ws_index_finalize(idx_), "ws_index_finalize");
+    int own = -1;
+    ws_index_device(idx_, &own);
+    if (own < 0 || devices.size() < 2) return;
+    std::vector<ws_index*> members{idx_};
+    for (int d : devices) {
+      if (d == own) continue;
+      ws_index* r = nullptr;
+      check(ws_index_replicate(idx_, d, &r), "ws_index_replicate");
+      replicas_.push_back(r);
+      members.push_back(r);
+    }
+    if (members.size() > 1) check(ws_group_create(members.data(), (int)members.size(), WS_GROUP_REPLICATED, &group_), "ws_group_create");
+  }
+  ws_group* group() const { return group_; }
 
   // PostfilterVamanaIndex over the points as given (postfilter_vamana.h:91-124)
   void init_unsorted(const float* points, const float* labels, size_t n, size_t dim, int metric, int device) {
@@ -257,9 +330,74 @@ class Arena {
   }
 
   ws_index* idx_ = nullptr;
+  std::vector<ws_index*> replicas_;
+  ws_group* group_ = nullptr;
   size_t n_ = 0, dim_ = 0;
   std::vector<float> labels_;
   std::vector<Plan> plans_;
+};
+
+// ---- label-range shards ------------------------------------------------------
+// The label-sorted points are cut into one contiguous range per device; every shard is an Arena of its own (own
+// tree, own graphs, decode table = original ids), built on its device by its own host thread.  One group call
+// answers a batch on all shards and merges the partial rows (ws_group, WS_GROUP_LABEL_SHARDED).
+class LabelShards {
+ public:
+  LabelShards() = default;
+  LabelShards(const LabelShards&) = delete;
+  LabelShards& operator=(const LabelShards&) = delete;
+  ~LabelShards() { if (group_) ws_group_destroy(group_); }
+
+  // per_shard(arena, shard, count) stages geometry / graphs on an arena whose points are already uploaded
+  template <class F>
+  void init(const float* points, const float* labels, size_t n, size_t dim, int metric, const std::vector<int>& devices,
+            F&& per_shard) {
+    const size_t G = devices.size();
+    if (n < G) throw std::runtime_error("fewer points than label shards");
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return labels[a] < labels[b]; });
+    arenas_.resize(G);
+    std::vector<std::string> errors(G);
+    std::vector<std::thread> threads;
+    for (size_t s = 0; s < G; s++) {
+      arenas_[s] = std::make_unique<Arena>();
+      threads.emplace_back([&, s]() {
+        try {
+          auto [lo, hi] = shard_bounds(n, s, G);
+          const size_t cnt = hi - lo;
+          std::vector<float> pts(cnt * dim), lab(cnt);
+          for (size_t i = 0; i < cnt; i++) {
+            std::memcpy(&pts[i * dim], points + (size_t)order[lo + i] * dim, dim * sizeof(float));
+            lab[i] = labels[order[lo + i]];
+          }
+          Arena& a = *arenas_[s];
+          a.init_presorted(pts.data(), lab.data(), order.data() + lo, cnt, dim, metric, devices[s]);
+          per_shard(a, s, cnt);
+          a.finalize();
+          // the reference's r = n-1 rule (prefiltering.h:159-184) excludes the DATA SET's last point, not a shard's
+          if (s + 1 < G) check(ws_index_set_option(a.get(), "prefilter_open_tail", 1), "ws_index_set_option");
+        } catch (const std::exception& e) {
+          errors[s] = e.what();
+          if (errors[s].empty()) errors[s] = "unknown error";
+        }
+      });
+    }
+    for (std::thread& t : threads) t.join();
+    for (size_t s = 0; s < G; s++)
+      if (!errors[s].empty()) throw std::runtime_error("label shard " + std::to_string(s) + ": " + errors[s]);
+    std::vector<ws_index*> members;
+    for (auto& a : arenas_) members.push_back(a->get());
+    check(ws_group_create(members.data(), (int)members.size(), WS_GROUP_LABEL_SHARDED, &group_), "ws_group_create");
+  }
+  bool active() const { return group_ != nullptr; }
+  ws_group* group() const { return group_; }
+  Arena& shard(size_t i) { return *arenas_[i]; }
+  size_t size() const { return arenas_.size(); }
+
+ private:
+  std::vector<std::unique_ptr<Arena>> arenas_;
+  ws_group* group_ = nullptr;
 };
 
 struct BatchResult {
@@ -271,41 +409,55 @@ struct BatchResult {
 class PrefilterIndex {
  public:
   PrefilterIndex(const float* points, const float* labels, size_t n, size_t dim, int metric, const BuildParams&,
-                 int device = default_device()) {
-    arena_.init_sorted(points, labels, n, dim, metric, device);
-    check(ws_index_finalize(arena_.get()), "ws_index_finalize");
+                 const DevicePlan& plan = device_plan()) : dim_(dim) {
+    if (plan.label_sharded) {
+      shards_.init(points, labels, n, dim, metric, plan.devices, [](Arena&, size_t, size_t) {});
+      return;
+    }
+    arena_.init_sorted(points, labels, n, dim, metric, plan.devices[0]);
+    arena_.finalize(plan.devices);
   }
   // prefiltering.h:124-146
   void batch_search(const float* queries, const float* filters, uint64_t nq, const QueryParams& qp, uint32_t* ids,
                     float* dists) {
     if (qp.k < 1) throw std::runtime_error("k must be >= 1");
-    check(ws_prefilter_batch(arena_.get(), queries, filters, nq, (uint32_t)qp.k, ids, dists, 0), "ws_prefilter_batch");
+    ws_group* g = shards_.active() ? shards_.group() : arena_.group();
+    if (g) check(ws_group_prefilter_batch(g, queries, filters, nq, (uint32_t)qp.k, ids, dists), "ws_group_prefilter_batch");
+    else check(ws_prefilter_batch(arena_.get(), queries, filters, nq, (uint32_t)qp.k, ids, dists, 0), "ws_prefilter_batch");
   }
-  Arena& arena() { return arena_; }
-  size_t dim() const { return arena_.dim(); }
+  Arena& arena() { return shards_.active() ? shards_.shard(0) : arena_; }
+  ws_group* group() { return shards_.active() ? shards_.group() : arena_.group(); }
+  size_t dim() const { return dim_; }
 
  private:
   Arena arena_;
+  LabelShards shards_;
+  size_t dim_ = 0;
 };
 
 // ---- PostfilterVamanaIndex (src/postfilter_vamana.h) -------------------------------------------
 class PostfilterVamanaIndex {
  public:
   PostfilterVamanaIndex(const float* points, const float* labels, size_t n, size_t dim, int metric,
-                        const BuildParams& bp, int device = default_device()) {
-    arena_.init_unsorted(points, labels, n, dim, metric, device);
+                        const BuildParams& bp, const DevicePlan& plan = device_plan()) {
+    arena_.init_unsorted(points, labels, n, dim, metric, plan.devices[0]);
     float mn = *std::min_element(labels, labels + n), mx = *std::max_element(labels, labels + n);
     arena_.plan_graph(0, n, mn, mx);
     node_ = arena_.realize_graphs(bp)[0];
-    check(ws_index_finalize(arena_.get()), "ws_index_finalize");
+    arena_.finalize(plan.devices);
   }
   // postfilter_vamana.h:191-219 (missing slots: id 0xFFFFFFFF, FLT_MAX)
   void batch_search(const float* queries, const float* filters, uint64_t nq, const QueryParams& qp, uint32_t* ids,
                     float* dists) {
     ws_query_params c = qp.to_c();
-    check(ws_postfilter_batch(arena_.get(), node_, queries, filters, nq, &c, WS_PAD_MINUS1, ids, dists, 0),
-          "ws_postfilter_batch");
+    if (arena_.group())
+      check(ws_group_postfilter_batch(arena_.group(), node_, queries, filters, nq, &c, WS_PAD_MINUS1, ids, dists),
+            "ws_group_postfilter_batch");
+    else
+      check(ws_postfilter_batch(arena_.get(), node_, queries, filters, nq, &c, WS_PAD_MINUS1, ids, dists, 0),
+            "ws_postfilter_batch");
   }
+  ws_group* group() { return arena_.group(); }
   Arena& arena() { return arena_; }
   size_t dim() const { return arena_.dim(); }
 
@@ -323,14 +475,30 @@ class RangeFilterTreeBase {
  protected:
   RangeFilterTreeBase(const float* points, const float* labels, size_t n, size_t dim, int metric,
                       int32_t cutoff, size_t split_factor, const BuildParams& bp, bool vamana_nodes,
-                      int device) {
+                      const DevicePlan& plan) : dim_(dim) {
     if (split_factor < 2) throw std::runtime_error("split_factor must be at least 2");
-    arena_.init_sorted(points, labels, n, dim, metric, device);
-    const std::vector<float>& sl = arena_.labels();
-    // range_filter_tree.h:129-189
-    offsets_.push_back({0, (uint64_t)n});
-    while ((int64_t)offsets_.back()[1] > (int64_t)cutoff) {
-      const std::vector<uint64_t>& last = offsets_.back();
+    if (plan.label_sharded) {
+      // every shard is a B-WST of its own over its label range (the reference's tree cut at the shard boundaries)
+      std::vector<std::vector<std::vector<uint64_t>>> per(plan.devices.size());
+      shards_.init(points, labels, n, dim, metric, plan.devices, [&](Arena& a, size_t s, size_t cnt) {
+        per[s] = stage_tree(a, cnt, cutoff, split_factor, bp, vamana_nodes);
+      });
+      offsets_ = per[0];
+      return;
+    }
+    arena_.init_sorted(points, labels, n, dim, metric, plan.devices[0]);
+    offsets_ = stage_tree(arena_, n, cutoff, split_factor, bp, vamana_nodes);
+    arena_.finalize(plan.devices);
+  }
+
+  // range_filter_tree.h:129-189 over the arena's n points: bucket offsets per row, one graph per bucket
+  static std::vector<std::vector<uint64_t>> stage_tree(Arena& arena, size_t n, int32_t cutoff, size_t split_factor,
+                                                       const BuildParams& bp, bool vamana_nodes) {
+    std::vector<std::vector<uint64_t>> offsets;
+    const std::vector<float>& sl = arena.labels();
+    offsets.push_back({0, (uint64_t)n});
+    while ((int64_t)offsets.back()[1] > (int64_t)cutoff) {
+      const std::vector<uint64_t>& last = offsets.back();
       size_t last_nb = last.size() - 1;
       std::vector<uint64_t> next(last_nb * split_factor + 1);
       next.back() = n;
@@ -346,24 +514,24 @@ class RangeFilterTreeBase {
       }
       for (size_t i = 0; i + 1 < next.size(); i++)
         if (next[i + 1] <= next[i]) throw std::runtime_error("cutoff/split_factor produce an empty bucket");
-      offsets_.push_back(std::move(next));
+      offsets.push_back(std::move(next));
     }
     std::vector<uint32_t> row_nb;
     std::vector<uint64_t> off_flat;
-    for (auto& row : offsets_) {
+    for (auto& row : offsets) {
       row_nb.push_back((uint32_t)row.size() - 1);
       off_flat.insert(off_flat.end(), row.begin(), row.end());
       if (vamana_nodes)
         for (size_t b = 0; b + 1 < row.size(); b++)
-          arena_.plan_graph(row[b], row[b + 1] - row[b], sl[row[b]], sl[row[b + 1] - 1]);
+          arena.plan_graph(row[b], row[b + 1] - row[b], sl[row[b]], sl[row[b + 1] - 1]);
     }
     // no node handles = PrefilterIndex sub-indices: a bucket query is a scan of the bucket's slice
     std::vector<int32_t> nodes_flat;
-    if (vamana_nodes) nodes_flat = arena_.realize_graphs(bp);
-    check(ws_index_set_wst(arena_.get(), (uint32_t)offsets_.size(), (uint32_t)split_factor, cutoff, row_nb.data(),
+    if (vamana_nodes) nodes_flat = arena.realize_graphs(bp);
+    check(ws_index_set_wst(arena.get(), (uint32_t)offsets.size(), (uint32_t)split_factor, cutoff, row_nb.data(),
                            off_flat.data(), vamana_nodes ? nodes_flat.data() : nullptr),
           "ws_index_set_wst");
-    check(ws_index_finalize(arena_.get()), "ws_index_finalize");
+    return offsets;
   }
 
  public:
@@ -377,15 +545,20 @@ class RangeFilterTreeBase {
   void batch_search(const float* queries, const float* filters, uint64_t nq, const std::string& query_method,
                     const QueryParams& qp, uint32_t* ids, float* dists) {
     ws_query_params c = qp.to_c();
-    check(ws_tree_batch(arena_.get(), method_from_string(query_method), queries, filters, nq, &c, ids, dists, 0),
-          "ws_tree_batch");
+    ws_group* g = group();
+    if (g) check(ws_group_tree_batch(g, method_from_string(query_method), queries, filters, nq, &c, ids, dists), "ws_group_tree_batch");
+    else check(ws_tree_batch(arena_.get(), method_from_string(query_method), queries, filters, nq, &c, ids, dists, 0), "ws_tree_batch");
   }
-  Arena& arena() { return arena_; }
-  size_t dim() const { return arena_.dim(); }
+  Arena& arena() { return shards_.active() ? shards_.shard(0) : arena_; }
+  ws_group* group() { return shards_.active() ? shards_.group() : arena_.group(); }
+  size_t dim() const { return dim_; }
+  // bucket offsets of the tree (of shard 0's tree when label-sharded)
   const std::vector<std::vector<uint64_t>>& bucket_offsets() const { return offsets_; }
 
  private:
   Arena arena_;
+  LabelShards shards_;
+  size_t dim_ = 0;
   std::vector<std::vector<uint64_t>> offsets_;
 };
 
@@ -394,16 +567,16 @@ class VamanaRangeFilterTreeIndex : public RangeFilterTreeBase {
  public:
   VamanaRangeFilterTreeIndex(const float* points, const float* labels, size_t n, size_t dim, int metric,
                              int32_t cutoff, size_t split_factor, const BuildParams& bp,
-                             int device = default_device())
-      : RangeFilterTreeBase(points, labels, n, dim, metric, cutoff, split_factor, bp, true, device) {}
+                             const DevicePlan& plan = device_plan())
+      : RangeFilterTreeBase(points, labels, n, dim, metric, cutoff, split_factor, bp, true, plan) {}
 };
 
 // RangeFilterTreeIndex<T, Point> = PrefilterIndex sub-indices (python_bindings.cpp:119-127)
 class RangeFilterTreeIndex : public RangeFilterTreeBase {
  public:
   RangeFilterTreeIndex(const float* points, const float* labels, size_t n, size_t dim, int metric,
-                       int32_t cutoff, size_t split_factor, const BuildParams& bp, int device = default_device())
-      : RangeFilterTreeBase(points, labels, n, dim, metric, cutoff, split_factor, bp, false, device) {}
+                       int32_t cutoff, size_t split_factor, const BuildParams& bp, const DevicePlan& plan = device_plan())
+      : RangeFilterTreeBase(points, labels, n, dim, metric, cutoff, split_factor, bp, false, plan) {}
 };
 
 // ---- SuperOptimizedPostfilterTree (src/super_optimized_postfilter_tree.h) ------------------------
@@ -411,11 +584,11 @@ class SuperOptimizedPostfilterTree {
  public:
   SuperOptimizedPostfilterTree(const float* points, const float* labels, size_t n, size_t dim, int metric,
                                int32_t cutoff, float split_factor, float shift_factor, const BuildParams& bp,
-                               int device = default_device()) {
+                               const DevicePlan& plan = device_plan()) {
     // super_optimized_postfilter_tree.h:127-132
     if (split_factor <= 1) throw std::runtime_error("split_factor must be greater than 1");
     if (shift_factor >= 1 || shift_factor <= 0) throw std::runtime_error("shift_factor must be between 0 and 1");
-    arena_.init_sorted(points, labels, n, dim, metric, device);
+    arena_.init_sorted(points, labels, n, dim, metric, plan.devices[0]);
     const std::vector<float>& sl = arena_.labels();
     std::vector<uint64_t> sizes{(uint64_t)n}, shifts{0};
     std::vector<uint32_t> row_nb{1};
@@ -439,16 +612,19 @@ class SuperOptimizedPostfilterTree {
     check(ws_index_set_super(arena_.get(), (uint32_t)sizes.size(), cutoff, sizes.data(), shifts.data(), row_nb.data(),
                              nodes_flat.data()),
           "ws_index_set_super");
-    check(ws_index_finalize(arena_.get()), "ws_index_finalize");
+    arena_.finalize(plan.devices);
     sizes_ = sizes; shifts_ = shifts;
   }
   // super_optimized_postfilter_tree.h:60-87
   void batch_search(const float* queries, const float* filters, uint64_t nq, const QueryParams& qp, uint32_t* ids,
                     float* dists) {
     ws_query_params c = qp.to_c();
-    check(ws_tree_batch(arena_.get(), WS_METHOD_SUPER_POSTFILTER, queries, filters, nq, &c, ids, dists, 0),
-          "ws_tree_batch");
+    if (arena_.group())
+      check(ws_group_tree_batch(arena_.group(), WS_METHOD_SUPER_POSTFILTER, queries, filters, nq, &c, ids, dists), "ws_group_tree_batch");
+    else
+      check(ws_tree_batch(arena_.get(), WS_METHOD_SUPER_POSTFILTER, queries, filters, nq, &c, ids, dists, 0), "ws_tree_batch");
   }
+  ws_group* group() { return arena_.group(); }
   Arena& arena() { return arena_; }
   size_t dim() const { return arena_.dim(); }
   const std::vector<uint64_t>& bucket_sizes() const { return sizes_; }

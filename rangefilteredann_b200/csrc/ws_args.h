@@ -127,11 +127,19 @@ struct WsPrefilterDirectArgs {
   uint32_t nq;
 };
 
+#define WS_MAX_PARTS 16
 struct WsMergePartsArgs {
-  const uint32_t* ids;    // [parts][nq][k]
-  const float* dists;     // [parts][nq][k]
-  uint32_t parts, k, nq, pad_id;
-  uint32_t* out_ids;      // [nq][k]
+  // either one gathered buffer [parts][nq_total][k] (the all-gather layout) ...
+  const uint32_t* ids;
+  const float* dists;
+  // ... or, with ids == nullptr, one [nq_total][k] buffer per part, each possibly in a PEER device's memory (the
+  // kernel then gathers over NVLink with plain loads while it merges: no staging copy, no collective launch)
+  const uint32_t* part_ids[WS_MAX_PARTS];
+  const float* part_dists[WS_MAX_PARTS];
+  uint32_t parts, k, pad_id;
+  uint32_t nq_total;      // rows per part
+  uint32_t q0, nq;        // this launch merges rows [q0, q0 + nq)
+  uint32_t* out_ids;      // [nq_total][k]; rows [q0, q0 + nq) are written
   float* out_dists;
 };
 

@@ -44,6 +44,9 @@ struct WsTask {            // 32 bytes
 struct WsGeom {
   const float* labels;     // [n] sorted
   uint64_t n;
+  uint64_t pf_n;           // the `n` PrefilterIndex::query_knn's bounds use: n (the reference's r = n-1 rule, the last
+                           // point is never inside a window) or n+1 (plain lower bound — every label shard but the
+                           // last one, whose last point is NOT the data set's last point)
   // ---- B-WST (range_filter_tree.h:129-189)
   uint32_t wst_rows;
   uint32_t split;

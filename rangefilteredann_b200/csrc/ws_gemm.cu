@@ -7,26 +7,30 @@
 //
 //   plan    ws_gemm_plan_kernel     window -> [a,b) (prefiltering.h:159-184), sort by a, groups,
 //                                   work items (group x chunk of the label axis)
-//   pack    ws_gemm_pack_kernel     sorted query matrix, pre-scaled (-2q for L2, -q for MIPS),
-//                                   rounded to tf32; per-query error slack
-//   GEMM    ws_gemm_topk_kernel     tcgen05.mma kind::tf32, 128x128 fp32 accumulators in TMEM,
-//                                   operands staged by TMA (128B swizzle) STRAIGHT FROM THE fp32
-//                                   ARENA (no second copy of the vectors); the epilogue reads the
-//                                   accumulators with tcgen05.ld, adds |x|^2, and keeps per query
-//                                   (one TMEM lane = one query) every point whose approximate
-//                                   score is below (k-th best approximate score + slack)
+//   pack    ws_gemm_pack_kernel     sorted query matrix, pre-scaled (-2q for L2, -q for MIPS), as fp16
+//                                   with a per-query power-of-two scale; per-query error slack
+//   GEMM    ws_gemm_topk_kernel     tcgen05.mma kind::f16 (fp16 x fp16 -> fp32), 128x128 accumulators in
+//                                   TMEM, points staged by TMA (128B swizzle) from an fp16 MIRROR of the
+//                                   arena (half(x * 2^e): same 11-bit significand as tf32, half the bytes,
+//                                   twice the tensor rate; the fp32 arena stays the source of truth); the
+//                                   epilogue reads the accumulators with tcgen05.ld, rescales, adds |x|^2,
+//                                   and keeps per query (one TMEM lane = one query) every point whose
+//                                   approximate score is below (k-th best approximate score + slack)
 //   re-rank ws_gemm_rerank_kernel   exact fp32 distances of the survivors with the scan kernel's
 //                                   arithmetic, top-k, decode, pad  (prefiltering.h:196-201)
 //
-// Exactness.  score~(q,x) = |x|^2 - 2 q.x (L2) or -q.x (MIPS) computed with tf32 operands
-// differs from the fp32 value by at most E = c * |q| * max|x| (c: two tf32 roundings per
-// product, Cauchy-Schwarz over the row; see ws_gemm_pack_kernel).  A point is dropped only when
+// Exactness.  score~(q,x) = |x|^2 - 2 q.x (L2) or -q.x (MIPS) computed with fp16 operands
+// differs from the fp32 value by at most E = c * |q| * max|x| + a (c: two roundings to 11-bit
+// significands per product, Cauchy-Schwarz over the row, fp32 accumulation; a: absolute term for
+// the norm table and tiny queries; see ws_gemm_pack_kernel).  A point is dropped only when
 // score~ >= kth~ + 2E, which implies its true distance is >= the true distance of k points that
 // were kept — so the re-ranked top-k is the exact fp32 top-k of the scan kernel, bit for bit,
 // without a verification pass.  If a query's survivor buffer overflows (degenerate data: very
 // many points inside the slack) the re-rank warp falls back to the exact streaming scan of the
 // window (ws_scan_task), still on the device.
 #include "ws_gemm.h"
+
+#include <cuda_fp16.h>
 
 // The shared device code (scan task, sorts, result writers) is header-only; this translation unit
 // gets its own internal-linkage copy so the kernels it does not use never clash at link time.
@@ -124,42 +128,29 @@ __device__ __forceinline__ void wsg_tmem_alloc(uint32_t* smem_slot, uint32_t col
 __device__ __forceinline__ void wsg_tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, tf32 operands, fp32 accumulate; one thread issues
-__device__ __forceinline__ void wsg_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem]^T, fp16 operands, fp32 accumulate; one thread issues.  The A operand lives in
+// TMEM (lane = row, one 32-bit column per PAIR of fp16 elements: K = 16 per instruction = 8 columns): only the point
+// block is read from shared memory — an SS-mode 128x128 MMA needs 8 KB of shared-memory operands per 64 tensor
+// cycles, twice what the operand path delivers (measured in round 1 with tf32: 140 cycles per MMA, 45 % tensor
+// utilisation with nothing else running).
+__device__ __forceinline__ void wsg_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Same with the A operand in TMEM (lane = row, one 32-bit column per tf32 element): only the
-// point block is read from shared memory — an SS-mode 128x128x8 tf32 MMA needs 8 KB of shared
-// memory operands per 64 tensor cycles, twice what the operand path delivers (measured: 140
-// cycles per MMA, 45 % tensor utilisation with nothing else running).
-__device__ __forceinline__ void wsg_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  const uint32_t z = 0;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(z), "r"(z), "r"(z), "r"(z)
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // 32 consecutive 32-bit columns of this thread's TMEM lane <- registers
-__device__ __forceinline__ void wsg_tmem_st32(uint32_t taddr, const float (&v)[32]) {
+__device__ __forceinline__ void wsg_tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
       "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
-      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
-      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
-      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
-      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
@@ -186,7 +177,7 @@ __device__ __forceinline__ void wsg_tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // K-major operand block in shared memory: 128 rows x 128 B, 128-byte swizzle (what the TMA box
-// {32 fp32, 128 rows} with CU_TENSOR_MAP_SWIZZLE_128B writes).  Descriptor fields
+// {64 fp16, 128 rows} with CU_TENSOR_MAP_SWIZZLE_128B writes).  Descriptor fields
 // (cute::UMMA::SmemDescriptor): start address >> 4 [0,14), leading byte offset >> 4 [16,30)
 // (unused for swizzled K-major), stride byte offset >> 4 [32,46) = 1024 B between 8-row
 // groups, version 1 [46,48), layout SWIZZLE_128B = 2 [61,64).
@@ -198,16 +189,10 @@ __device__ __forceinline__ uint64_t wsg_make_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 [4,6), a/b format TF32 = 2
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 [4,6), a/b format F16 = 0
 // [7,10)/[10,13), both K-major, N >> 3 [17,23), M >> 4 [24,29)
 __device__ __forceinline__ uint32_t wsg_make_idesc() {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(WSG_TILE_N >> 3) << 17) | ((uint32_t)(WSG_TILE_M >> 4) << 24);
-}
-
-__device__ __forceinline__ float wsg_to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(WSG_TILE_N >> 3) << 17) | ((uint32_t)(WSG_TILE_M >> 4) << 24);
 }
 
 // ---- one-time per index: |x|^2 and max |x| -------------------------------------------------
@@ -216,6 +201,7 @@ __global__ void __launch_bounds__(256) ws_gemm_norm_kernel(WsGemmNormArgs A) {
   const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
   float mx = 0.f;
+  uint32_t ma = 0;  // bits of the largest |x_i| (as unsigned: NaN / inf order above every finite value)
   for (uint64_t r = warp; r < A.npad; r += nwarps) {
     if (r >= A.n) {
       if (lane == 0) A.norms[r] = __int_as_float(0x7f800000);
@@ -226,13 +212,31 @@ __global__ void __launch_bounds__(256) ws_gemm_norm_kernel(WsGemmNormArgs A) {
     for (uint32_t c = lane; c < A.dpad; c += 32) {
       const float v = row[c];
       acc = fmaf(v, v, acc);
+      ma = max(ma, __float_as_uint(v) & 0x7FFFFFFFu);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) A.norms[r] = A.metric == 0 ? acc : 0.f;
     mx = fmaxf(mx, acc);
   }
-  if (lane == 0) atomicMax(A.max_sq, __float_as_uint(mx));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ma = max(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+  if (lane == 0) {
+    atomicMax(A.max_sq, __float_as_uint(mx));
+    atomicMax(A.max_abs, ma);
+  }
+}
+
+__global__ void __launch_bounds__(256) ws_gemm_cvt_kernel(WsGemmCvtArgs A) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
+  for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < A.count; i += stride) {  // count % 16 == 0
+    const float4 v = *reinterpret_cast<const float4*>(A.vecs + i);
+    const __half2 a = __floats2half2_rn(v.x * A.scale, v.y * A.scale), b = __floats2half2_rn(v.z * A.scale, v.w * A.scale);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&a);
+    o.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(A.out + i) = o;
+  }
 }
 
 // ---- plan ------------------------------------------------------------------------------------
@@ -251,8 +255,8 @@ __device__ __forceinline__ uint32_t wsg_bound(const float* labels, uint64_t n, f
 __global__ void __launch_bounds__(128) ws_gemm_bounds_kernel(WsGemmPlanArgs A) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.nq) return;
-  uint32_t a = wsg_bound(A.labels, A.n, A.windows[2 * (size_t)i]);
-  uint32_t b = wsg_bound(A.labels, A.n, A.windows[2 * (size_t)i + 1]);
+  uint32_t a = wsg_bound(A.labels, A.n_bound, A.windows[2 * (size_t)i]);
+  uint32_t b = wsg_bound(A.labels, A.n_bound, A.windows[2 * (size_t)i + 1]);
   if (b <= a) { a = 0; b = 0; }
   A.qa[i] = a; A.qb[i] = b;
 }
@@ -397,26 +401,52 @@ __global__ void __launch_bounds__(256) ws_gemm_pack_kernel(WsGemmPackArgs A) {
   const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= A.rows_pad) return;
   const uint32_t q = A.perm[row];
-  float* out = A.qpack + (size_t)row * A.dpad;
-  float acc = 0.f;
+  uint16_t* out = A.qpack + (size_t)row * A.kcols;
   const float scale = A.metric == 0 ? -2.f : -1.f;
-  for (uint32_t c = lane; c < A.dpad; c += 32) {
-    float v = 0.f;
-    if (q != 0xFFFFFFFFu && c < A.dim) v = A.queries[(size_t)q * A.dim + c];
-    acc = fmaf(v, v, acc);
-    out[c] = wsg_to_tf32(scale * v);
-  }
+  // pass 1: |q|^2 and the largest |scale * q_i|
+  float acc = 0.f, mab = 0.f;
+  if (q != 0xFFFFFFFFu)
+    for (uint32_t c = lane; c < A.dim; c += 32) {
+      const float v = A.queries[(size_t)q * A.dim + c];
+      acc = fmaf(v, v, acc);
+      mab = fmaxf(mab, fabsf(scale * v));
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    mab = fmaxf(mab, __shfl_xor_sync(0xffffffffu, mab, o));
+  }
+  // per-query power-of-two scale: the largest component lands in [2^13, 2^14) (fp16 overflows at 2^16)
+  int qe = 0;
+  const bool sane = acc < 3.0e38f && mab < 3.0e38f;  // false for NaN / inf
+  if (sane && mab > 0.f) {
+    int ex;
+    frexpf(mab, &ex);  // mab = m * 2^ex, m in [0.5, 1)
+    qe = 14 - ex;
+  }
+  const bool ok = sane && qe >= -60 && qe <= 60;
+  if (!ok) qe = 0;
+  const float qs = exp2f((float)qe);
+  for (uint32_t c = lane; c < A.kcols; c += 32) {
+    float v = 0.f;
+    if (ok && q != 0xFFFFFFFFu && c < A.dim) v = scale * A.queries[(size_t)q * A.dim + c] * qs;
+    out[c] = __half_as_ushort(__float2half_rn(v));
+  }
   if (lane == 0) {
-    // per product q_i x_i: q rounded to nearest tf32 (2^-11), x truncated or rounded by the
-    // tensor core (2^-10)  ->  |err| <= 1.5 * 2^-10 * |q_i x_i| (1 + 2^-11); summed with
-    // Cauchy-Schwarz and multiplied by |scale|; 5 % head room covers the fp32 accumulation
-    // (128 * 2^-24) and the rounding of |x|^2.
-    const float xmax = sqrtf(__uint_as_float(*A.max_sq));
-    const float e = fabsf(scale) * 1.5f * 0.0009765625f * 1.05f * sqrtf(acc) * xmax;
-    A.slack[row] = 2.f * e;
-    A.qnorm[row] = acc;
+    // Per product (scale q_i)(x_i): both factors rounded to nearest fp16 (11-bit significands, 2^-11 each; the scaled
+    // values sit far above the subnormal range)  ->  |err| <= (2^-10 + 2^-22) |scale q_i x_i|, summed with
+    // Cauchy-Schwarz; the products are exact in fp32 and accumulated in fp32 over dpad terms (dpad * 2^-21 covers an
+    // accumulator that truncates).  The absolute term covers the fp32 rounding of |x|^2 (summed in another order than
+    // the exact distance), of the exact distance itself, and queries so small that the relative term vanishes.
+    const float xmax2 = __uint_as_float(*A.max_sq);
+    const float xmax = sqrtf(xmax2);
+    const float rel = 0.0009765625f * 1.02f + (float)A.dpad * 4.76837158e-7f;
+    const float e = fabsf(scale) * sqrtf(acc) * xmax * rel + (float)A.dpad * 2.38418579e-7f * (acc + xmax2);
+    // a query this engine cannot scale (NaN, inf, absurd magnitude): infinite slack keeps every point, the survivor
+    // list overflows and the re-rank warp answers with the exact streaming scan
+    A.slack[row] = ok ? 2.f * e : __int_as_float(0x7f800000);
+    A.qnorm[row] = ok ? acc : 0.f;
+    A.rscale[row] = exp2f((float)(-(A.x_exp + qe)));
   }
 }
 
@@ -458,7 +488,7 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32) ws_gemm_seed_kernel(WsG
     const uint64_t kth = ws_shfl_idx_u64(kk < 32 ? k0 : k1, kk & 31);
     const float D = ws_unord((uint32_t)(kth >> 32));
     const float e = 0.5f * A.slack[row];
-    out = METRIC == 0 ? D - A.qnorm[row] + e : D + e;
+    out = METRIC == 0 ? D - A.qnorm[row] + e : D + e;  // +inf when the slack is (unscalable query)
   }
   if (lane == 0) A.thr0[row] = ws_ord(out);
 }
@@ -557,7 +587,7 @@ __device__ __forceinline__ bool wsg_flush(float (&tk)[WSG_KTOP], WsGemmSmem* S, 
 }
 
 __global__ void __launch_bounds__(WSG_THREADS, 1)
-ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, WsGemmArgs A) {
+ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmB, WsGemmArgs A) {
   extern __shared__ unsigned char wsg_smem_raw[];
   // operand blocks need 1024-byte alignment (128B swizzle atoms)
   unsigned char* base = wsg_smem_raw + ((1024u - (wsg_smem_u32(wsg_smem_raw) & 1023u)) & 1023u);
@@ -572,7 +602,6 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     wsg_mbar_init(&S->a_full, WSG_EPI_WARPS); wsg_mbar_init(&S->a_empty, 1);
     for (int i = 0; i < WSG_ACC_STAGES; i++) { wsg_mbar_init(&S->acc_full[i], 1); wsg_mbar_init(&S->acc_empty[i], WSG_EPI_WARPS); }
     wsg_fence_barrier_init();
-    wsg_prefetch_tmap(&tmA);
     wsg_prefetch_tmap(&tmB);
   }
   if (warp == 1) wsg_tmem_alloc(&S->tmem_base, 512);
@@ -583,10 +612,11 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   wsg_tc_fence_after();
   const uint32_t tmem_base = S->tmem_base;
 
-  // A pipeline stage holds one whole tile of points (nkb blocks of 16 KB): one barrier round trip and one
-  // pair of tcgen05.commit per 4*nkb MMAs.  (With a stage per 32-column block the tensor pipe drained at
-  // every commit: 1830 cycles per tile instead of the 1024 its 16 MMAs need.)
-  const uint32_t nstages = WSG_B_STAGES / nkb;
+  // A pipeline stage holds kbps blocks of 16 KB — a whole tile of points up to 256 columns, half a tile above
+  // (a stage is at most 64 KB): one barrier round trip and one tcgen05.commit per 4*kbps MMAs.  (With a stage
+  // per block the tensor pipe drained at every commit: 1830 cycles per tile instead of the 1024 its MMAs needed.)
+  const uint32_t kbps = A.kbps, spt = nkb / kbps;  // blocks per stage, stages per tile
+  const uint32_t nstages = WSG_B_STAGES / kbps;
   if (warp == 0) {
     // ===== TMA producer (whole warp walks the loop, one elected lane issues) =====
     uint32_t stage = 0, phase = 0;
@@ -609,18 +639,21 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t rot = wsg_rotation(item);
       for (uint32_t t = 0; t < item.ntiles; t++) {
         const int p = (int)(item.p0 + wsg_tile(t, rot, item.ntiles) * WSG_TILE_N);
-        wsg_mbar_wait(&S->empty[stage], phase ^ 1);
-        if (wsg_elect_one()) {
-          if (A.dbg & 2) {
-            wsg_mbar_arrive(&S->full[stage]);
-          } else {
-            wsg_mbar_expect_tx(&S->full[stage], nkb * WSG_KBLK_BYTES);
-            for (uint32_t kb = 0; kb < nkb; kb++)
-              wsg_tma_load_2d(sB + (stage * nkb + kb) * WSG_KBLK_BYTES, &tmB, &S->full[stage], (int)(kb * WSG_KBLK), p);
+        for (uint32_t sp = 0; sp < spt; sp++) {
+          wsg_mbar_wait(&S->empty[stage], phase ^ 1);
+          if (wsg_elect_one()) {
+            if (A.dbg & 2) {
+              wsg_mbar_arrive(&S->full[stage]);
+            } else {
+              // blocks past the row's last column (dpad rounded up to the block count) are zero-filled by the TMA unit
+              wsg_mbar_expect_tx(&S->full[stage], kbps * WSG_KBLK_BYTES);
+              for (uint32_t kb = 0; kb < kbps; kb++)
+                wsg_tma_load_2d(sB + (stage * kbps + kb) * WSG_KBLK_BYTES, &tmB, &S->full[stage], (int)((sp * kbps + kb) * WSG_KBLK), p);
+            }
           }
+          __syncwarp();
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -631,8 +664,9 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // therefore taken in the MIDDLE of tile t's MMAs, and descriptors are plain adds.
     const uint32_t idesc = wsg_make_idesc();
     const uint64_t desc0 = wsg_make_desc(wsg_smem_u32(sB));
-    const uint32_t tmem_acc0 = tmem_base + WSG_TILE_N;  // columns [0,128) hold the queries
-    const uint32_t nmma = nkb * 4, half = nmma / 2;
+    const uint32_t tmem_acc0 = tmem_base + A.acc_col0;  // the columns below hold the queries
+    const uint32_t nacc = A.nacc;
+    const uint32_t nmma = kbps * 4, half = nmma / 2;    // one MMA = 16 fp16 columns = 32 B of every row, 8 TMEM columns of A
     uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
     for (uint32_t iseq = 0;; iseq++) {
       const uint32_t it = wsg_take_item(S, iseq);
@@ -645,28 +679,32 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       wsg_tc_fence_after();
       for (uint32_t t = 0; t < ntiles; t++) {
         const uint32_t d_tmem = tmem_acc0 + acc * WSG_TILE_N;
-        const uint64_t db = desc0 + (uint64_t)(stage * nkb) * (WSG_KBLK_BYTES >> 4);
-        if (wsg_elect_one()) {
-          for (uint32_t i = 0; i < half; i++)  // MMA i: 32-column block i/4, 8-column step i%4
-            wsg_mma_tf32_ts(d_tmem, tmem_base + i * 8, db + (uint64_t)((i >> 2) * (WSG_KBLK_BYTES >> 4) + (i & 3) * 2), idesc, i != 0 ? 1u : 0u);
+        for (uint32_t sp = 0; sp < spt; sp++) {
+          const uint64_t db = desc0 + (uint64_t)(stage * kbps) * (WSG_KBLK_BYTES >> 4);
+          const uint32_t ta = tmem_base + sp * kbps * 32;  // this stage's 32 query columns per block
+          if (wsg_elect_one()) {
+            for (uint32_t i = 0; i < half; i++)  // MMA i: block i/4 of the stage, 16-column step i%4
+              wsg_mma_f16_ts(d_tmem, ta + i * 8, db + (uint64_t)((i >> 2) * (WSG_KBLK_BYTES >> 4) + (i & 3) * 2), idesc, (sp | i) != 0 ? 1u : 0u);
+          }
+          __syncwarp();
+          const bool last_sp = sp + 1 == spt;
+          uint32_t nstage = stage + 1, nphase = phase, nxacc = acc, nxacc_phase = acc_phase;
+          if (nstage == nstages) { nstage = 0; nphase ^= 1; }
+          if (last_sp && ++nxacc == nacc) { nxacc = 0; nxacc_phase ^= 1; }
+          if (!(last_sp && t + 1 == ntiles)) {  // next stage's operands (and accumulator), while this stage's MMAs are queued
+            if (last_sp) wsg_mbar_wait(&S->acc_empty[nxacc], nxacc_phase ^ 1);
+            wsg_mbar_wait(&S->full[nstage], nphase);
+            wsg_tc_fence_after();
+          }
+          if (wsg_elect_one()) {
+            for (uint32_t i = half; i < nmma; i++)
+              wsg_mma_f16_ts(d_tmem, ta + i * 8, db + (uint64_t)((i >> 2) * (WSG_KBLK_BYTES >> 4) + (i & 3) * 2), idesc, 1u);
+            wsg_mma_commit(&S->empty[stage]);
+            if (last_sp) wsg_mma_commit(&S->acc_full[acc]);
+          }
+          __syncwarp();
+          stage = nstage; phase = nphase; acc = nxacc; acc_phase = nxacc_phase;
         }
-        __syncwarp();
-        uint32_t nstage = stage + 1, nphase = phase, nacc = acc + 1, nacc_phase = acc_phase;
-        if (nstage == nstages) { nstage = 0; nphase ^= 1; }
-        if (nacc == WSG_ACC_STAGES) { nacc = 0; nacc_phase ^= 1; }
-        if (t + 1 < ntiles) {  // next tile's operands and accumulator, while this tile's MMAs are queued
-          wsg_mbar_wait(&S->acc_empty[nacc], nacc_phase ^ 1);
-          wsg_mbar_wait(&S->full[nstage], nphase);
-          wsg_tc_fence_after();
-        }
-        if (wsg_elect_one()) {
-          for (uint32_t i = half; i < nmma; i++)
-            wsg_mma_tf32_ts(d_tmem, tmem_base + i * 8, db + (uint64_t)((i >> 2) * (WSG_KBLK_BYTES >> 4) + (i & 3) * 2), idesc, 1u);
-          wsg_mma_commit(&S->empty[stage]);
-          wsg_mma_commit(&S->acc_full[acc]);
-        }
-        __syncwarp();
-        stage = nstage; phase = nphase; acc = nacc; acc_phase = nacc_phase;
       }
       if (wsg_elect_one()) wsg_mma_commit(&S->a_empty);
       __syncwarp();
@@ -692,21 +730,24 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t rot = wsg_rotation(item);
       // the query's window clipped to this item's slice of the label axis (ranks < 2^31)
       const int wlo = (int)max(A.row_a[row], item.p0), whi = (int)min(A.row_b[row], item.pend);
+      const float rs = A.rscale[row];  // accumulator units -> score units (a power of two)
       {
         // the group's queries -> TMEM columns [32*chunk, 32*chunk+32) of lanes [32*quarter, +32), once the
         // previous item's MMAs have drained
         wsg_mbar_wait(&S->a_empty, a_phase ^ 1);
         a_phase ^= 1;
         wsg_tc_fence_after();
-        float qv[32];
-        const float* qrow = A.qpack + (size_t)row * A.dpad + chunk * 32;
+        // block c of the packed row = 64 fp16 = 32 TMEM columns of this lane (two elements per column)
+        for (uint32_t c = (uint32_t)chunk; c < nkb; c += 4) {
+          uint32_t qv[32];
+          const uint4* qrow = reinterpret_cast<const uint4*>(A.qpack + (size_t)row * A.kcols) + c * 8;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if ((uint32_t)(chunk * 32 + 4 * j) < A.dpad) x = __ldg(reinterpret_cast<const float4*>(qrow) + j);
-          qv[4 * j] = x.x; qv[4 * j + 1] = x.y; qv[4 * j + 2] = x.z; qv[4 * j + 3] = x.w;
+          for (int j = 0; j < 8; j++) {
+            const uint4 x = __ldg(qrow + j);
+            qv[4 * j] = x.x; qv[4 * j + 1] = x.y; qv[4 * j + 2] = x.z; qv[4 * j + 3] = x.w;
+          }
+          wsg_tmem_st32(tmem_base + lane_addr + c * 32, qv);
         }
-        wsg_tmem_st32(tmem_base + lane_addr + chunk * 32, qv);
         wsg_tc_fence_before();
         __syncwarp();
         if (lane == 0) wsg_mbar_arrive(&S->a_full);
@@ -727,7 +768,7 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (__any_sync(0xffffffffu, hi > lo) && !(A.dbg & 1)) {
           const bool whole = __all_sync(0xffffffffu, lo == 0 && hi == 32);
           float s[32];
-          wsg_tmem_ld32(tmem_base + lane_addr + WSG_TILE_N + acc * WSG_TILE_N + chunk * 32, s);
+          wsg_tmem_ld32(tmem_base + lane_addr + A.acc_col0 + acc * WSG_TILE_N + chunk * 32, s);
           // the scores are in registers: hand the accumulator stage back before filtering them
           wsg_tc_fence_before();
           __syncwarp();
@@ -736,7 +777,8 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 8; j++) {
             const float4 nv = nr[j];
-            s[4 * j + 0] += nv.x; s[4 * j + 1] += nv.y; s[4 * j + 2] += nv.z; s[4 * j + 3] += nv.w;
+            s[4 * j + 0] = fmaf(s[4 * j + 0], rs, nv.x); s[4 * j + 1] = fmaf(s[4 * j + 1], rs, nv.y);
+            s[4 * j + 2] = fmaf(s[4 * j + 2], rs, nv.z); s[4 * j + 3] = fmaf(s[4 * j + 3], rs, nv.w);
           }
           if (!whole) {
 #pragma unroll
@@ -768,7 +810,7 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           __syncwarp();
           if (lane == 0) wsg_mbar_arrive(&S->acc_empty[acc]);
         }
-        if (++acc == WSG_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        if (++acc == A.nacc) { acc = 0; acc_phase ^= 1; }
       }
       __syncwarp();
       if (lane == 0) atomicAdd(&S->warps_done, 1u);
@@ -1012,8 +1054,12 @@ cudaError_t wsg_launch_pack(cudaStream_t st, const WsGemmPackArgs& a) {
   ws_gemm_pack_kernel<<<(a.rows_pad + 7) / 8, 256, 0, st>>>(a);
   return cudaGetLastError();
 }
-cudaError_t wsg_launch_topk(int grid, cudaStream_t st, const CUtensorMap& tm_a, const CUtensorMap& tm_b, const WsGemmArgs& a) {
-  ws_gemm_topk_kernel<<<grid, WSG_THREADS, wsg_topk_smem_bytes(), st>>>(tm_a, tm_b, a);
+cudaError_t wsg_launch_topk(int grid, cudaStream_t st, const CUtensorMap& tm_b, const WsGemmArgs& a) {
+  ws_gemm_topk_kernel<<<grid, WSG_THREADS, wsg_topk_smem_bytes(), st>>>(tm_b, a);
+  return cudaGetLastError();
+}
+cudaError_t wsg_launch_cvt(int grid, cudaStream_t st, const WsGemmCvtArgs& a) {
+  ws_gemm_cvt_kernel<<<grid, 256, 0, st>>>(a);
   return cudaGetLastError();
 }
 template <int KQ, int METRIC>
@@ -1028,8 +1074,8 @@ cudaError_t wsg_launch_seed(int kq, int metric, bool exact, cudaStream_t st, con
   case KQ_:                                                                          \
     return metric == 0 ? wsg_launch_seed_t<KQ_, 0>(exact, grid, st, a) : wsg_launch_seed_t<KQ_, 1>(exact, grid, st, a);
   switch (kq) {
-    WSG_SD(1) WSG_SD(2) WSG_SD(3) WSG_SD(4)
-    default: return cudaErrorInvalidValue;
+    WSG_SD(1) WSG_SD(2) WSG_SD(3) WSG_SD(4) WSG_SD(8) WSG_SD(16)
+    default: return cudaErrorInvalidValue;  // dpad <= 512 on this path
   }
 #undef WSG_SD
 }
@@ -1045,8 +1091,8 @@ cudaError_t wsg_launch_rerank(int kq, int metric, bool exact, cudaStream_t st, c
   case KQ_:                                                                          \
     return metric == 0 ? wsg_launch_rerank_t<KQ_, 0>(exact, grid, st, a) : wsg_launch_rerank_t<KQ_, 1>(exact, grid, st, a);
   switch (kq) {
-    WSG_RR(1) WSG_RR(2) WSG_RR(3) WSG_RR(4)
-    default: return cudaErrorInvalidValue;  // dpad <= 128 on this path
+    WSG_RR(1) WSG_RR(2) WSG_RR(3) WSG_RR(4) WSG_RR(8) WSG_RR(16)
+    default: return cudaErrorInvalidValue;  // dpad <= 512 on this path
   }
 #undef WSG_RR
 }

@@ -6,11 +6,12 @@
 
 #define WSG_TILE_M 128       // queries per group = TMEM lanes
 #define WSG_TILE_N 128       // points per tile   = TMEM columns per accumulator stage
-#define WSG_KBLK 32          // fp32 columns per 128-byte swizzle block
+#define WSG_KBLK 64          // fp16 columns per 128-byte swizzle block
 #define WSG_KBLK_BYTES (WSG_TILE_N * 128)  // one operand block: 128 rows x 128 B = 16 KB
-#define WSG_MAX_KB 4         // dpad <= 128
+#define WSG_MAX_KB 8         // dpad <= 512
 #define WSG_B_STAGES 12      // ring of point blocks (192 KB)
-#define WSG_ACC_STAGES 3     // 3 x 128 accumulator columns + 128 columns holding the query operand = 512
+#define WSG_ACC_STAGES 3     // accumulator stages of 128 TMEM columns: 3 next to a query operand of <= 128 columns
+                             // (dpad <= 256), 2 next to one of 256 columns (dpad <= 512)
 #define WSG_KTOP 16          // k <= 16 on this path
 #define WSG_CAND_CAP 512     // survivors kept per (item, query)
 #define WSG_SCHED 64         // per-CTA ring of item ids (see WsGemmSmem::sched)
@@ -37,12 +38,23 @@ struct WsGemmNormArgs {
   int metric;
   float* norms;       // L2: |x|^2; MIPS: 0
   uint32_t* max_sq;   // float bits of max |x|^2 (non-negative floats order like uints)
+  uint32_t* max_abs;  // float bits of max |x_i| (NaN / inf components make it >= 0x7f800000: not eligible)
+};
+
+// fp16 mirror of the arena for the sweep: half(x * scale), scale a power of two that puts the largest
+// component in [2^13, 2^14).  Rows keep the arena's stride (dpad elements).
+struct WsGemmCvtArgs {
+  const float* vecs;
+  uint64_t count;     // n * dpad
+  float scale;
+  uint16_t* out;      // __half bits
 };
 
 struct WsGemmPlanArgs {
   const float* windows;   // [nq][2] of this slice
   const float* labels;
   uint64_t n;
+  uint64_t n_bound;       // n, or n + 1 for a label shard whose last point may be inside a window (WsGeom::pf_n)
   uint32_t nq;            // <= WSG_MAX_ROWS
   uint32_t rows_pad;      // nq rounded up to 128
   uint32_t* qa;           // [nq] scratch: window bounds per query (ws_gemm_bounds_kernel)
@@ -68,7 +80,10 @@ struct WsGemmPackArgs {
   int metric;
   const uint32_t* perm;
   const uint32_t* max_sq;
-  float* qpack;           // [rows_pad][dpad]
+  uint32_t kcols;         // fp16 columns of a packed row (blocks per tile x 64; zero beyond dpad)
+  int32_t x_exp;          // the arena mirror holds half(x * 2^x_exp)
+  uint16_t* qpack;        // [rows_pad][kcols] half(scale * q * 2^q_exp(row))
+  float* rscale;          // [rows_pad]  2^-(x_exp + q_exp(row)): accumulator -> score units
   float* slack;           // [rows_pad]  2E
   float* qnorm;           // [rows_pad]  |q|^2
 };
@@ -100,9 +115,13 @@ struct WsGemmArgs {
   uint64_t* cand;       // [max_items][WSG_CAND_CAP][128]  (score~, point) keys
   uint32_t* cand_cnt;   // [max_items][128]   0xFFFFFFFF: overflow
   float* cand_thr;      // [max_items][128]   final threshold
-  const float* qpack;   // [rows_pad][dpad] packed queries (the A operand, copied into TMEM per item)
-  uint32_t dpad;
-  uint32_t nkb;         // 32-column blocks per row
+  const uint16_t* qpack;  // [rows_pad][kcols] packed fp16 queries (the A operand, copied into TMEM per item)
+  const float* rscale;  // [rows_pad] accumulator -> score units
+  uint32_t kcols;
+  uint32_t nkb;         // 64-column fp16 blocks per tile (1, 2, 3, 4, 6 or 8)
+  uint32_t kbps;        // blocks per pipeline stage (<= 4: a stage is at most 64 KB)
+  uint32_t nacc;        // accumulator stages in use (3, or 2 when the query operand takes 256 columns)
+  uint32_t acc_col0;    // first accumulator column (128 or 256)
   uint32_t k;
   uint32_t dbg;         // timing experiments only (results invalid): 1 = epilogue releases stages without
                         // reading them, 2 = producer signals point blocks without loading them
@@ -136,8 +155,9 @@ struct WsGemmRerankArgs {
 size_t wsg_topk_smem_bytes();
 cudaError_t wsg_init_attributes();
 cudaError_t wsg_launch_norm(int grid, cudaStream_t st, const WsGemmNormArgs& a);
+cudaError_t wsg_launch_cvt(int grid, cudaStream_t st, const WsGemmCvtArgs& a);
 cudaError_t wsg_launch_plan(uint32_t nsort, cudaStream_t st, const WsGemmPlanArgs& a);
 cudaError_t wsg_launch_pack(cudaStream_t st, const WsGemmPackArgs& a);
 cudaError_t wsg_launch_seed(int kq, int metric, bool exact, cudaStream_t st, const WsGemmSeedArgs& a);
-cudaError_t wsg_launch_topk(int grid, cudaStream_t st, const CUtensorMap& tm_a, const CUtensorMap& tm_b, const WsGemmArgs& a);
+cudaError_t wsg_launch_topk(int grid, cudaStream_t st, const CUtensorMap& tm_b, const WsGemmArgs& a);
 cudaError_t wsg_launch_rerank(int kq, int metric, bool exact, cudaStream_t st, const WsGemmRerankArgs& a);

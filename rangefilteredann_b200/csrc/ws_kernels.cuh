@@ -31,8 +31,8 @@ __global__ void __launch_bounds__(128) ws_decompose_kernel(WsDecompArgs A) {
     case 2: ws_decompose_three_split(A.g, lo, hi, A.p, em); break;
     case 3: ws_decompose_super(A.g, lo, hi, em); break;
     case WS_MODE_PREFILTER: {
-      uint64_t s = ws_prefilter_bound(A.g.labels, A.g.n, lo);
-      uint64_t e = ws_prefilter_bound(A.g.labels, A.g.n, hi);
+      uint64_t s = ws_prefilter_bound(A.g.labels, A.g.pf_n, lo);
+      uint64_t e = ws_prefilter_bound(A.g.labels, A.g.pf_n, hi);
       em.scan(s, e, lo, hi);
       break;
     }
@@ -1147,7 +1147,8 @@ __global__ void __launch_bounds__(WS_CTA_THREADS) ws_merge_parts_kernel(WsMergeP
   tk.buf = buf; tk.cnt = &s_cnt; tk.nbest = &s_nbest; tk.tau = &s_tau;
   const int tid = threadIdx.x;
   const int K = (int)A.k;
-  for (uint32_t q = blockIdx.x; q < A.nq; q += gridDim.x) {
+  for (uint32_t qi = blockIdx.x; qi < A.nq; qi += gridDim.x) {
+    const uint32_t q = A.q0 + qi;
     __syncthreads();
     ws_topk_init(tk, tid);
     __syncthreads();
@@ -1159,10 +1160,12 @@ __global__ void __launch_bounds__(WS_CTA_THREADS) ws_merge_parts_kernel(WsMergeP
         nbest = s_nbest;
         appended = 0;
       }
-      const size_t base = ((size_t)p * A.nq + q) * K;
+      const uint32_t* pi = A.ids ? A.ids + (size_t)p * A.nq_total * K : A.part_ids[p];
+      const float* pd = A.ids ? A.dists + (size_t)p * A.nq_total * K : A.part_dists[p];
+      const size_t base = (size_t)q * K;
       for (int i = tid; i < K; i += WS_CTA_THREADS) {
-        const float d = A.dists[base + i];
-        buf[nbest + appended + i] = (d == 3.402823466e+38f) ? WS_KEY_MAX : ws_key(d, A.ids[base + i]);
+        const float d = pd[base + i];
+        buf[nbest + appended + i] = (d == 3.402823466e+38f) ? WS_KEY_MAX : ws_key(d, pi[base + i]);
       }
       appended += K;
     }

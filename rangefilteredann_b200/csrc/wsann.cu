@@ -135,6 +135,12 @@ struct ws_index {
   // scratch (grown on demand)
   WsDevBuf tasks, res_keys, res_cnt, counts, queues, ctrl, d_queries, d_windows, d_ids, d_dists,
       bitmap, flush;
+  // multi-GPU (ws_group.inl): NCCL communicator of this arena's rank, gathered partial rows, and — for
+  // device-pointer batches issued by a group — the host copy of the batch's windows (routing sample)
+  void* comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
+  WsDevBuf x_all_ids, x_all_dists;
+  const float* hint_windows = nullptr;
   unsigned long long* d_stats = nullptr;
   // sticky error word, never cleared by a batch: bit 0 = task-slot capacity overflow (tasks dropped), bit 1 = a task
   // outgrew the last beam tier and was dropped.  Read (and cleared) by host-buffer batches before they return and by
@@ -143,21 +149,21 @@ struct ws_index {
   uint64_t launches = 0;
 
   // tensor-core prefilter (ws_gemm.cuh)
+  int64_t opt_open_tail = 0;     // 1: prefilter windows may include the arena's last point (label shards, WsGeom::pf_n)
   int64_t opt_direct = 2;        // one-launch prefilter (K1d): 0 never, 1 always, 2 auto (host-sampled mean window <= scan_chunk)
   int64_t opt_gemm = 2;          // 0 never, 1 whenever eligible, 2 auto (host-sampled mean window >= opt_gemm_min_window)
-  int64_t opt_gemm_min_window = 2048;
+  int64_t opt_gemm_min_window = 768;
   int64_t opt_gemm_dynamic = 1;  // sweep kernel draws work items from a device counter (0: static striping)
   int64_t opt_gemm_items = 0;    // target work items per plan (0: 2 per SM)
   int64_t opt_gemm_min_tiles = 8;
   int64_t opt_gemm_debug = 0;     // timing experiments (ws_gemm.h WsGemmArgs::dbg); results are invalid when set
   int64_t opt_gemm_chunk_mb = 8;  // largest slice of the label axis one work item sweeps
   bool gemm_ready = false;
-  WsDevBuf g_norms, g_ctrl, g_perm, g_row_a, g_row_b, g_items, g_group_items, g_group_cnt, g_qpack, g_slack, g_cand,
+  bool gemm_unfit = false;        // the arena cannot be mirrored in fp16 (non-finite or absurdly scaled components)
+  int32_t g_x_exp = 0;            // the fp16 mirror holds half(x * 2^g_x_exp)
+  WsDevBuf g_norms, g_ctrl, g_perm, g_row_a, g_row_b, g_items, g_group_items, g_group_cnt, g_qpack, g_rscale, g_vecs16, g_slack, g_cand,
       g_cand_cnt, g_cand_thr, g_res_keys, g_res_cnt, g_thr0, g_qnorm, g_qa, g_qb;
   CUtensorMap g_tm_b{};
-  CUtensorMap g_tm_a{};
-  const void* g_tm_a_ptr = nullptr;
-  uint32_t g_tm_a_rows = 0;
 
   // optional per-kernel CUDA-event timing (ws_index_kernel_times)
   int64_t opt_profile = 0;
@@ -330,8 +336,8 @@ void ws_index_destroy(ws_index* idx) {
     for (void* p : idx->geom_dev_allocs) cudaFree(p);
     WsDevBuf* bufs[] = {&idx->tasks, &idx->res_keys, &idx->res_cnt, &idx->counts, &idx->queues, &idx->ctrl,
                         &idx->d_queries, &idx->d_windows, &idx->d_ids, &idx->d_dists, &idx->bitmap, &idx->flush,
-                        &idx->g_norms, &idx->g_ctrl, &idx->g_perm, &idx->g_row_a, &idx->g_row_b, &idx->g_items,
-                        &idx->g_group_items, &idx->g_group_cnt, &idx->g_qpack, &idx->g_slack, &idx->g_cand,
+                        &idx->x_all_ids, &idx->x_all_dists, &idx->g_norms, &idx->g_ctrl, &idx->g_perm, &idx->g_row_a, &idx->g_row_b, &idx->g_items,
+                        &idx->g_group_items, &idx->g_group_cnt, &idx->g_qpack, &idx->g_rscale, &idx->g_vecs16, &idx->g_slack, &idx->g_cand,
                         &idx->g_cand_cnt, &idx->g_cand_thr, &idx->g_res_keys, &idx->g_res_cnt, &idx->g_thr0, &idx->g_qnorm, &idx->g_qa, &idx->g_qb};
     for (WsDevBuf* b : bufs) cudaFree(b->p);
     for (cudaEvent_t e : idx->ev_pool) cudaEventDestroy(e);
@@ -487,6 +493,7 @@ int ws_index_finalize(ws_index* idx) {
   WsGeom& h = idx->hgeom;
   h.labels = idx->h_labels.data();
   h.n = idx->n;
+  h.pf_n = idx->n + (idx->opt_open_tail ? 1 : 0);
   h.wst_rows = idx->wst_rows; h.split = idx->split; h.cutoff = idx->cutoff;
   h.wst_nb = idx->wst_nb.data(); h.wst_off_ptr = idx->wst_off_ptr.data(); h.wst_off = idx->wst_off.data();
   h.wst_node_ptr = idx->wst_node_ptr.data(); h.wst_nodes = idx->wst_nodes.data();
@@ -571,15 +578,16 @@ static int ws_tmap_encoder(ws_tmap_encode_fn* out) {
   return WS_OK;
 }
 
-// [rows][dpad] fp32 row-major -> boxes of 128 rows x 32 columns, 128-byte swizzle, zero fill
+// [rows][dpad] fp16 row-major -> boxes of 128 rows x 64 columns (128 B), 128-byte swizzle; columns past dpad and rows
+// past `rows` read as zeros
 static int ws_make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t dpad) {
   ws_tmap_encode_fn enc;
   WS_TRY(ws_tmap_encoder(&enc));
   cuuint64_t gdim[2] = {dpad, rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)dpad * sizeof(float)};
+  cuuint64_t gstride[1] = {(cuuint64_t)dpad * sizeof(uint16_t)};
   cuuint32_t box[2] = {WSG_KBLK, WSG_TILE_N};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return ws_fail(WS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %llu x %u", (int)r, (unsigned long long)rows, dpad);
@@ -587,23 +595,43 @@ static int ws_make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint32
 }
 
 static bool ws_gemm_eligible(const ws_index* idx, uint32_t k) {
-  return idx->label_sorted && k <= WSG_KTOP && idx->dpad <= WSG_MAX_KB * WSG_KBLK && idx->n >= 2 * WSG_TILE_N &&
-         idx->n < 0x7FFFFE00ull;
+  return idx->label_sorted && !idx->gemm_unfit && k <= WSG_KTOP && idx->dpad <= WSG_MAX_KB * WSG_KBLK &&
+         idx->n >= 2 * WSG_TILE_N && idx->n < 0x7FFFFE00ull;
 }
 
-// one-time per index: |x|^2 table, max norm, tensor map of the arena
+// one-time per index: |x|^2 table, max norm, the fp16 mirror of the arena and its tensor map.  Sets gemm_unfit
+// (and returns WS_OK) when the arena cannot be mirrored; the caller then answers with the scan kernels.
 static int ws_gemm_prepare(ws_index* idx) {
-  if (idx->gemm_ready) return WS_OK;
+  if (idx->gemm_ready || idx->gemm_unfit) return WS_OK;
   const uint64_t npad = idx->n + 2 * WSG_TILE_N;
   WS_TRY(ws_ensure(idx, idx->g_norms, npad * sizeof(float)));
   WS_TRY(ws_ensure(idx, idx->g_ctrl, 64 * sizeof(unsigned long long)));
   WS_CUDA(cudaMemsetAsync(idx->g_ctrl.p, 0, 64 * sizeof(unsigned long long), idx->stream));
   WsGemmNormArgs na;
   na.vecs = idx->d_vecs; na.n = idx->n; na.dpad = idx->dpad; na.npad = (uint32_t)npad; na.metric = idx->metric;
-  na.norms = (float*)idx->g_norms.p; na.max_sq = (uint32_t*)idx->g_ctrl.p + 8;
+  na.norms = (float*)idx->g_norms.p; na.max_sq = (uint32_t*)idx->g_ctrl.p + 8; na.max_abs = (uint32_t*)idx->g_ctrl.p + 9;
   WS_CUDA(wsg_launch_norm(idx->num_sms * 8, idx->stream, na));
   idx->launches++;
-  WS_TRY(ws_make_tmap(&idx->g_tm_b, idx->d_vecs, idx->n, idx->dpad));
+  uint32_t h_max[2] = {0, 0};  // bits of max |x|^2 and max |x_i|
+  WS_CUDA(cudaMemcpyAsync(h_max, (uint32_t*)idx->g_ctrl.p + 8, sizeof(h_max), cudaMemcpyDeviceToHost, idx->stream));
+  WS_CUDA(cudaStreamSynchronize(idx->stream));
+  float max_sq, max_abs;
+  std::memcpy(&max_sq, &h_max[0], 4);
+  std::memcpy(&max_abs, &h_max[1], 4);
+  int ex = 0;
+  if (std::isfinite(max_abs) && max_abs > 0.f) std::frexp(max_abs, &ex);  // max_abs = m * 2^ex, m in [0.5, 1)
+  // the largest component lands in [2^13, 2^14): far from fp16's overflow (2^16) and subnormals (2^-14)
+  if (!std::isfinite(max_abs) || !std::isfinite(max_sq) || !(max_abs > 0.f) || ex < -60 || ex > 60) {
+    idx->gemm_unfit = true;
+    return WS_OK;
+  }
+  idx->g_x_exp = 14 - ex;
+  WS_TRY(ws_ensure(idx, idx->g_vecs16, (size_t)idx->n * idx->dpad * sizeof(uint16_t)));
+  WsGemmCvtArgs ca;
+  ca.vecs = idx->d_vecs; ca.count = idx->n * idx->dpad; ca.scale = std::ldexp(1.0f, idx->g_x_exp); ca.out = (uint16_t*)idx->g_vecs16.p;
+  WS_CUDA(wsg_launch_cvt(idx->num_sms * 8, idx->stream, ca));
+  idx->launches++;
+  WS_TRY(ws_make_tmap(&idx->g_tm_b, idx->g_vecs16.p, idx->n, idx->dpad));
   idx->gemm_ready = true;
   return WS_OK;
 }
@@ -612,13 +640,21 @@ static int ws_gemm_prepare(ws_index* idx) {
 // dq/dw/dids/ddists are device pointers; work is only enqueued on the index stream.
 static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw, uint64_t nq, uint32_t k, uint32_t* dids,
                                  float* ddists, const uint32_t* decode, uint32_t pad_id, uint32_t* overflow_flag) {
-  WS_TRY(ws_gemm_prepare(idx));
   cudaStream_t st = idx->stream;
+  // 64-column fp16 blocks per tile: 1-4, 6 or 8 (a pipeline stage holds at most 4 of them; the columns past dpad are
+  // zero-filled by the TMA unit on the point side and by the pack kernel on the query side)
+  uint32_t nkb = (idx->dpad + WSG_KBLK - 1) / WSG_KBLK;
+  if (nkb == 5) nkb = 6;
+  if (nkb == 7) nkb = 8;
+  const uint32_t kbps = nkb <= 4 ? nkb : nkb / 2;
+  const uint32_t kcols = nkb * WSG_KBLK;
+  const uint32_t acc_col0 = nkb <= 4 ? 128u : 256u;  // TMEM columns [0, acc_col0) hold the queries (32 per block)
+  const uint32_t nacc = nkb <= 4 ? 3u : 2u;
   const uint32_t max_rows = (uint32_t)std::min<uint64_t>(WSG_MAX_ROWS, (nq + 127) / 128 * 128);
   const uint32_t max_groups = max_rows / 128;
   const uint32_t target = (uint32_t)(idx->opt_gemm_items > 0 ? idx->opt_gemm_items : 2 * (int64_t)idx->num_sms);
   // slices of the label axis swept at the same time by different query groups must stay in L2
-  const uint32_t max_tiles = (uint32_t)std::max<uint64_t>(32, ((uint64_t)idx->opt_gemm_chunk_mb << 20) / ((uint64_t)idx->dpad * 4 * WSG_TILE_N));
+  const uint32_t max_tiles = (uint32_t)std::max<uint64_t>(32, ((uint64_t)idx->opt_gemm_chunk_mb << 20) / ((uint64_t)idx->dpad * 2 * WSG_TILE_N));
   const uint64_t tiles_bound = (uint64_t)max_groups * ((idx->n + WSG_TILE_N - 1) / WSG_TILE_N);
   const uint32_t max_items = (uint32_t)(target + tiles_bound / max_tiles + 2 * max_groups + 8);
   WS_TRY(ws_ensure(idx, idx->g_qa, max_rows * sizeof(uint32_t)));
@@ -629,7 +665,8 @@ static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw
   WS_TRY(ws_ensure(idx, idx->g_items, max_items * sizeof(WsGemmItem)));
   WS_TRY(ws_ensure(idx, idx->g_group_items, (size_t)max_groups * WSG_MAX_SPLITS * sizeof(uint32_t)));
   WS_TRY(ws_ensure(idx, idx->g_group_cnt, max_groups * sizeof(uint32_t)));
-  WS_TRY(ws_ensure(idx, idx->g_qpack, (size_t)max_rows * idx->dpad * sizeof(float)));
+  WS_TRY(ws_ensure(idx, idx->g_qpack, (size_t)max_rows * kcols * sizeof(uint16_t)));
+  WS_TRY(ws_ensure(idx, idx->g_rscale, max_rows * sizeof(float)));
   WS_TRY(ws_ensure(idx, idx->g_slack, max_rows * sizeof(float)));
   WS_TRY(ws_ensure(idx, idx->g_thr0, max_rows * sizeof(float)));
   WS_TRY(ws_ensure(idx, idx->g_qnorm, max_rows * sizeof(float)));
@@ -638,11 +675,6 @@ static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw
   WS_TRY(ws_ensure(idx, idx->g_cand_thr, (size_t)max_items * WSG_TILE_M * sizeof(float)));
   WS_TRY(ws_ensure(idx, idx->g_res_keys, (size_t)max_rows * k * sizeof(uint64_t)));
   WS_TRY(ws_ensure(idx, idx->g_res_cnt, max_rows * sizeof(uint32_t)));
-  if (idx->g_tm_a_ptr != idx->g_qpack.p || idx->g_tm_a_rows != max_rows) {
-    WS_TRY(ws_make_tmap(&idx->g_tm_a, idx->g_qpack.p, max_rows, idx->dpad));
-    idx->g_tm_a_ptr = idx->g_qpack.p;
-    idx->g_tm_a_rows = max_rows;
-  }
   const size_t gemm_smem = wsg_topk_smem_bytes();
   if (gemm_smem > idx->smem_optin) return ws_fail(WS_ERR_CUDA, "tensor-core prefilter needs %zu B of shared memory (> %zu)", gemm_smem, idx->smem_optin);
   static bool attr_set = false;
@@ -661,7 +693,7 @@ static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw
     uint32_t nsort = 128;
     while (nsort < rows_pad) nsort <<= 1;
     WsGemmPlanArgs pa;
-    pa.windows = dw + 2 * q0; pa.labels = idx->d_labels; pa.n = idx->n; pa.nq = sn; pa.rows_pad = rows_pad;
+    pa.windows = dw + 2 * q0; pa.labels = idx->d_labels; pa.n = idx->n; pa.n_bound = idx->hgeom.pf_n; pa.nq = sn; pa.rows_pad = rows_pad;
     pa.qa = (uint32_t*)idx->g_qa.p; pa.qb = (uint32_t*)idx->g_qb.p; pa.max_tiles = max_tiles;
     pa.perm = (uint32_t*)idx->g_perm.p; pa.row_a = (uint32_t*)idx->g_row_a.p; pa.row_b = (uint32_t*)idx->g_row_b.p;
     pa.items = (WsGemmItem*)idx->g_items.p; pa.nitems = gctrl32 + 10; pa.sched_ctr = gctrl32 + 12; pa.max_items = max_items;
@@ -670,7 +702,8 @@ static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw
     pa.overflow = overflow_flag;
     WsGemmPackArgs ka;
     ka.queries = dq + q0 * idx->dim; ka.dim = idx->dim; ka.dpad = idx->dpad; ka.rows_pad = rows_pad; ka.metric = idx->metric;
-    ka.perm = pa.perm; ka.max_sq = gctrl32 + 8; ka.qpack = (float*)idx->g_qpack.p; ka.slack = (float*)idx->g_slack.p;
+    ka.perm = pa.perm; ka.max_sq = gctrl32 + 8; ka.qpack = (uint16_t*)idx->g_qpack.p; ka.slack = (float*)idx->g_slack.p;
+    ka.kcols = kcols; ka.x_exp = idx->g_x_exp; ka.rscale = (float*)idx->g_rscale.p;
     ka.qnorm = (float*)idx->g_qnorm.p;
     WsGemmSeedArgs sa;
     sa.vecs = idx->d_vecs; sa.queries = ka.queries; sa.dim = idx->dim; sa.dpad = idx->dpad; sa.rows_pad = rows_pad; sa.k = k;
@@ -688,10 +721,11 @@ static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw
     WsGemmArgs ga;
     ga.items = pa.items; ga.nitems = pa.nitems; ga.sched_ctr = pa.sched_ctr; ga.dyn = idx->opt_gemm_dynamic ? 1u : 0u; ga.row_a = pa.row_a; ga.row_b = pa.row_b; ga.slack = ka.slack; ga.gthr = sa.thr0;
     ga.norms = (const float*)idx->g_norms.p; ga.cand = (uint64_t*)idx->g_cand.p; ga.cand_cnt = (uint32_t*)idx->g_cand_cnt.p;
-    ga.cand_thr = (float*)idx->g_cand_thr.p; ga.nkb = (idx->dpad + WSG_KBLK - 1) / WSG_KBLK; ga.k = k; ga.dbg = (uint32_t)idx->opt_gemm_debug; ga.qpack = ka.qpack; ga.dpad = idx->dpad;
+    ga.cand_thr = (float*)idx->g_cand_thr.p; ga.nkb = nkb; ga.kbps = kbps; ga.nacc = nacc; ga.acc_col0 = acc_col0; ga.k = k;
+    ga.dbg = (uint32_t)idx->opt_gemm_debug; ga.qpack = ka.qpack; ga.rscale = ka.rscale; ga.kcols = kcols;
     {
       WsKernelScope ks(idx, 9);
-      WS_CUDA(wsg_launch_topk(idx->num_sms, st, idx->g_tm_a, idx->g_tm_b, ga));
+      WS_CUDA(wsg_launch_topk(idx->num_sms, st, idx->g_tm_b, ga));
     }
     WsGemmRerankArgs ra;
     ra.vecs = idx->d_vecs; ra.queries = ka.queries; ra.dim = idx->dim; ra.dpad = idx->dpad; ra.rows_pad = rows_pad;
@@ -785,7 +819,9 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
   // ---- prefilter batches: how the batch is answered depends on the window sizes.  With host buffers a
   // sample of the batch's windows is measured here; device-pointer calls take the options as they are.
   double mean_window = -1.0;  // rows per window over a sample of 64 queries (host buffers only)
-  if (plan.mode == WS_MODE_PREFILTER && !dev_ptrs && nq >= 256) {
+  const float* host_windows = dev_ptrs ? idx->hint_windows : windows;
+  if (plan.mode == WS_MODE_PREFILTER && host_windows && nq >= 256) {
+    const float* windows = host_windows;
     const std::vector<float>& L = idx->h_labels;
     const uint64_t step = std::max<uint64_t>(1, nq / 64);
     double sum = 0; uint64_t cnt = 0;
@@ -801,6 +837,10 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
   if (plan.mode == WS_MODE_PREFILTER && idx->opt_gemm != 0 && ws_gemm_eligible(idx, k)) {
     if (idx->opt_gemm == 1) use_gemm = true;
     else use_gemm = mean_window >= (double)idx->opt_gemm_min_window;
+    if (use_gemm) {
+      WS_TRY(ws_gemm_prepare(idx));  // first use: norm table + fp16 mirror of the arena
+      use_gemm = !idx->gemm_unfit;
+    }
   }
   // small windows: the whole batch in one launch (K1d)
   bool use_direct = false;
@@ -829,7 +869,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
     pa.s.tasks = nullptr; pa.s.res_keys = (uint64_t*)idx->res_keys.p; pa.s.res_cnt = (uint32_t*)idx->res_cnt.p;
     pa.s.k = k; pa.s.q_in = nullptr; pa.s.q_in_count = nullptr; pa.s.q_head = nullptr; pa.s.stats = idx->d_stats;
     pa.s.out_ids = dids; pa.s.out_dists = ddists; pa.s.decode = plan.use_decode ? idx->d_decode : nullptr; pa.s.pad_id = plan.pad_id;
-    pa.labels = idx->d_labels; pa.n = idx->n; pa.windows = dw; pa.nq = (uint32_t)nq;
+    pa.labels = idx->d_labels; pa.n = idx->hgeom.pf_n; pa.windows = dw; pa.nq = (uint32_t)nq;
     int occ = 0;
     WS_LAUNCH("occupancy query", wsl_prefilter_direct_occ(kq, metric, exact_rows, &occ));
     if (occ < 1) return ws_fail(WS_ERR_CUDA, "prefilter kernel does not fit on an SM");
@@ -1347,8 +1387,9 @@ int ws_merge_partial_topk(ws_index* idx, const uint32_t* ids, const float* dists
   if (!ids || !dists || !out_ids || !out_dists) return ws_fail(WS_ERR_BADARG, "null buffer");
   if (k == 0 || k > kMaxK || parts == 0) return ws_fail(WS_ERR_BADARG, "k=%u parts=%u", k, parts);
   if (nq == 0) return WS_OK;
-  WsMergePartsArgs a;
-  a.ids = ids; a.dists = dists; a.parts = parts; a.k = k; a.nq = (uint32_t)nq; a.pad_id = pad_id;
+  if (parts > WS_MAX_PARTS) return ws_fail(WS_ERR_BADARG, "parts=%u above %d", parts, WS_MAX_PARTS);
+  WsMergePartsArgs a{};
+  a.ids = ids; a.dists = dists; a.parts = parts; a.k = k; a.nq = (uint32_t)nq; a.nq_total = (uint32_t)nq; a.q0 = 0; a.pad_id = pad_id;
   a.out_ids = out_ids; a.out_dists = out_dists;
   int grid = (int)std::min<uint64_t>(nq, (uint64_t)idx->num_sms * 16);
   WS_CUDA(wsl_merge_parts(grid, idx->stream, a));
@@ -1392,6 +1433,9 @@ int ws_index_set_option(ws_index* idx, const char* name, int64_t value) {
     idx->opt_expand = value;
   } else if (s == "emulate_query_id_skip") {
     idx->opt_skip_query_id = value != 0;
+  } else if (s == "prefilter_open_tail") {
+    idx->opt_open_tail = value != 0;
+    idx->hgeom.pf_n = idx->dgeom.pf_n = idx->n + (idx->opt_open_tail ? 1 : 0);
   } else if (s == "scan_chunk") {
     if (value < 256) return ws_fail(WS_ERR_BADARG, "scan_chunk must be >= 256");
     idx->opt_scan_chunk = value;
@@ -1501,8 +1545,8 @@ int ws_debug_decompose_host(ws_index* idx, int method, const float* windows, uin
       case 2: ws_decompose_three_split(idx->hgeom, lo, hi, p, em); break;
       case 3: ws_decompose_super(idx->hgeom, lo, hi, em); break;
       default: {
-        uint64_t s = ws_prefilter_bound(idx->hgeom.labels, idx->n, lo);
-        uint64_t e = ws_prefilter_bound(idx->hgeom.labels, idx->n, hi);
+        uint64_t s = ws_prefilter_bound(idx->hgeom.labels, idx->hgeom.pf_n, lo);
+        uint64_t e = ws_prefilter_bound(idx->hgeom.labels, idx->hgeom.pf_n, hi);
         em.scan(s, e, lo, hi);
       }
     }
@@ -1525,3 +1569,5 @@ int ws_debug_decompose_host(ws_index* idx, int method, const float* windows, uin
 }
 
 }  // extern "C"
+
+#include "ws_group.inl"

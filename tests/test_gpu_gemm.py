@@ -1,4 +1,4 @@
-"""Tensor-core prefilter (csrc/ws_gemm.cu) vs the streaming-scan prefilter: the tf32 sweep only
+"""Tensor-core prefilter (csrc/ws_gemm.cu) vs the streaming-scan prefilter: the fp16 sweep only
 SELECTS candidates (with a proven error slack) and the survivors are re-ranked with the scan
 kernel's fp32 arithmetic, so ids AND distances must be bit-identical to the scan path (which is
 itself bit-identical to the device-order oracle, test_gpu_oracle.py) on every input: ragged
@@ -145,3 +145,57 @@ def test_auto_mode_through_the_pybind_surface(engine):
         ids0, dists0 = idx.batch_search(queries, [tuple(x) for x in w], 1024, qp)
         assert np.array_equal(ids, ids0) and np.array_equal(dists.view(np.uint32), dists0.view(np.uint32))
     h.set_option("gemm_prefilter", 2)
+
+
+@pytest.mark.parametrize("d,angular", [(256, False), (192, False), (320, True), (512, True)])
+def test_wide_rows(engine, d, angular):
+    """rows above 128 columns: 3-8 blocks of 64 fp16 per tile (d=512: two pipeline stages per tile, the
+    query operand takes 256 TMEM columns and leaves two accumulator stages; d=320: 5 blocks padded to 6)"""
+    data, queries, labels, idx, h = make(engine, 12000, d, 600, angular=angular, seed=12)
+    w = mixed_windows(labels, 560, seed=71)
+    assert_same(h, queries, w, 10)
+
+
+def test_zero_tiny_and_huge_queries(engine):
+    """the error slack has an absolute term (norm-table and distance rounding), so a zero or tiny query still gets
+    the exact rows; a query too large to scale into fp16 falls back to the exact scan inside the re-rank kernel"""
+    data, queries, labels, idx, h = make(engine, 30000, 128, 512, seed=13)
+    q = queries.copy()
+    q[0] = 0.0
+    q[1] *= 1e-6
+    q[2] *= 1e-20
+    q[3] *= 1e6
+    q[4] *= 1e25      # beyond the per-query scale range: exact-scan fallback
+    q[5, 7] = 3e38    # |q|^2 overflows fp32
+    q[6, :] = 0.0
+    q[6, 3] = 1e-30   # one subnormal-scale component
+    w = synth.make_windows(labels, -2, 512, seed=81)
+    assert_same(h, q, w, 10)
+    w = mixed_windows(labels, 480, seed=82)
+    assert_same(h, q, w, 5)
+
+
+@pytest.mark.parametrize("scale", [1e-12, 3.7e9])
+def test_badly_scaled_arena(engine, scale):
+    """component magnitudes far from 1: the fp16 mirror is built with a power-of-two scale"""
+    data, queries, labels = synth.make_dataset(20000, 64, 400, 14)
+    data = (data * scale).astype(np.float32)
+    queries = (queries * scale).astype(np.float32)
+    idx = engine.PrefilterIndexFloatEuclidian(data, labels)
+    h = capi.Handle.borrow(idx)
+    w = mixed_windows(labels, 360, seed=91)
+    assert_same(h, queries, w, 10)
+
+
+def test_non_finite_arena_uses_scan(engine):
+    """an arena with an inf component cannot be mirrored in fp16: the batch is answered by the scan kernels"""
+    data, queries, labels = synth.make_dataset(5000, 32, 300, 15)
+    data[17, 3] = np.inf
+    idx = engine.PrefilterIndexFloatEuclidian(data, labels)
+    h = capi.Handle.borrow(idx)
+    w = synth.make_windows(labels, -2, 300, seed=3)
+    h.set_option("profile_kernels", 1)
+    h.kernel_times(reset=True)
+    run(h, queries, w, 10, 1)
+    kt = h.kernel_times(reset=True)
+    assert "gemm_sweep" not in kt and kt["scan"]["launches"] >= 1

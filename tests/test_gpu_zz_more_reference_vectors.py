@@ -18,7 +18,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, device_graph_build
 from golden_cases import TINY, tiny_cases
 from oracle_api import Oracle
 from rangefilteredann_b200 import synth
@@ -56,7 +56,8 @@ def test_vamana_bucket_tree_split_3(engine, tmp_path):
     data, queries, labels = synth.make_dataset(TINY["n"], TINY["d"], TINY["nq"], TINY["seed"])
     cache = str(tmp_path / "wst3") + "/"
     # cutoff 400: rows of 1, 3 and 9 buckets (3000 -> 1000 -> 334 / 333 points)
-    tree = engine.VamanaRangeFilterTreeIndexFloatEuclidian(data, labels, 400, 3, engine.BuildParams(64, 500, 1.0, cache))
+    with device_graph_build():
+        tree = engine.VamanaRangeFilterTreeIndexFloatEuclidian(data, labels, 400, 3, engine.BuildParams(64, 500, 1.0, cache))
     assert len([f for f in os.listdir(cache) if f.endswith(".bin")]) == 1 + 3 + 9
     orc = Oracle("wst", data, labels, cache, dist_mode=1, cutoff=400, split=3.0)
     for name, windows, qkw in tiny_cases(labels):
