@@ -38,14 +38,80 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CONFIGS = {
-    # BASELINE.json configs[0] / configs[1]
-    "c1": dict(n=100_000, d=128, nq=10_000, seed=0, cutoff=1000, name="SIFT-shaped synthetic 100Kx128 fp32 L2"),
-    "c2": dict(n=1_000_000, d=128, nq=10_000, seed=0, cutoff=1000, name="SIFT-shaped synthetic 1Mx128 fp32 L2"),
+    # BASELINE.json configs[0] / configs[1]: the headline (c2 is what the driver's default run measures)
+    "c1": dict(n=100_000, d=128, nq=10_000, seed=0, cutoff=1000, metric="l2", tree="wst",
+               name="SIFT-shaped synthetic 100Kx128 fp32 L2"),
+    "c2": dict(n=1_000_000, d=128, nq=10_000, seed=0, cutoff=1000, metric="l2", tree="wst",
+               name="SIFT-shaped synthetic 1Mx128 fp32 L2"),
+    # configs[2]: GloVe's size, angular (rows normalised, MIPS arithmetic), super optimized postfilter tree, swept over
+    # the reference driver's beams x final_beam_multiplies (experiments/run_our_method.py:29-39,487-532)
+    "c3": dict(n=1_183_514, d=100, nq=10_000, seed=0, cutoff=1000, metric="mips", angular=True, tree="super",
+               beams=[10, 20, 40, 80, 160, 320, 640, 1280], mults=[1, 2, 3, 4, 8, 16, 32],
+               name="GloVe-shaped synthetic 1.18Mx100 angular"),
+    # configs[3]: RedCaps shape (CLIP-like 512-d angular, timestamp-style labels with many duplicates,
+    # generate_redcaps_data.py:77-80), optimized postfilter; --n scales the row count (stated in the line)
+    "c4": dict(n=12_000_000, d=512, nq=10_000, seed=0, cutoff=1000, metric="mips", angular=True, labels="timestamp",
+               tree="wst", name="RedCaps-shaped synthetic 12Mx512 angular, timestamp-style labels"),
+    # configs[4]: Deep shape, label-range sharded (--mode label_shard / group); --n scales the row count
+    "c5": dict(n=100_000_000, d=96, nq=10_000, seed=0, cutoff=1000, metric="l2", tree="wst",
+               name="Deep-shaped synthetic 100Mx96 fp32 L2"),
+    # configs[4], second half: the reference's adversarial recipe (generate_advserial_dataset.py:8-60: 100 clusters,
+    # label ranges = clusters, query from cluster a with cluster b's range) plus windows whose smallest containing
+    # bucket is the root (blow-up 2^4 ... 2^10)
+    "c5adv": dict(n=1_000_000, d=96, nq=9_900, seed=0, cutoff=1000, metric="l2", tree="wst", adversarial=True,
+                  name="adversarial 100-cluster synthetic 1Mx96 (normalised rows, L2)"),
 }
-POWERS = list(range(-16, 1))
+ALL_POWERS = list(range(-16, 1))
+POWERS = ALL_POWERS  # the fractions of the run (narrowed by --powers; "adv" / "blowup-p" keys for c5adv)
 K = 10
 BEAMS = [10, 20, 40, 80, 160, 320]
 MULTS = [1, 2, 4]
+
+
+def frac_name(p) -> str:
+    return f"2^{p}" if isinstance(p, int) else str(p)
+
+
+def make_inputs(cfg: dict, rank: int = 0, window_seed_shift: int = 0):
+    """data, queries, labels, {fraction: windows[nq,2]} — the same on every rank except rank > 0's queries and
+    windows of the weak-scaling run (own streams)."""
+    from rangefilteredann_b200 import synth
+    angular = bool(cfg.get("angular"))
+    if cfg.get("adversarial"):
+        data, queries, labels, adv_w = synth.make_adversarial(cfg["n"], cfg["d"], cfg["seed"])
+        windows = {}
+        for p in POWERS:
+            if p == "adv":
+                windows[p] = adv_w
+            else:
+                windows[p] = synth.make_blowup_windows(labels, int(str(p).split("blowup")[1]), len(queries), seed=1000 + window_seed_shift)
+        return data, queries, labels, windows
+    data, queries, labels = synth.make_dataset(cfg["n"], cfg["d"], cfg["nq"], cfg["seed"], angular=angular,
+                                               label_kind=cfg.get("labels", "unique"))
+    if rank > 0:
+        queries = synth.make_rank_queries(cfg["d"], cfg["nq"], cfg["seed"], rank, angular=angular)
+    windows = {p: synth.make_windows(labels, p, cfg["nq"], seed=1000 + window_seed_shift + p) for p in POWERS}
+    return data, queries, labels, windows
+
+
+def class_suffix(cfg: dict) -> str:
+    return "FloatMips" if cfg["metric"] == "mips" else "FloatEuclidian"
+
+
+def make_indices(mod, cfg: dict, cdir: str, data, labels):
+    """(tree index, prefilter index) of `mod` (this engine or the reference — same class names and arguments)."""
+    sfx = class_suffix(cfg)
+    bp = mod.BuildParams(64, 500, 1.0, cdir)
+    if cfg["tree"] == "super":
+        tree = getattr(mod, "SuperOptimizedPostfilterTreeIndex" + sfx)(data, labels, cfg["cutoff"], 2.0, 0.5, bp)
+    else:
+        tree = getattr(mod, "VamanaRangeFilterTreeIndex" + sfx)(data, labels, cfg["cutoff"], 2, bp)
+    pre = getattr(mod, "PrefilterIndex" + sfx)(data, labels)
+    return tree, pre
+
+
+def tree_methods(cfg: dict):
+    return ("super",) if cfg["tree"] == "super" else ("fenwick", "optimized_postfilter")
 RECALL_TARGET = 0.95
 PREFILTER_OPS = ("prefilter", "prefilter_direct", "prefilter_tc")
 # the engine's own routing of a PrefilterIndex batch (csrc/wsann.cu ws_run_batch, defaults of the options
@@ -64,9 +130,18 @@ def auto_prefilter_route(mean_window: float) -> str:
 
 def workload_string(cfg: dict) -> str:
     """One string for both arms (the driver compares them)."""
-    return (f"{cfg['name']}, uniform unique labels, 2-WST (cutoff 1000, R=64 L=500 alpha=1, one set of reference-format "
-            f"graph files searched by both arms), prefilter / range-filter tree / optimized postfilter, "
-            f"17 fractions x {cfg['nq']} queries, k=10, per fraction the fastest method reaching recall@10 >= 0.95")
+    labels = {"timestamp": "timestamp-style integer labels (duplicates)"}.get(cfg.get("labels", ""), "uniform unique labels")
+    if cfg.get("adversarial"):
+        labels = "cluster-aligned labels"
+    if cfg["tree"] == "super":
+        tree = ("super optimized postfilter tree (cutoff 1000, split 2, shift 0.5, R=64 L=500 alpha=1, one set of "
+                "reference-format graph files searched by both arms), prefilter / super optimized postfilter")
+    else:
+        tree = ("2-WST (cutoff 1000, R=64 L=500 alpha=1, one set of reference-format graph files searched by both arms), "
+                "prefilter / range-filter tree / optimized postfilter")
+    scaled = f" [rows scaled to {cfg['n']} for this run]" if cfg.get("scaled") else ""
+    return (f"{cfg['name']}{scaled}, {labels}, {tree}, {len(POWERS)} fractions x {cfg['nq']} queries, k=10, "
+            f"per fraction the fastest method reaching recall@10 >= 0.95")
 
 
 def rows_equal_up_to_ties(ids, dists, rids, rdists, rtol=1e-5):
@@ -93,6 +168,35 @@ def rows_equal_up_to_ties(ids, dists, rids, rdists, rtol=1e-5):
 # oracle/_ref is the reference compiled with its own flags (CMakeLists.txt:17-24) except that -march=native
 # becomes -march=x86-64-v3 (AVX2 + FMA; the build container's CPU is not the GPU box's)
 REF_MARCH = "x86-64-v3 (oracle/Makefile; the reference's CMake uses -march=native)"
+
+
+def reduce_max(values, device=None) -> list[float]:
+    """max over ranks of a small vector of timings (all ranks get the result)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.cpu()]
+
+
+def gather_rows(local: np.ndarray, world: int):
+    """Concatenate per-rank result rows on rank 0 (strong scaling: the host gather of nq x k ids; the data path
+    itself needs no collective)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or world == 1:
+        return local
+    objs = [None] * world if dist.get_rank() == 0 else None
+    dist.gather_object(local, objs, dst=0)
+    return np.concatenate(objs, axis=0) if dist.get_rank() == 0 else None
+
+
+def broadcast_bytes(payload: bytes | None, src: int = 0) -> bytes:
+    """Rank `src` hands a small byte string (the NCCL id of the in-library communicator) to every rank."""
+    import torch.distributed as dist
+    box = [payload]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
 
 
 def log(*a):
@@ -123,7 +227,9 @@ def emit(line: dict):
 # data, graphs, ground truth
 # ------------------------------------------------------------------------------------------
 def cache_dir(cfg_name: str) -> str:
-    return os.path.join(ROOT, "data_cache", cfg_name, "wst") + "/"
+    cfg = CONFIGS[cfg_name]
+    tag = cfg_name + (f"-n{cfg['n']}" if cfg.get("scaled") else "")
+    return os.path.join(ROOT, "data_cache", tag, cfg["tree"]) + "/"
 
 
 def expected_graph_count(n: int, cutoff: int, split: int = 2) -> int:
@@ -176,28 +282,28 @@ def ensure_graphs(cfg_name: str, cfg: dict, data, labels, rank: int):
     GPU is visible (the index constructor builds and saves whatever is missing), else by the
     reference builder (oracle/_ref)."""
     cdir = cache_dir(cfg_name)
-    want = expected_graph_count(cfg["n"], cfg["cutoff"])
+    want = expected_graph_count(cfg["n"], cfg["cutoff"]) if cfg["tree"] == "wst" else 1
     have = len([f for f in os.listdir(cdir) if f.endswith(".bin")]) if os.path.isdir(cdir) else 0
-    if have >= want or rank != 0:
+    if (have >= want and cfg["tree"] == "wst") or rank != 0:
         return cdir
     os.makedirs(cdir, exist_ok=True)
     t0 = time.time()
     from rangefilteredann_b200 import load_engine
     eng = load_engine()
     if eng.device_count() > 0:
-        log(f"graph cache {cdir} has {have}/{want} files: building the rest on the GPU (untimed setup)")
-        eng.VamanaRangeFilterTreeIndexFloatEuclidian(data, labels, cfg["cutoff"], 2, eng.BuildParams(64, 500, 1.0, cdir))
+        log(f"graph cache {cdir} has {have} files: loading / building the rest on the GPU (untimed setup)")
+        make_indices(eng, cfg, cdir, data, labels)
     else:
-        log(f"graph cache {cdir} has {have}/{want} files: building with the reference builder (untimed setup)")
+        log(f"graph cache {cdir} has {have} files: building with the reference builder (untimed setup)")
         ref = load_ref()
         if ref is None:
             raise SystemExit("no graph cache, no GPU and no oracle/_ref to build it with")
-        ref.VamanaRangeFilterTreeIndexFloatEuclidian(data, labels, cfg["cutoff"], 2, ref.BuildParams(64, 500, 1.0, cdir))
+        make_indices(ref, cfg, cdir, data, labels)
     log(f"graph cache built in {time.time() - t0:.1f}s")
     return cdir
 
 
-def ground_truth_torch(data, queries, labels, windows_by_power, device):
+def ground_truth_torch(data, queries, labels, windows_by_power, device, metric="l2"):
     """Closed-interval brute-force top-10 (filter_generation_utils.py:142-168) in fp32 on
     the GPU with torch — independent of the engine under test."""
     import torch
@@ -210,10 +316,11 @@ def ground_truth_torch(data, queries, labels, windows_by_power, device):
     chunk = max(1, min(len(queries), (1 << 30) // max(1, len(data))))
     for p, w in windows_by_power.items():
         W = torch.from_numpy(w).to(device)
-        gt = np.empty((len(queries), K), np.int64)
-        for s in range(0, len(queries), chunk):
-            e = min(len(queries), s + chunk)
-            d = xn[None, :] - 2.0 * (Q[s:e] @ X.T)
+        nq_p = len(w)
+        gt = np.empty((nq_p, K), np.int64)
+        for s in range(0, nq_p, chunk):
+            e = min(nq_p, s + chunk)
+            d = (xn[None, :] - 2.0 * (Q[s:e] @ X.T)) if metric == "l2" else -(Q[s:e] @ X.T)
             mask = (L[None, :] >= W[s:e, 0:1]) & (L[None, :] <= W[s:e, 1:2])
             d = torch.where(mask, d, torch.full_like(d, float("inf")))
             vals, idx = torch.topk(d, K, dim=1, largest=False)
@@ -556,7 +663,7 @@ def run_engine(args, rank, world, local_rank):
     barrier()
 
     # ---- reduce over ranks (max time)
-    ms_total, e2e_ms = sharding.reduce_max([ms_total, e2e_s * 1000.0], device=f"cuda:{local_rank}" if world > 1 else None)
+    ms_total, e2e_ms = reduce_max([ms_total, e2e_s * 1000.0], device=f"cuda:{local_rank}" if world > 1 else None)
     if rank != 0:
         return
 

@@ -107,6 +107,9 @@ int ws_index_create(int device, int metric, uint64_t n, uint32_t dim, const floa
                     const float* labels, const uint32_t* decode, int label_sorted,
                     ws_index** out);
 void ws_index_destroy(ws_index* idx);
+/* Replace the id table (arena rank -> the id written into result rows): a label shard built over a slice of a data
+ * set re-labels its rows with data-set-wide ids, so that rows of different shards can be merged. */
+int ws_index_set_decode(ws_index* idx, const uint32_t* decode);
 
 /* One Vamana graph over arena ranks [start, start+count) — a PostfilterVamanaIndex's
  * Graph<int32> (postfilter_vamana.h:35,54-79; graph.h:115-206).  `degrees`[count] and

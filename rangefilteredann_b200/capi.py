@@ -53,6 +53,7 @@ def lib() -> C.CDLL:
         L.ws_index_set_wst.argtypes = [vp, u32, u32, i32, vp, vp, vp]
         L.ws_index_set_super.argtypes = [vp, u32, i32, vp, vp, vp, vp]
         L.ws_index_finalize.argtypes = [vp]
+        L.ws_index_set_decode.argtypes = [vp, vp]
         L.ws_prefilter_batch.argtypes = [vp, vp, vp, u64, u32, vp, vp, u32]
         L.ws_postfilter_batch.argtypes = [vp, i32, vp, vp, u64, C.POINTER(QueryParamsC), C.c_int, vp, vp, u32]
         L.ws_tree_batch.argtypes = [vp, C.c_int, vp, vp, u64, C.POINTER(QueryParamsC), vp, vp, u32]
@@ -77,6 +78,23 @@ def lib() -> C.CDLL:
         L.ws_debug_decompose_host.argtypes = [vp, C.c_int, vp, u64, C.POINTER(QueryParamsC), u32, vp, vp]
         L.ws_device_count.argtypes = [C.POINTER(C.c_int)]
         L.ws_index_device.argtypes = [vp, C.POINTER(C.c_int)]
+        # multi-GPU (ws_group / NCCL inside the library)
+        L.ws_index_replicate.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        L.ws_group_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(vp)]
+        L.ws_group_destroy.argtypes = [vp]
+        L.ws_group_destroy.restype = None
+        L.ws_group_size.argtypes = [vp, C.POINTER(C.c_int)]
+        L.ws_group_member.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        L.ws_group_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+        L.ws_group_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.ws_group_prefilter_batch.argtypes = [vp, vp, vp, u64, u32, vp, vp]
+        L.ws_group_postfilter_batch.argtypes = [vp, i32, vp, vp, u64, C.POINTER(QueryParamsC), C.c_int, vp, vp]
+        L.ws_group_tree_batch.argtypes = [vp, C.c_int, vp, vp, u64, C.POINTER(QueryParamsC), vp, vp]
+        L.ws_nccl_unique_id.argtypes = [vp]
+        L.ws_nccl_version.argtypes = [C.POINTER(C.c_int)]
+        L.ws_index_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.ws_index_comm_destroy.argtypes = [vp]
+        L.ws_allgather_merge.argtypes = [vp, vp, vp, u64, u32, u32, vp, vp]
         _lib = L
     return _lib
 
@@ -185,12 +203,104 @@ class Handle:
         check(lib().ws_merge_partial_topk(self.raw, ids_dev, dists_dev, parts, nq, k, pad_id, out_ids_dev, out_dists_dev),
               "ws_merge_partial_topk")
 
+    # ---- one process per GPU: NCCL inside the library
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, NCCL_ID_BYTES)
+        check(lib().ws_index_comm_init(self.raw, nranks, rank, buf), "ws_index_comm_init")
+
+    def comm_destroy(self):
+        check(lib().ws_index_comm_destroy(self.raw), "ws_index_comm_destroy")
+
+    def allgather_merge(self, ids_dev, dists_dev, nq: int, k: int, pad_id: int, out_ids_dev, out_dists_dev):
+        check(lib().ws_allgather_merge(self.raw, ids_dev, dists_dev, nq, k, pad_id, out_ids_dev, out_dists_dev),
+              "ws_allgather_merge")
+
+    def set_decode(self, decode: np.ndarray):
+        decode = np.ascontiguousarray(decode, dtype=np.uint32)
+        check(lib().ws_index_set_decode(self.raw, ptr(decode)), "ws_index_set_decode")
+
+    def replicate(self, device: int) -> "Handle":
+        out = C.c_void_p()
+        check(lib().ws_index_replicate(self.raw, device, C.byref(out)), "ws_index_replicate")
+        return Handle(out.value, True)
+
     def postfilter_batch(self, node: int, queries, windows, nq: int, qp: QueryParamsC, pad: int, ids, dists,
                          device_ptrs=False):
         f = WS_FLAG_DEVICE_PTRS if device_ptrs else 0
         a = [x if isinstance(x, C.c_void_p) else ptr(x) for x in (queries, windows, ids, dists)]
         check(lib().ws_postfilter_batch(self.raw, node, a[0], a[1], nq, C.byref(qp), pad, a[2], a[3], f),
               "ws_postfilter_batch")
+
+
+NCCL_ID_BYTES = 128
+GROUP_REPLICATED, GROUP_LABEL_SHARDED = 0, 1
+
+
+def nccl_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 calls it and hands the bytes to the other ranks)."""
+    buf = C.create_string_buffer(NCCL_ID_BYTES)
+    check(lib().ws_nccl_unique_id(buf), "ws_nccl_unique_id")
+    return buf.raw
+
+
+def nccl_version() -> int:
+    v = C.c_int()
+    check(lib().ws_nccl_version(C.byref(v)), "ws_nccl_version")
+    return v.value
+
+
+class Group:
+    """ws_group*: several arenas, one per device, behind one batch call (include/wsann.h)."""
+
+    def __init__(self, raw: int, owned: bool, keep=None):
+        self.raw = C.c_void_p(raw)
+        self.owned = owned
+        self._keep = keep  # member handles that must outlive the group
+
+    @classmethod
+    def create(cls, members: list, mode: int) -> "Group":
+        arr = (C.c_void_p * len(members))(*[m.raw for m in members])
+        out = C.c_void_p()
+        check(lib().ws_group_create(arr, len(members), mode, C.byref(out)), "ws_group_create")
+        return cls(out.value, True, list(members))
+
+    @classmethod
+    def borrow(cls, index_obj) -> "Group | None":
+        raw = index_obj._group_handle()
+        return cls(raw, False) if raw else None
+
+    def __del__(self):
+        if self.owned and self.raw:
+            lib().ws_group_destroy(self.raw)
+            self.raw = None
+
+    def size(self) -> int:
+        n = C.c_int()
+        check(lib().ws_group_size(self.raw, C.byref(n)), "ws_group_size")
+        return n.value
+
+    def member(self, i: int) -> Handle:
+        out = C.c_void_p()
+        check(lib().ws_group_member(self.raw, i, C.byref(out)), "ws_group_member")
+        return Handle(out.value, False)
+
+    def set_option(self, name: str, value: int):
+        check(lib().ws_group_set_option(self.raw, name.encode(), int(value)), "ws_group_set_option")
+
+    def info(self) -> dict:
+        peer, exch = C.c_int(), C.c_int()
+        ms = (C.c_double * 3)()
+        check(lib().ws_group_info(self.raw, C.byref(peer), C.byref(exch), ms), "ws_group_info")
+        return {"peer_access": bool(peer.value), "exchange": "nccl_allgather" if exch.value else "peer_loads",
+                "search_ms": ms[0], "exchange_merge_ms": ms[1], "total_ms": ms[2]}
+
+    def prefilter_batch(self, queries, windows, nq: int, k: int, ids, dists):
+        check(lib().ws_group_prefilter_batch(self.raw, ptr(queries), ptr(windows), nq, k, ptr(ids), ptr(dists)),
+              "ws_group_prefilter_batch")
+
+    def tree_batch(self, method: str, queries, windows, nq: int, qp: QueryParamsC, ids, dists):
+        check(lib().ws_group_tree_batch(self.raw, METHODS[method], ptr(queries), ptr(windows), nq, C.byref(qp), ptr(ids), ptr(dists)),
+              "ws_group_tree_batch")
 
 
 def pinned_array(shape, dtype) -> np.ndarray:

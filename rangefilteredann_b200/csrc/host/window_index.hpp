@@ -211,8 +211,8 @@ class Arena {
     ws_index_device(idx_, &own);
     if (own < 0 || devices.size() < 2) return;
     std::vector<ws_index*> members{idx_};
-    for (int d : devices) {
-      if (d == own) continue;
+    for (size_t i = 1; i < devices.size(); i++) {  // devices[0] is this arena's own device
+      const int d = devices[i];
       ws_index* r = nullptr;
       check(ws_index_replicate(idx_, d, &r), "ws_index_replicate");
       replicas_.push_back(r);

@@ -69,6 +69,8 @@ struct WsBeamArgs {
   uint32_t cand_cap;       // power of two >= expand * R
   uint32_t expand;         // nodes expanded per step (1 = reference order)
   int32_t skip_query_id;   // emulate `a == p.id()` (beamSearch.h:128)
+  uint32_t query_id_base;  // p.id() of this launch's first query: a query's position in the CALLER's batch (a group
+                           // hands each member a slice of the batch)
   long long max_beam, final_mult, limit, degree_limit;
   uint32_t* bitmap;        // GLOBAL_SEEN: [gridDim.x][bitmap_words]
   uint64_t bitmap_words;

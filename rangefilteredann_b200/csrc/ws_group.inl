@@ -373,7 +373,12 @@ static int ws_group_batch(ws_group* g, const WsGroupCall& c, const float* querie
       const uint64_t lo = (uint64_t)i * base + std::min<uint64_t>(i, rem);
       const uint64_t cnt = base + ((uint64_t)i < rem ? 1 : 0);
       if (cnt == 0) return (int)WS_OK;
-      return ws_group_member_call(g->m[i], c, queries + lo * dim, windows + 2 * lo, cnt, ids + lo * k, dists + lo * k, 0);
+      // beamSearch.h:128 compares neighbour ids with the query's position in the batch: keep the caller's numbering
+      std::lock_guard<std::recursive_mutex> lock(g->m[i]->mu);
+      g->m[i]->query_id_base = (uint32_t)lo;
+      const int rc = ws_group_member_call(g->m[i], c, queries + lo * dim, windows + 2 * lo, cnt, ids + lo * k, dists + lo * k, 0);
+      g->m[i]->query_id_base = 0;
+      return rc;
     });
   }
   // ---- label-sharded: every member answers the whole batch on its shard

@@ -778,7 +778,7 @@ __global__ void __launch_bounds__(WS_WARPS_PER_CTA * 32, (CS <= 7 ? WS_WARP_MINB
     float4 q[KQ];
     ws_load_query_global<KQ, EXACT>(A.queries, A.dim, A.dpad, task.query, tl, q);
     const float4* vbase_tl = reinterpret_cast<const float4*>(A.vecs + (size_t)node.start * A.dpad) + tl;
-    const int skip_id = A.skip_query_id ? (int)task.query : -1;
+    const int skip_id = A.skip_query_id ? (int)(task.query + A.query_id_base) : -1;
 
     long long beam = task.beam;
     int phase = (task.flags & WS_TF_FINAL) ? 1 : 0;
@@ -1233,7 +1233,7 @@ __global__ void __launch_bounds__(WS_CTA2_THREADS, 1) ws_beam_cta2_kernel(WsBeam
     float4 q[KQ];
     ws_load_query_global<KQ, EXACT>(A.queries, A.dim, A.dpad, task.query, tl, q);
     const float4* vbase_tl = reinterpret_cast<const float4*>(A.vecs + (size_t)node.start * A.dpad) + tl;
-    const int skip_id = A.skip_query_id ? (int)task.query : -1;
+    const int skip_id = A.skip_query_id ? (int)(task.query + A.query_id_base) : -1;
 
     long long beam = task.beam;
     int phase = (task.flags & WS_TF_FINAL) ? 1 : 0;

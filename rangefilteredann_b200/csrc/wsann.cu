@@ -141,6 +141,7 @@ struct ws_index {
   int comm_rank = 0, comm_size = 1;
   WsDevBuf x_all_ids, x_all_dists;
   const float* hint_windows = nullptr;
+  uint32_t query_id_base = 0;  // position of this batch's first query in the caller's batch (ws_group slices)
   unsigned long long* d_stats = nullptr;
   // sticky error word, never cleared by a batch: bit 0 = task-slot capacity overflow (tasks dropped), bit 1 = a task
   // outgrew the last beam tier and was dropped.  Read (and cleared) by host-buffer batches before they return and by
@@ -969,7 +970,7 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
       ba.q_out = t_next >= 0 ? queues + (size_t)t_next * slots : nullptr;
       ba.q_out_count = t_next >= 0 ? ctrl + t_next : nullptr;
       ba.beam_cap = beam_cap; ba.hash_mask = hash_entries ? hash_entries - 1 : 0; ba.cand_cap = cand_cap;
-      ba.expand = E; ba.skip_query_id = (int32_t)idx->opt_skip_query_id;
+      ba.expand = E; ba.skip_query_id = (int32_t)idx->opt_skip_query_id; ba.query_id_base = idx->query_id_base;
       ba.max_beam = qp.postfiltering_max_beam; ba.final_mult = qp.final_beam_multiply;
       ba.limit = qp.limit > 0 ? qp.limit : (1ll << 62);
       ba.degree_limit = qp.degree_limit > 0 ? qp.degree_limit : (1ll << 62);
@@ -1394,6 +1395,19 @@ int ws_merge_partial_topk(ws_index* idx, const uint32_t* ids, const float* dists
   int grid = (int)std::min<uint64_t>(nq, (uint64_t)idx->num_sms * 16);
   WS_CUDA(wsl_merge_parts(grid, idx->stream, a));
   idx->launches++;
+  return WS_OK;
+}
+
+int ws_index_set_decode(ws_index* idx, const uint32_t* decode) {
+  WS_NEED_DEVICE(idx);
+  if (!decode) return ws_fail(WS_ERR_BADARG, "null decode table");
+  WS_CUDA(cudaStreamSynchronize(idx->stream));
+  if (!idx->d_decode) {
+    WS_CUDA(cudaMalloc(&idx->d_decode, idx->n * sizeof(uint32_t)));
+    idx->hbm_bytes += idx->n * sizeof(uint32_t);
+    idx->has_decode = true;
+  }
+  WS_CUDA(cudaMemcpy(idx->d_decode, decode, idx->n * sizeof(uint32_t), cudaMemcpyHostToDevice));
   return WS_OK;
 }
 

@@ -1,28 +1,33 @@
-"""Label-range sharded window search (BASELINE.json config 5 shape).
+"""Label-range sharded window search, one process per GPU (BASELINE.json config 5 shape).
 
-For datasets that do not fit one GPU, rank r owns the contiguous slice of the label-sorted
-points [r*N/W, (r+1)*N/W) with its own B-WST over that slice.  Every rank answers the whole
-(small) query batch on its shard — windows that miss the shard's label range come back as
-pads — then the per-rank [nq][k] rows are all-gathered (NCCL over NVLink/NVSwitch on GPUs;
-gloo in the CPU tests) and merged per query on every rank (`ws_merge_partial_topk`).
+For data sets that do not fit one GPU, rank r owns the contiguous slice [r*N/W, (r+1)*N/W) of the label-sorted
+points with its own B-WST over that slice.  Every rank answers the whole (small) query batch on its shard —
+windows that miss the shard's label range come back as pads — then the per-rank [nq][k] rows are all-gathered
+with NCCL over NVLink/NVSwitch and merged per query on every rank.  Both steps run inside libwsann_cuda.so
+(`ws_allgather_merge`: ncclAllGather on the index stream + the K4b merge kernel, device memory only); the host
+program only has to hand rank 0's 128-byte NCCL id to the other ranks (any broadcast it already has).
 
-This equals the reference's fenwick decomposition cut at the shard boundaries: a window
-spanning several shards is answered by <= W smaller sub-trees instead of one large node, so
-recall can only rise (range_filter_tree.h:297-401).  torch.distributed is plumbing only.
+This equals the reference's fenwick decomposition cut at the shard boundaries: a window spanning several shards
+is answered by <= W smaller sub-trees instead of one large node, so recall can only rise
+(range_filter_tree.h:297-401).  Prefilter rows are identical to the single-GPU rows.
+
+The single-process form of the same thing (all GPUs of the box behind one `batch_search` call, partial rows
+gathered by peer loads) is selected with WSANN_DEVICES=… WSANN_SHARD_MODE=label (csrc/host/window_index.hpp).
 """
 from __future__ import annotations
 
-import ctypes as C
 import os
 
 import numpy as np
+
+from . import capi
+from .sharding import shard_bounds
 
 FLT_MAX = np.float32(3.4028235e38)
 
 
 def shard_of_sorted_labels(labels: np.ndarray, rank: int, world: int):
     """Original ids of the points rank `rank` owns (contiguous in label order; ties by id)."""
-    from .sharding import shard_bounds
     order = np.argsort(labels, kind="stable")
     lo, hi = shard_bounds(len(labels), rank, world)
     return order[lo:hi]
@@ -44,61 +49,81 @@ def merge_partial_topk_numpy(ids: np.ndarray, dists: np.ndarray, k: int, pad_id:
 
 
 class LabelShardedTree:
-    """One rank's shard + the collective batch_search.  Construct on every rank."""
+    """One rank's shard + the collective batch_search.  Construct on every rank; `unique_id` is
+    `capi.nccl_unique_id()` of rank 0, handed to every rank by the host program (None: no communicator, only
+    `local_search` works — single-process tests)."""
 
     def __init__(self, data: np.ndarray, labels: np.ndarray, rank: int, world: int, cache_root: str,
                  cutoff: int = 1000, split_factor: int = 2, metric: str = "Euclidian",
-                 max_degree: int = 64, limit: int = 500, alpha: float = 1.0):
+                 max_degree: int = 64, limit: int = 500, alpha: float = 1.0, unique_id: bytes | None = None):
         from . import load_engine
         self.rank, self.world = rank, world
         self.eng = load_engine()
-        self.owned = shard_of_sorted_labels(labels, rank, world).astype(np.uint32)  # local id -> global id
+        self.owned = shard_of_sorted_labels(labels, rank, world).astype(np.uint32)  # shard-local id -> data-set id
         sfx = "FloatMips" if metric == "mips" else "FloatEuclidian"
         cache = os.path.join(cache_root, f"shard{rank}of{world}") + "/"
         os.makedirs(cache, exist_ok=True)
         self.tree = getattr(self.eng, "VamanaRangeFilterTreeIndex" + sfx)(
             np.ascontiguousarray(data[self.owned]), np.ascontiguousarray(labels[self.owned]), cutoff, split_factor,
             self.eng.BuildParams(max_degree, limit, alpha, cache))
+        self.h = capi.Handle.borrow(self.tree)
+        # the shard's rows are already label-sorted (ties by id), so arena rank == shard-local id: result rows carry
+        # data-set ids straight from the kernels
+        self.h.set_decode(self.owned)
+        if rank + 1 < world:  # prefiltering.h:159-184's r = n-1 rule excludes the DATA SET's last point only
+            self.h.set_option("prefilter_open_tail", 1)
+        self.dim = data.shape[1]
+        self._cap = 0
+        if unique_id is not None and world > 1:
+            self.h.comm_init(world, rank, unique_id)
+        self._has_comm = unique_id is not None and world > 1
 
+    # ---- device-resident plumbing
+    def _ensure(self, nq: int, k: int):
+        if nq * k <= self._cap:
+            return
+        h = self.h
+        self.dq = h.dalloc(nq * self.dim * 4)
+        self.dw = h.dalloc(nq * 8)
+        self.part_ids, self.part_d = h.dalloc(nq * k * 4), h.dalloc(nq * k * 4)
+        self.out_ids, self.out_d = h.dalloc(nq * k * 4), h.dalloc(nq * k * 4)
+        self._cap = nq * k
+
+    def upload(self, queries: np.ndarray, windows: np.ndarray, k: int):
+        nq = len(windows)
+        self._ensure(nq, k)
+        self.h.h2d(self.dq, np.ascontiguousarray(queries[:nq], dtype=np.float32))
+        self.h.h2d(self.dw, np.ascontiguousarray(windows, dtype=np.float32))
+        return nq
+
+    def search_device(self, nq: int, method: str, qp_c: capi.QueryParamsC, k: int):
+        """Enqueue: local search -> ncclAllGather -> merge, all on the index stream (no host sync)."""
+        if method == "prefilter":
+            self.h.prefilter_batch(self.dq, self.dw, nq, k, self.part_ids, self.part_d, device_ptrs=True)
+        else:
+            self.h.tree_batch(method, self.dq, self.dw, nq, qp_c, self.part_ids, self.part_d, device_ptrs=True)
+        if self._has_comm:
+            self.h.allgather_merge(self.part_ids, self.part_d, nq, k, 0xFFFFFFFF if method == "prefilter" else 0, self.out_ids, self.out_d)
+
+    def fetch(self, nq: int, k: int):
+        ids, d = np.empty((nq, k), np.uint32), np.empty((nq, k), np.float32)
+        src = (self.out_ids, self.out_d) if self._has_comm else (self.part_ids, self.part_d)
+        self.h.d2h(ids, src[0])
+        self.h.d2h(d, src[1])
+        return ids, d
+
+    # ---- host-buffer calls
     def local_search(self, queries, windows, method, qp):
-        """This shard's partial rows with GLOBAL ids (pads keep dist FLT_MAX)."""
+        """This shard's partial rows with data-set ids (pads keep dist FLT_MAX)."""
+        if method == "prefilter":
+            raise ValueError("local_search answers tree methods")
         ids, dists = self.tree.batch_search(queries, windows, len(windows), method, qp)
-        gids = self.owned[np.minimum(ids, len(self.owned) - 1)]
-        gids[dists == FLT_MAX] = 0
-        return gids.astype(np.uint32), dists
+        ids = ids.copy()
+        ids[dists == FLT_MAX] = 0
+        return ids, dists
 
-    def batch_search(self, queries, windows, method, qp, k: int):
-        """Collective: local search, all-gather of [nq][k] rows, per-query merge on device."""
-        gids, dists = self.local_search(queries, windows, method, qp)
-        from . import capi
-        return allgather_merge(gids, dists, k, self.world, lambda: capi.Handle.borrow(self.tree))
-
-
-def allgather_merge(gids: np.ndarray, dists: np.ndarray, k: int, world: int, handle_factory=None):
-    """All-gather every rank's [nq][k] (global id, dist) rows and merge them per query.
-    NCCL backend: tensors stay on the GPU and `ws_merge_partial_topk` merges; gloo backend
-    (CPU tests): numpy merge."""
-    import torch
-    import torch.distributed as dist
-    nq = len(gids)
-    if world == 1 or not dist.is_initialized():
-        return gids, dists
-    on_gpu = dist.get_backend() == "nccl"
-    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
-    t_ids = torch.from_numpy(np.ascontiguousarray(gids).view(np.int32)).to(dev)  # NCCL has no uint32; bits preserved
-    t_d = torch.from_numpy(np.ascontiguousarray(dists)).to(dev)
-    all_ids = torch.empty((world * nq, k), dtype=torch.int32, device=dev)  # rank-major concatenation
-    all_d = torch.empty((world * nq, k), dtype=torch.float32, device=dev)
-    dist.all_gather_into_tensor(all_ids, t_ids)
-    dist.all_gather_into_tensor(all_d, t_d)
-    all_ids, all_d = all_ids.view(world, nq, k), all_d.view(world, nq, k)
-    if not on_gpu:
-        return merge_partial_topk_numpy(all_ids.numpy().view(np.uint32), all_d.numpy(), k)
-    h = handle_factory()
-    out_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
-    out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    torch.cuda.synchronize()  # the gathered tensors were produced on torch's stream
-    h.merge_partial_topk(C.c_void_p(all_ids.data_ptr()), C.c_void_p(all_d.data_ptr()), world, nq, k, 0,
-                         C.c_void_p(out_ids.data_ptr()), C.c_void_p(out_d.data_ptr()))
-    h.sync()
-    return out_ids.cpu().numpy().view(np.uint32), out_d.cpu().numpy()
+    def batch_search(self, queries, windows, method, qp_c: capi.QueryParamsC, k: int):
+        """Collective: every rank calls it with the same batch and gets the same merged rows."""
+        nq = self.upload(queries, windows, k)
+        self.search_device(nq, method, qp_c, k)
+        return self.fetch(nq, k)

@@ -1,7 +1,7 @@
-"""Host-side plumbing of the multi-GPU path: queries are independent units,
-so the batch is sharded over ranks with the index replicated and no data-path collective.
-torch.distributed is used only for the barrier and the max-over-ranks timing reduction
-(NCCL on the GPU box, gloo in the CPU tests)."""
+"""Host-side arithmetic of the multi-GPU paths: queries are independent units, so a batch is
+sharded over ranks / devices with the index replicated and no data-path collective; label shards are contiguous
+ranges of the label-sorted points.  Pure index arithmetic — the rank plumbing (barrier, timing reduction) belongs
+to the launcher (bench.py uses torch.distributed for it)."""
 from __future__ import annotations
 
 import numpy as np
@@ -23,25 +23,3 @@ def shard_queries(queries: np.ndarray, windows: np.ndarray, rank: int, world: in
 def weak_batch(queries_all: np.ndarray, nq: int, rank: int) -> np.ndarray:
     """Weak-scaling batch of bench.py: rank r answers its own block of nq queries."""
     return np.ascontiguousarray(queries_all[rank * nq:(rank + 1) * nq])
-
-
-def reduce_max(values, device=None) -> list[float]:
-    """max over ranks of a small vector of timings (all ranks get the result)."""
-    import torch
-    import torch.distributed as dist
-    t = torch.tensor(list(values), dtype=torch.float64, device=device)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return [float(x) for x in t.cpu()]
-
-
-def gather_rows(local: np.ndarray, world: int) -> np.ndarray | None:
-    """Concatenate per-rank result rows on rank 0 (host gather of nq x k ids; the data path
-    itself needs no collective)."""
-    import torch
-    import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()) or world == 1:
-        return local
-    objs = [None] * world if dist.get_rank() == 0 else None
-    dist.gather_object(local, objs, dst=0)
-    return np.concatenate(objs, axis=0) if dist.get_rank() == 0 else None

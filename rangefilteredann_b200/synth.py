@@ -142,3 +142,39 @@ def recall_std(results: np.ndarray, gt: np.ndarray, k: int = TOP_K) -> float:
         res = set(int(x) for x in results[i][:k])
         tot += len(res & g) / len(g)
     return tot / len(results)
+
+
+def make_adversarial(n: int, d: int, seed: int = 0, clusters: int = 100, intra_var: float = 0.01,
+                     inter_var: float = 1.0):
+    """The reference's adversarial set (generate_datasets/generate_advserial_dataset.py:8-60): `clusters` tight
+    Gaussian clusters, the label of a point is its cluster index - 0.5 + U(0,1) — so label ranges and clusters
+    coincide — and every query is drawn from cluster a while its window is cluster b's label range (a != b): the
+    graph neighbourhood of the query holds no in-window point, which is the worst case for postfiltering.
+    Rows are L2-normalised as there.  Returns (data, queries[clusters*(clusters-1)], labels, windows)."""
+    rng = np.random.default_rng(seed)
+    per = n // clusters
+    means = (np.sqrt(inter_var) * rng.standard_normal((clusters, d))).astype(np.float32)
+    data = np.empty((per * clusters, d), np.float32)
+    labels = np.empty(per * clusters, np.float32)
+    for c in range(clusters):
+        data[c * per:(c + 1) * per] = means[c] + np.sqrt(intra_var) * rng.standard_normal((per, d), dtype=np.float32)
+        labels[c * per:(c + 1) * per] = (c - 0.5 + rng.uniform(size=per)).astype(np.float32)
+    qc, gc = np.nonzero(~np.eye(clusters, dtype=bool))
+    queries = means[qc] + np.sqrt(intra_var) * rng.standard_normal((len(qc), d), dtype=np.float32)
+    windows = np.stack([gc - 0.5, gc + 0.5], axis=1).astype(np.float32)
+    data /= np.linalg.norm(data, axis=1, keepdims=True)
+    queries /= np.linalg.norm(queries, axis=1, keepdims=True)
+    return data, queries.astype(np.float32), labels, windows
+
+
+def make_blowup_windows(labels: np.ndarray, power: int, nq: int, seed: int) -> np.ndarray:
+    """Large-blow-up windows (SURVEY.md §8d, C5-adversarial ii): windows of fraction 2**power that straddle the
+    median label rank, so the smallest B-WST bucket containing one is the ROOT (blow-up = 2**-power): optimized
+    postfiltering must search the whole data set with selectivity 2**power."""
+    rng = np.random.default_rng(seed)
+    s = np.sort(labels.astype(np.float64))
+    n = len(s)
+    m = max(2, int(n * 2.0 ** power))
+    start = n // 2 - rng.integers(1, m, size=nq)
+    start = np.clip(start, 0, n - m - 1)
+    return np.stack([s[start], s[start + m]], axis=1).astype(np.float32)

@@ -8,6 +8,7 @@ import pytest
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+import bench
 from rangefilteredann_b200 import label_shard, sharding
 
 
@@ -30,8 +31,8 @@ def _worker(rank, world, port, out):
         assert len(q) == hi - lo and np.array_equal(q, queries[lo:hi]) and np.array_equal(w, windows[lo:hi])
         # every rank "answers" its shard: fake ids = global row index
         local = np.arange(lo, hi, dtype=np.uint32)[:, None].repeat(10, axis=1)
-        allrows = sharding.gather_rows(local, world)
-        t = sharding.reduce_max([1.0 + rank, 5.0 - rank])
+        allrows = bench.gather_rows(local, world)
+        t = bench.reduce_max([1.0 + rank, 5.0 - rank])
         dist.barrier()
         if rank == 0:
             ok = allrows.shape == (1001, 10) and np.array_equal(allrows[:, 0], np.arange(1001))
@@ -45,7 +46,13 @@ def _worker(rank, world, port, out):
         d = np.sort(prng.uniform(size=(nq, k)).astype(np.float32), axis=1)
         d[rank::5, 6:] = label_shard.FLT_MAX  # some short rows
         gids[d == label_shard.FLT_MAX] = 0
-        mi, md = label_shard.allgather_merge(gids, d, k, world)
+        # (on GPUs the exchange is ncclAllGather inside libwsann_cuda.so; here the launcher's plumbing carries the
+        # rows and the 128-byte communicator id the same way bench.py hands it around)
+        uid = bench.broadcast_bytes(bytes(range(128)) if rank == 0 else None)
+        assert uid == bytes(range(128))
+        rows = [None] * world
+        dist.all_gather_object(rows, (gids, d))
+        mi, md = label_shard.merge_partial_topk_numpy(np.stack([r[0] for r in rows]), np.stack([r[1] for r in rows]), k)
         # every rank must hold the same merged rows, equal to a direct merge of both inputs
         parts_i, parts_d = [], []
         for r in range(world):
