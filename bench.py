@@ -68,6 +68,12 @@ BEAMS = [10, 20, 40, 80, 160, 320]
 MULTS = [1, 2, 4]
 
 
+def fractions_label() -> str:
+    if POWERS == ALL_POWERS:
+        return "2^-16..2^0"
+    return ", ".join(frac_name(p) for p in POWERS)
+
+
 def frac_name(p) -> str:
     return f"2^{p}" if isinstance(p, int) else str(p)
 
@@ -189,6 +195,15 @@ def gather_rows(local: np.ndarray, world: int):
     objs = [None] * world if dist.get_rank() == 0 else None
     dist.gather_object(local, objs, dst=0)
     return np.concatenate(objs, axis=0) if dist.get_rank() == 0 else None
+
+
+def broadcast_object(obj, src: int = 0):
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return obj
+    box = [obj]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
 
 
 def broadcast_bytes(payload: bytes | None, src: int = 0) -> bytes:
@@ -447,10 +462,11 @@ class ClockSampler:
 class EngineRunner:
     """Device-resident and host-buffer execution of one (fraction, operating point)."""
 
-    def __init__(self, tree_index, nq: int, d: int):
+    def __init__(self, tree_index, nq: int, d: int, cfg: dict):
         from rangefilteredann_b200 import capi
         self.capi = capi
         self.tree = tree_index
+        self.cfg = cfg
         self.h = capi.Handle.borrow(tree_index)
         self.nq, self.d = nq, d
         self.dq = self.h.dalloc(nq * d * 4)
@@ -481,6 +497,9 @@ class EngineRunner:
             qp = self.capi.query_params(k=K, beam=beam, final_multiply=mult)
             self.h.tree_batch(method, self.dq, self.dwin[power], self.nq, qp, self.dids, self.ddists, device_ptrs=True)
 
+    def sync(self):
+        self.h.sync()
+
     def fetch(self):
         ids = np.empty((self.nq, K), np.uint32)
         self.h.d2h(ids, self.dids)
@@ -495,29 +514,33 @@ class EngineRunner:
         return best
 
 
-def choose_operating_points(runner: EngineRunner, gts, rank):
+def choose_operating_points(runner, gts, rank, cfg):
     """Untimed sweep: per fraction and method, the first (smallest) beam reaching the recall
     target for each final_multiply; the fastest of those is the method's operating point."""
     table = {}
+    beams = cfg.get("beams", BEAMS)
+    mults = cfg.get("mults", MULTS)
     for p in POWERS:
         per_method = {}
-        # prefilter: exact
-        runner.launch_dev(p, ("prefilter", 0, 0))
-        r = recall_at_k(runner.fetch(), gts[p])
-        ms = runner.time_dev(p, ("prefilter", 0, 0))
-        per_method["prefilter"] = dict(op=("prefilter", 0, 0), recall=r, ms=ms)
-        for alt in ("prefilter_direct", "prefilter_tc"):
+        # prefilter: exact.  Slow variants are not timed where they are hopeless (the one-launch kernel and the
+        # task path re-read every window once per query: seconds per batch on multi-million-row windows)
+        auto = auto_prefilter_route(runner.mean_window[p])
+        heavy = runner.mean_window[p] * runner.nq * cfg["d"] * 4 > 4e12
+        for alt in PREFILTER_OPS:
+            if alt not in getattr(runner, "prefilter_ops", PREFILTER_OPS) or (heavy and alt != auto):
+                continue
             runner.launch_dev(p, (alt, 0, 0))
             r = recall_at_k(runner.fetch(), gts[p])
             ms = runner.time_dev(p, (alt, 0, 0))
             per_method[alt] = dict(op=(alt, 0, 0), recall=r, ms=ms)
         # what PrefilterIndex.batch_search picks by itself for this fraction's windows (the step uses THIS, not the
         # fastest of the three)
-        per_method["prefilter_auto"] = dict(per_method[auto_prefilter_route(runner.mean_window[p])])
-        for method in ("fenwick", "optimized_postfilter"):
+        if auto in per_method:
+            per_method["prefilter_auto"] = dict(per_method[auto])
+        for method in tree_methods(cfg):
             best = None
-            for mult in (MULTS if method == "optimized_postfilter" else [1]):
-                for beam in BEAMS:
+            for mult in ([1] if method == "fenwick" else mults):
+                for beam in beams:
                     op = (method, beam, mult)
                     runner.launch_dev(p, op)
                     r = recall_at_k(runner.fetch(), gts[p])
@@ -533,7 +556,7 @@ def choose_operating_points(runner: EngineRunner, gts, rank):
                 per_method[method] = best
         table[p] = per_method
         if rank == 0:
-            log(f"2^{p}: " + ", ".join(f"{m}: beam {v['op'][1]} x{v['op'][2]} recall {v['recall']:.4f} {v['ms']:.3f} ms"
+            log(f"{frac_name(p)}: " + ", ".join(f"{m}: beam {v['op'][1]} x{v['op'][2]} recall {v['recall']:.4f} {v['ms']:.3f} ms"
                                         for m, v in per_method.items()))
     return table
 
@@ -547,12 +570,17 @@ def run_engine(args, rank, world, local_rank):
     os.environ["WSANN_DEVICE"] = str(local_rank)
     t_setup = time.time()
     # data and labels are the same on every rank, for every world size and in the reference arm (the graph
-    # cache is keyed by them); each rank answers its own batch of queries (weak scaling)
-    data, queries, labels = synth.make_dataset(cfg["n"], cfg["d"], cfg["nq"], cfg["seed"])
-    if rank > 0:
-        queries = synth.make_rank_queries(cfg["d"], cfg["nq"], cfg["seed"], rank)
+    # cache is keyed by them).  Weak scaling: each rank answers its own batch of queries.  Strong scaling: the ONE
+    # batch of rank 0 is cut into contiguous slices, one per rank (no data-path collective).
     from rangefilteredann_b200 import sharding
-    windows = {p: synth.make_windows(labels, p, cfg["nq"], seed=1000 + 17 * rank + p) for p in POWERS}
+    strong = args.scaling == "strong" and world > 1
+    data, queries, labels, windows = make_inputs(cfg, 0 if strong else rank, 0 if strong else 17 * rank)
+    nq_rank = cfg["nq"]
+    if strong:
+        lo, hi = sharding.shard_bounds(cfg["nq"], rank, world)
+        queries = np.ascontiguousarray(queries[lo:hi])
+        windows = {p: np.ascontiguousarray(w[lo:hi]) for p, w in windows.items()}
+        nq_rank = hi - lo
     cdir = cache_dir(args.config)
     os.makedirs(cdir, exist_ok=True)
     if rank == 0:
@@ -562,27 +590,30 @@ def run_engine(args, rank, world, local_rank):
         if rank == 0:
             ensure_graphs(args.config, cfg, data, labels, 0)
         dist.barrier()
-    tree = eng.VamanaRangeFilterTreeIndexFloatEuclidian(data, labels, cfg["cutoff"], 2, eng.BuildParams(64, 500, 1.0, cdir))
+    # the classes run_our_method.py:249,357,387,516 call (tree methods; "prefiltering")
+    tree, pre = make_indices(eng, cfg, cdir, data, labels)
     log(f"rank {rank}: data + index ready in {time.time() - t_setup:.1f}s")
-    gts = ground_truth_torch(data, queries, labels, windows, f"cuda:{local_rank}")
-    pre = eng.PrefilterIndexFloatEuclidian(data, labels)  # the class run_our_method.py:249 calls for "prefiltering"
+    gts = ground_truth_torch(data, queries, labels, windows, f"cuda:{local_rank}", cfg["metric"])
     sorted_labels = np.sort(labels)
-    runner = EngineRunner(tree, cfg["nq"], cfg["d"])
+    runner = EngineRunner(tree, nq_rank, cfg["d"], cfg)
     runner.upload(queries, windows, sorted_labels)
     h = runner.h
     if args.ops_file and os.path.exists(args.ops_file):
         saved = json.load(open(args.ops_file))
-        table = {int(p): {m: dict(op=tuple(v["op"]), recall=v["recall"], ms=v["ms"]) for m, v in pm.items()}
+        table = {(int(p) if p.lstrip("-").isdigit() else p): {m: dict(op=tuple(v["op"]), recall=v["recall"], ms=v["ms"]) for m, v in pm.items()}
                  for p, pm in saved.items()}
     else:
-        table = choose_operating_points(runner, gts, rank)
+        table = choose_operating_points(runner, gts, rank, cfg)
         if args.ops_file and rank == 0:
             json.dump({str(p): {m: dict(op=list(v["op"]), recall=v["recall"], ms=v["ms"]) for m, v in pm.items()}
                        for p, pm in table.items()}, open(args.ops_file, "w"))
     # per fraction: the fastest of {prefilter as the engine routes it by itself, range-filter tree, optimized postfilter}
-    step_methods = ("prefilter_auto", "fenwick", "optimized_postfilter")
+    step_methods = ("prefilter_auto",) + tree_methods(cfg)
     ops = {p: min((table[p][m] for m in step_methods if m in table[p]), key=lambda v: v["ms"])["op"] for p in POWERS}
-    nq_step = cfg["nq"] * len(POWERS)
+    if strong:  # every rank must run the same operating points: rank 0's choice
+        ops = broadcast_object(ops)
+    nq_step = nq_rank * len(POWERS)
+    nq_step_total = cfg["nq"] * len(POWERS) if strong else nq_rank * len(POWERS) * world
 
     def barrier():
         h.sync()
@@ -631,9 +662,11 @@ def run_engine(args, rank, world, local_rank):
     def e2e_call(p):
         method, beam, mult = ops[p]
         if method in PREFILTER_OPS:
-            return pre.batch_search(queries, windows[p], cfg["nq"], qps_by_op.setdefault((10, 1), eng.QueryParams(K, 10, 1.35, 10_000_000, 10_000, 1, 10000, None, False)))
+            return pre.batch_search(queries, windows[p], nq_rank, qps_by_op.setdefault((10, 1), eng.QueryParams(K, 10, 1.35, 10_000_000, 10_000, 1, 10000, None, False)))
         qp = qps_by_op.setdefault((beam, mult), eng.QueryParams(K, beam, 1.35, 10_000_000, 10_000, mult, 10000, None, False))
-        return tree.batch_search(queries, windows[p], cfg["nq"], method, qp)
+        if method == "super":
+            return tree.batch_search(queries, windows[p], nq_rank, qp)
+        return tree.batch_search(queries, windows[p], nq_rank, method, qp)
 
     def step_e2e():
         for p in POWERS:
@@ -648,9 +681,9 @@ def run_engine(args, rank, world, local_rank):
             hpre.kernel_times(reset=True)
             e2e_call(p)
             kt = hpre.kernel_times(reset=True)
-            routes[f"2^{p}"] = "prefilter_tc" if "gemm_sweep" in kt else ("prefilter" if "decompose" in kt else "prefilter_direct")
-            if routes[f"2^{p}"] != ops[p][0]:
-                log(f"WARNING 2^{p}: auto routing took {routes[f'2^{p}']}, the device-timed step ran {ops[p][0]}")
+            routes[frac_name(p)] = "prefilter_tc" if "gemm_sweep" in kt else ("prefilter" if "decompose" in kt else "prefilter_direct")
+            if routes[frac_name(p)] != ops[p][0]:
+                log(f"WARNING {frac_name(p)}: auto routing took {routes[frac_name(p)]}, the device-timed step ran {ops[p][0]}")
     hpre.set_option("profile_kernels", 0)
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
@@ -668,8 +701,8 @@ def run_engine(args, rank, world, local_rank):
         return
 
     ms_per_step = ms_total / args.steps
-    value = world * nq_step / (ms_per_step / 1000.0)
-    e2e_value = world * nq_step / (e2e_ms / args.steps / 1000.0)
+    value = nq_step_total / (ms_per_step / 1000.0)
+    e2e_value = nq_step_total / (e2e_ms / args.steps / 1000.0)
 
     # ---- roofline of the dominant kernel
     peaks = {}
@@ -680,6 +713,7 @@ def run_engine(args, rank, world, local_rank):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     dpad_bytes = ((cfg["d"] * 4 + 63) // 64) * 64
+    nq_step = nq_rank * len(POWERS)
     beam_ms = sum(v["ms"] for kname, v in ktimes.items() if kname.startswith("beam"))
     beam_launches = sum(v["launches"] for kname, v in ktimes.items() if kname.startswith("beam"))
     scan_ms = ktimes.get("scan", {}).get("ms", 0.0)
@@ -695,11 +729,11 @@ def run_engine(args, rank, world, local_rank):
     tensor_peak = float(peaks.get("bf16_tflops", 1590.0))
     gemm_info = None
     if gemm_ms > 0:
-        gemm_info = {"kernel": "ws_gemm_topk_kernel (tcgen05 kind::tf32)", "bound": "tensor",
+        gemm_info = {"kernel": "ws_gemm_topk_kernel (tcgen05 kind::f16, fp32 accumulate, fp32 re-rank)", "bound": "tensor",
                      "achieved": round(gemm_flops / (gemm_ms / 1000.0) / 1e12, 1), "peak": tensor_peak, "unit": "TFLOP/s",
                      "frac": round(gemm_flops / (gemm_ms / 1000.0) / 1e12 / tensor_peak, 4),
-                     "peak_source": "measured dense bf16 (MEASURED_PEAKS.json bf16_tflops); the kernel runs tf32, whose "
-                                    "dense rate is half of bf16",
+                     "peak_source": "measured dense bf16 (MEASURED_PEAKS.json bf16_tflops); flops = 2*d per (query, "
+                                    "in-window point) — tiles also score the out-of-window points of a group's union",
                      "ms_per_step": round(gemm_ms / args.steps, 4),
                      "flops_per_step": gemm_flops / args.steps}
     # streaming-scan prefilter (task path or one-launch kernel): rows * d_pad * 4, rows counted
@@ -762,22 +796,22 @@ def run_engine(args, rank, world, local_rank):
 
     per_fraction = {}
     for p in POWERS:
-        per_fraction[f"2^{p}"] = {m: {"beam": v["op"][1], "final_multiply": v["op"][2], "recall": round(v["recall"], 4),
-                                      "qps": round(cfg["nq"] / (v["ms"] / 1000.0))} for m, v in table[p].items()}
-        per_fraction[f"2^{p}"]["best"] = ops[p][0]
+        per_fraction[frac_name(p)] = {m: {"beam": v["op"][1], "final_multiply": v["op"][2], "recall": round(v["recall"], 4),
+                                          "qps": round(nq_rank / (v["ms"] / 1000.0))} for m, v in table[p].items()}
+        per_fraction[frac_name(p)]["best"] = ops[p][0]
     line = {
-        "metric": "QPS at recall@10>=0.95, one pass over filter fractions 2^-16..2^0",
+        "metric": "QPS at recall@10>=0.95, one pass over filter fractions " + fractions_label(),
         "value": round(value, 1), "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_string(cfg),
-                   "name": args.config, "queries_per_step": nq_step * world,
+                   "name": args.config, "queries_per_step": nq_step_total, "queries_per_rank_per_fraction": nq_rank,
                    "l2_policy": "working set (vectors + adjacency, >= 0.25 GB, random gathers) exceeds the 126 MB L2; no flush",
                    "parallelism": f"query-sharded dp{world}, index replicated"},
         "e2e": {"value": round(e2e_value, 1), "unit": "queries/s",
-                "h2d_bytes_per_step": int(len(POWERS) * cfg["nq"] * (cfg["d"] * 4 + 8)),
-                "d2h_bytes_per_step": int(len(POWERS) * cfg["nq"] * K * 8),
-                "api": "pybind PrefilterIndexFloatEuclidian.batch_search / VamanaRangeFilterTreeIndexFloatEuclidian.batch_search, "
+                "h2d_bytes_per_step": int(len(POWERS) * nq_rank * (cfg["d"] * 4 + 8)),
+                "d2h_bytes_per_step": int(len(POWERS) * nq_rank * K * 8),
+                "api": f"pybind PrefilterIndex{class_suffix(cfg)}.batch_search / {type(tree).__name__}.batch_search, "
                        "pageable numpy arrays, default engine options (prefilter batches routed by the engine)",
                 "prefilter_routes": routes},
         "gpu_launches": int(launches),
@@ -799,16 +833,330 @@ def run_engine(args, rank, world, local_rank):
 
 
 # ------------------------------------------------------------------------------------------
+# label-range sharded mode (one process per GPU) and the in-engine group mode (one process, N GPUs)
+# ------------------------------------------------------------------------------------------
+class ShardRunner:
+    """One rank of the label-sharded run: local search on the shard + ncclAllGather + merge, all enqueued on the
+    index stream by libwsann_cuda.so (rangefilteredann_b200/label_shard.py).  Timings are max over ranks so that every
+    rank takes the same sweep decisions (the calls are collective)."""
+
+    def __init__(self, shard, nq: int, cfg: dict, world: int, device):
+        from rangefilteredann_b200 import capi
+        self.capi, self.shard, self.nq, self.cfg, self.world, self.device = capi, shard, nq, cfg, world, device
+        self.h = shard.h
+        self.mean_window = {}
+        self.windows = {}
+        self.queries = None
+        self.cur = None
+
+    def upload(self, queries, windows_by_power, sorted_labels):
+        self.queries = queries
+        for p, w in windows_by_power.items():
+            self.windows[p] = w
+            rows = np.searchsorted(sorted_labels, w[:, 1]) - np.searchsorted(sorted_labels, w[:, 0])
+            self.mean_window[p] = float(np.mean(rows.clip(min=0))) / self.world  # per shard
+
+    def _stage(self, power):
+        if self.cur != power:
+            self.shard.upload(self.queries, self.windows[power], K)
+            self.cur = power
+
+    def launch_dev(self, power, op):
+        method, beam, mult = op
+        self._stage(power)
+        if method in PREFILTER_OPS:
+            self.h.set_option("gemm_prefilter", 1 if method == "prefilter_tc" else 0)
+            self.h.set_option("prefilter_direct", 1 if method == "prefilter_direct" else 0)
+            self.shard.search_device(self.nq, "prefilter", None, K)
+        else:
+            self.shard.search_device(self.nq, method, self.capi.query_params(k=K, beam=beam, final_multiply=mult), K)
+
+    def sync(self):
+        self.h.sync()
+
+    def fetch(self):
+        return self.shard.fetch(self.nq, K)[0]
+
+    def time_dev(self, power, op, reps=2):
+        best = 1e30
+        for _ in range(reps):
+            self.h.timer_start()
+            self.launch_dev(power, op)
+            best = min(best, self.h.timer_stop())
+        return reduce_max([best], device=self.device)[0]
+
+
+def run_label_shard(args, rank, world, local_rank):
+    """BASELINE.json configs[4]: every rank owns a contiguous label range of the data set with its own B-WST (graphs
+    built on its GPU), every rank answers the WHOLE batch, the partial [nq][k] rows are all-gathered over NVLink and
+    merged per query inside the library.  value = queries of the one shared batch per second (max over ranks)."""
+    from rangefilteredann_b200 import capi, label_shard, load_engine
+    eng = load_engine()
+    if eng.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device visible — this engine has no CPU fallback")
+    cfg = CONFIGS[args.config]
+    os.environ["WSANN_DEVICE"] = str(local_rank)
+    dev = f"cuda:{local_rank}" if world > 1 else None
+    t_setup = time.time()
+    data, queries, labels, windows = make_inputs(cfg)
+    nq = len(queries)
+    uid = None
+    if world > 1:
+        uid = broadcast_bytes(capi.nccl_unique_id() if rank == 0 else None)
+    tag = args.config + (f"-n{cfg['n']}" if cfg.get("scaled") else "")
+    shard = label_shard.LabelShardedTree(data, labels, rank, world, os.path.join(ROOT, "data_cache", tag, "label_shards"),
+                                         cutoff=cfg["cutoff"], metric=cfg["metric"], unique_id=uid)
+    log(f"rank {rank}: shard of {len(shard.owned)} points + tree ready in {time.time() - t_setup:.1f}s")
+    gts = ground_truth_torch(data, queries, labels, windows, f"cuda:{local_rank}", cfg["metric"])
+    runner = ShardRunner(shard, nq, cfg, world, dev)
+    runner.upload(queries, windows, np.sort(labels))
+    h = shard.h
+    table = choose_operating_points(runner, gts, rank, cfg)
+    step_methods = PREFILTER_OPS + tree_methods(cfg)
+    ops = {p: min((table[p][m] for m in step_methods if m in table[p]), key=lambda v: v["ms"])["op"] for p in POWERS}
+    ops = broadcast_object(ops)
+
+    def barrier():
+        h.sync()
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_dev():
+        for p in POWERS:
+            runner.launch_dev(p, ops[p])
+
+    for _ in range(args.warmup):
+        step_dev()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    l0 = h.launches()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_dev()
+    h.sync()
+    wall_ms = (time.perf_counter() - t0) * 1000.0
+    barrier()
+    launches = h.launches() - l0
+    clk = clocks.stop()
+    # device time of the kernels + collectives alone (queries already resident): per fraction, CUDA events
+    dev_ms, search_ms = 0.0, 0.0
+    per_fraction = {}
+    for p in POWERS:
+        t_all = runner.time_dev(p, ops[p], reps=3)
+        # the local search alone (communicator bypassed): what is left is the exchange + merge
+        shard._has_comm, had = False, shard._has_comm
+        t_search = runner.time_dev(p, ops[p], reps=3)
+        shard._has_comm = had
+        dev_ms += t_all
+        search_ms += t_search
+        per_fraction[frac_name(p)] = {"best": ops[p][0], "beam": ops[p][1], "final_multiply": ops[p][2], "recall": round(table[p][ops[p][0] if ops[p][0] in table[p] else "prefilter"]["recall"], 4),
+                                      "ms": round(t_all, 4), "local_search_ms": round(t_search, 4),
+                                      "exchange_merge_ms": round(max(0.0, t_all - t_search), 4),
+                                      "qps": round(nq / (t_all / 1000.0))}
+    # end to end: host numpy in, host numpy out, every step
+    qps = {p: capi.query_params(k=K, beam=max(1, ops[p][1]), final_multiply=max(1, ops[p][2])) for p in POWERS}
+
+    def step_e2e():
+        for p in POWERS:
+            m = ops[p][0]
+            if m in PREFILTER_OPS:
+                h.set_option("gemm_prefilter", 1 if m == "prefilter_tc" else 0)
+                h.set_option("prefilter_direct", 1 if m == "prefilter_direct" else 0)
+            shard.batch_search(queries, windows[p], "prefilter" if m in PREFILTER_OPS else m, qps[p], K)
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    e2e_ms = (time.perf_counter() - t0) * 1000.0
+    barrier()
+    wall_ms, e2e_ms, dev_ms, search_ms = reduce_max([wall_ms, e2e_ms, dev_ms, search_ms], device=dev)
+    if rank != 0:
+        return
+    nq_step = nq * len(POWERS)
+    ms_per_step = wall_ms / args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    line = {
+        "metric": "QPS at recall@10>=0.95, one pass over filter fractions " + fractions_label(),
+        "value": round(nq_step / (ms_per_step / 1000.0), 1), "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+        "scaling": "strong (label-sharded: the data set is cut into one label range per GPU, every GPU answers the whole batch)",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_string(cfg), "name": args.config, "mode": "label_shard", "rows_total": int(len(labels)),
+                   "rows_per_gpu": int(len(shard.owned)), "queries_per_step": nq_step,
+                   "parallelism": f"label-range sharded over {world} GPUs, one process per GPU; partial top-k rows exchanged with "
+                                  f"ncclAllGather inside libwsann_cuda.so (NCCL {capi.nccl_version() if world > 1 else 'unused'}) "
+                                  f"and merged on the device",
+                   "l2_policy": "working set (vectors + adjacency) exceeds the 126 MB L2; no flush"},
+        "e2e": {"value": round(nq_step / (e2e_ms / args.steps / 1000.0), 1), "unit": "queries/s",
+                "h2d_bytes_per_step": int(nq_step * (cfg["d"] * 4 + 8)), "d2h_bytes_per_step": int(nq_step * K * 8),
+                "api": "label_shard.LabelShardedTree.batch_search (host numpy in / out on every rank)"},
+        "gpu_launches": int(launches), "clocks": clk,
+        "device_ms_per_step": round(dev_ms, 4), "local_search_ms_per_step": round(search_ms, 4),
+        "exchange_merge_ms_per_step": round(max(0.0, dev_ms - search_ms), 4),
+        "exchange_bytes_per_step_per_rank": int(nq_step * K * 8),
+        "hbm_gbs_peak": peaks.get("hbm_gbs"),
+        "per_fraction": per_fraction,
+    }
+    emit(line)
+
+
+class GroupRunner:
+    """The public batch_search call with host buffers; behind it either one GPU or a ws_group of several."""
+
+    def __init__(self, tree, pre, nq: int, cfg: dict, eng):
+        self.tree, self.pre, self.nq, self.cfg, self.eng = tree, pre, nq, cfg, eng
+        self.mean_window, self.windows, self.queries = {}, {}, None
+        self.prefilter_ops = ("prefilter_tc",)  # stands for "as the engine routes it" (default options)
+        self.last = None
+
+    def upload(self, queries, windows_by_power, sorted_labels):
+        self.queries = queries
+        for p, w in windows_by_power.items():
+            self.windows[p] = w
+            self.mean_window[p] = 1e9  # route name only: the engine samples the windows itself
+
+    def launch_dev(self, power, op):
+        method, beam, mult = op
+        qp = self.eng.QueryParams(K, max(1, beam), 1.35, 10_000_000, 10_000, max(1, mult), 10000, None, False)
+        if method in PREFILTER_OPS:
+            self.last = self.pre.batch_search(self.queries, self.windows[power], self.nq, qp)
+        elif method == "super":
+            self.last = self.tree.batch_search(self.queries, self.windows[power], self.nq, qp)
+        else:
+            self.last = self.tree.batch_search(self.queries, self.windows[power], self.nq, method, qp)
+
+    def sync(self):
+        pass
+
+    def fetch(self):
+        return self.last[0]
+
+    def time_dev(self, power, op, reps=3):
+        best = 1e30
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            self.launch_dev(power, op)
+            best = min(best, (time.perf_counter() - t0) * 1000.0)
+        return best
+
+
+def run_group(args):
+    """ONE process, ONE batch_search call, N GPUs (ws_group inside libwsann_cuda.so): the drop-in caller's view of the
+    8-GPU box.  Timed end to end through the pybind classes with pageable numpy buffers, next to the same calls on one
+    GPU in the same process (strong scaling of the in-engine fan-out)."""
+    from rangefilteredann_b200 import capi, load_engine
+    eng = load_engine()
+    ndev = eng.device_count()
+    if ndev == 0:
+        raise SystemExit("bench.py: no CUDA device visible — this engine has no CPU fallback")
+    G = args.group_gpus or ndev
+    cfg = CONFIGS[args.config]
+    data, queries, labels, windows = make_inputs(cfg)
+    nq = len(queries)
+    cdir = cache_dir(args.config)
+    os.makedirs(cdir, exist_ok=True)
+    validate_cache(cdir, data, labels)
+    label = args.group_shard == "label"
+    os.environ["WSANN_DEVICES"] = "0"
+    os.environ.pop("WSANN_SHARD_MODE", None)
+    t0 = time.time()
+    tree1, pre1 = make_indices(eng, cfg, cdir, data, labels)
+    log(f"1-GPU index ready in {time.time() - t0:.1f}s")
+    os.environ["WSANN_DEVICES"] = args.group_devices or ",".join(str(i) for i in range(G))
+    G = len(os.environ["WSANN_DEVICES"].split(","))
+    if label:
+        os.environ["WSANN_SHARD_MODE"] = "label"
+    t0 = time.time()
+    treeG, preG = make_indices(eng, cfg, cdir, data, labels)
+    t_group_setup = time.time() - t0
+    log(f"{G}-GPU group ({'label shards' if label else 'replicas'}) ready in {t_group_setup:.1f}s")
+    gts = ground_truth_torch(data, queries, labels, windows, "cuda:0", cfg["metric"])
+    sorted_labels = np.sort(labels)
+    r1 = GroupRunner(tree1, pre1, nq, cfg, eng)
+    rG = GroupRunner(treeG, preG, nq, cfg, eng)
+    r1.upload(queries, windows, sorted_labels)
+    rG.upload(queries, windows, sorted_labels)
+    table = choose_operating_points(rG, gts, 0, cfg)
+    step_methods = PREFILTER_OPS + tree_methods(cfg)
+    ops = {p: min((table[p][m] for m in step_methods if m in table[p]), key=lambda v: v["ms"])["op"] for p in POWERS}
+
+    def step(r):
+        for p in POWERS:
+            r.launch_dev(p, ops[p])
+
+    res = {}
+    clk = None
+    for name, r in (("one_gpu", r1), ("group", rG)):
+        for _ in range(args.warmup):
+            step(r)
+        clocks = ClockSampler(0)
+        clocks.start()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step(r)
+        res[name] = (time.perf_counter() - t0) * 1000.0 / args.steps
+        c = clocks.stop()
+        clk = c if name == "group" else clk
+    per_fraction = {}
+    identical = 0
+    for p in POWERS:
+        t1 = r1.time_dev(p, ops[p])
+        a = r1.last
+        tG = rG.time_dev(p, ops[p])
+        b = rG.last
+        same = bool(np.array_equal(a[0], b[0]))
+        identical += int(same)
+        per_fraction[frac_name(p)] = {"best": ops[p][0], "beam": ops[p][1], "final_multiply": ops[p][2],
+                                      "recall": round(recall_at_k(b[0], gts[p]), 4), "recall_one_gpu": round(recall_at_k(a[0], gts[p]), 4),
+                                      "ms_one_gpu": round(t1, 4), "ms_group": round(tG, 4), "speedup": round(t1 / tG, 3),
+                                      "rows_identical_to_one_gpu": same}
+    g = capi.Group.borrow(treeG)
+    info = g.info() if g is not None else {}
+    nq_step = nq * len(POWERS)
+    launches = sum(g.member(i).launches() for i in range(g.size())) if g is not None else 0
+    speedup = res["one_gpu"] / res["group"]
+    line = {
+        "metric": "QPS at recall@10>=0.95, one pass over filter fractions " + fractions_label(),
+        "value": round(nq_step / (res["group"] / 1000.0), 1), "unit": "queries/s", "n_gpus": G, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(res["group"], 4), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_string(cfg), "name": args.config, "mode": "group/" + args.group_shard, "queries_per_step": nq_step,
+                   "parallelism": f"one process, one batch_search call, {G} GPUs: " +
+                                  ("label shards, partial rows gathered by peer loads over NVLink inside the merge kernel" if label
+                                   else "replicas (arena cloned device to device), the batch cut into one slice per GPU, one host thread per GPU"),
+                   "timing": "host wall clock around the synchronous public call (a group has no device-resident entry point), "
+                             "pageable numpy in / out: value and e2e are the same measurement"},
+        "e2e": {"value": round(nq_step / (res["group"] / 1000.0), 1), "unit": "queries/s",
+                "h2d_bytes_per_step": int(nq_step * (cfg["d"] * 4 + 8)) * (G if label else 1), "d2h_bytes_per_step": int(nq_step * K * 8),
+                "api": "pybind batch_search of the classes run_our_method.py calls, WSANN_DEVICES=" + os.environ["WSANN_DEVICES"]},
+        "one_gpu": {"value": round(nq_step / (res["one_gpu"] / 1000.0), 1), "ms_per_step": round(res["one_gpu"], 4)},
+        "speedup_vs_one_gpu": round(speedup, 3), "efficiency": round(speedup / G, 3),
+        "fractions_with_rows_identical_to_one_gpu": f"{identical}/{len(POWERS)}",
+        "group_setup_s": round(t_group_setup, 1), "group_info": info,
+        "gpu_launches": int(launches), "clocks": clk, "per_fraction": per_fraction,
+    }
+    emit(line)
+
+
+# ------------------------------------------------------------------------------------------
 # the reference arm / cpu baseline
 # ------------------------------------------------------------------------------------------
 def ref_indices(ref, cfg, cdir, data, labels):
-    bp = ref.BuildParams(64, 500, 1.0, cdir)
     devnull = os.open(os.devnull, os.O_WRONLY)
     saved = os.dup(1)
     os.dup2(devnull, 1)  # the reference prints one line per loaded graph
     try:
-        tree = ref.VamanaRangeFilterTreeIndexFloatEuclidian(data, labels, cfg["cutoff"], 2, bp)
-        pre = ref.PrefilterIndexFloatEuclidian(data, labels)
+        tree, pre = make_indices(ref, cfg, cdir, data, labels)
     finally:
         os.dup2(saved, 1)
         os.close(devnull)
@@ -821,6 +1169,8 @@ def ref_time(ref, tree, pre, queries, w, op, nq, want_dists=False):
     t0 = time.perf_counter()
     if method == "prefilter":
         ids, dd = pre.batch_search(queries[:nq], w[:nq], nq, qp)
+    elif method == "super":
+        ids, dd = tree.batch_search(queries[:nq], w[:nq], nq, qp)
     else:
         ids, dd = tree.batch_search(queries[:nq], w[:nq], nq, method, qp)
     dt = time.perf_counter() - t0
@@ -845,17 +1195,18 @@ def cpu_baseline(args, cfg, data, queries, labels, windows, gts, table, ops, eng
     cores = int(os.environ.get("PARLAY_NUM_THREADS", os.cpu_count()))
     tree, pre = ref_indices(ref, cfg, cache_dir(args.config), data, labels)
     total_q, total_t, detail = 0, 0.0, {}
+    sorted_labels = np.sort(labels)
     par = {"prefilter_rows_compared": 0, "prefilter_rows_equal_up_to_1e-5_ties": 0, "prefilter_rows_bit_identical_ids": 0,
            "recall_gate": 0.005, "recall_points_compared": 0, "recall_points_within_gate": 0, "max_abs_recall_diff": 0.0,
            "per_fraction": {}}
-    ref_time(ref, tree, pre, queries, windows[-8], ("prefilter", 0, 0), 64)  # warm the pool
+    ref_time(ref, tree, pre, queries, windows[POWERS[len(POWERS) // 2]], ("prefilter", 0, 0), 64)  # warm the pool
     for p in POWERS:
         best = None
         pf = {}
         for method, v in table[p].items():
             if method in ("prefilter_tc", "prefilter_direct", "prefilter_auto"):  # the reference has one prefilter implementation (timed as "prefilter")
                 continue
-            ns = min(args.cpu_sample, cfg["nq"])
+            ns = min(args.cpu_sample, len(windows[p]))
             t_probe, _ = ref_time(ref, tree, pre, queries, windows[p], v["op"], min(64, ns))
             per_q = t_probe / min(64, ns)
             ns = int(max(64, min(ns, args.cpu_budget_s / len(POWERS) / 3 / max(per_q, 1e-7))))
@@ -869,14 +1220,18 @@ def cpu_baseline(args, cfg, data, queries, labels, windows, gts, table, ops, eng
             qp = eng.QueryParams(K, max(beam, 1), 1.35, 10_000_000, 10_000, max(mult, 1), 10000, None, False)
             if method == "prefilter":
                 eids, ed = pre_e.batch_search(q_s, w_s, ns, qp)
-                ok = rows_equal_up_to_ties(eids, ed, ids, rd)
-                same = int((eids == ids).all(1).sum())
-                par["prefilter_rows_compared"] += ns
+                # windows holding fewer than k points: the reference copies k entries of a shorter frontier
+                # (prefiltering.h:139-142, undefined rows) — only rows with at least k in-window points are comparable
+                full = (np.searchsorted(sorted_labels, w_s[:, 1]) - np.searchsorted(sorted_labels, w_s[:, 0])) > K
+                ok = rows_equal_up_to_ties(eids[full], ed[full], ids[full], rd[full])
+                same = int((eids[full] == ids[full]).all(1).sum())
+                par["prefilter_rows_compared"] += int(full.sum())
                 par["prefilter_rows_equal_up_to_1e-5_ties"] += int(ok.sum())
                 par["prefilter_rows_bit_identical_ids"] += same
-                pf["prefilter"] = {"rows": ns, "equal_up_to_ties": int(ok.sum()), "identical_ids": same}
+                pf["prefilter"] = {"rows": int(full.sum()), "rows_with_fewer_than_k_points_skipped": int((~full).sum()),
+                                   "equal_up_to_ties": int(ok.sum()), "identical_ids": same}
             else:
-                eids, _ = tree_e.batch_search(q_s, w_s, ns, method, qp)
+                eids, _ = tree_e.batch_search(q_s, w_s, ns, qp) if method == "super" else tree_e.batch_search(q_s, w_s, ns, method, qp)
                 r_e = recall_at_k(eids, gts[p][:ns])
                 diff = abs(r_e - r)
                 par["recall_points_compared"] += 1
@@ -884,10 +1239,10 @@ def cpu_baseline(args, cfg, data, queries, labels, windows, gts, table, ops, eng
                 par["max_abs_recall_diff"] = max(par["max_abs_recall_diff"], diff)
                 pf[method] = {"beam": beam, "final_multiply": mult, "queries": ns, "recall_engine": round(r_e, 4),
                               "recall_reference": round(r, 4), "rows_identical_ids": int((eids == ids).all(1).sum())}
-        par["per_fraction"][f"2^{p}"] = pf
+        par["per_fraction"][frac_name(p)] = pf
         if best is None:
             continue
-        detail[f"2^{p}"] = {"method": best[1], "qps": round(1.0 / best[0]), "sample": best[2], "recall": round(best[3], 4)}
+        detail[frac_name(p)] = {"method": best[1], "qps": round(1.0 / best[0]), "sample": best[2], "recall": round(best[3], 4)}
         total_q += 1
         total_t += best[0]
     value = total_q / total_t if total_t > 0 else None  # queries/s for one query of every fraction
@@ -914,19 +1269,18 @@ def run_reference(args, rank, world):
     if ref is None:
         emit({"impl": "reference", "unavailable": "oracle/_ref not built in this snapshot"})
         return
-    data, queries, labels = synth.make_dataset(cfg["n"], cfg["d"], cfg["nq"], cfg["seed"])
-    windows = {p: synth.make_windows(labels, p, cfg["nq"], seed=1000 + p) for p in POWERS}
+    data, queries, labels, windows = make_inputs(cfg)
     validate_cache(cache_dir(args.config), data, labels)
     cdir = ensure_graphs(args.config, cfg, data, labels, 0)
     tree, pre = ref_indices(ref, cfg, cdir, data, labels)
     ns = args.ref_sample
-    gts = {p: synth.ground_truth(data, queries[:ns], labels, windows[p][:ns]) for p in POWERS}
+    gts = {p: synth.ground_truth(data, queries[:ns], labels, windows[p][:ns], angular=cfg["metric"] == "mips") for p in POWERS}
     # operating points: smallest beam reaching the recall target per method (CPU sweep on the sample)
     ops, est_qps = {}, {}
     for p in POWERS:
         cands = [("prefilter", 0, 0)]
-        for method in ("fenwick", "optimized_postfilter"):
-            for beam in BEAMS:
+        for method in tree_methods(cfg):
+            for beam in cfg.get("beams", BEAMS):
                 _, ids = ref_time(ref, tree, pre, queries, windows[p], (method, beam, 1), ns)
                 if recall_at_k(ids, gts[p]) >= RECALL_TARGET:
                     cands.append((method, beam, 1))
@@ -934,11 +1288,11 @@ def run_reference(args, rank, world):
         timed = [(ref_time(ref, tree, pre, queries, windows[p], op, ns)[0], op) for op in cands]
         ops[p] = min(timed)[1]
         est_qps[p] = ns / min(timed)[0]
-        log(f"reference 2^{p}: " + ", ".join(f"{op[0]} b{op[1]} {ns / t:.0f} qps" for t, op in timed))
+        log(f"reference {frac_name(p)}: " + ", ".join(f"{op[0]} b{op[1]} {ns / t:.0f} qps" for t, op in timed))
 
     # per-fraction batch sizes: large enough for parlay's fork-join to amortise on the fast
     # fractions, bounded (~0.25 s) on the slow ones
-    ns_p = {p: int(min(cfg["nq"], max(ns, 0.25 * est_qps[p]))) for p in POWERS}
+    ns_p = {p: int(min(len(windows[p]), max(ns, 0.25 * est_qps[p]))) for p in POWERS}
 
     def step():
         per_q = 0.0
@@ -957,7 +1311,7 @@ def run_reference(args, rank, world):
     # same definition as the engine arm: equal number of queries from every fraction
     value = len(POWERS) / (per_q_sum / args.steps)
     cores = int(os.environ.get("PARLAY_NUM_THREADS", os.cpu_count()))
-    line = {"impl": "reference", "metric": "QPS at recall@10>=0.95, one pass over filter fractions 2^-16..2^0",
+    line = {"impl": "reference", "metric": "QPS at recall@10>=0.95, one pass over filter fractions " + fractions_label(),
             "value": round(value, 1), "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(dt / args.steps * 1000.0, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -966,9 +1320,9 @@ def run_reference(args, rank, world):
                                    f"[{ns}, {cfg['nq']}] queries; value = 17 / sum of per-query times"},
             "cpu_baseline": {"value": round(value, 1), "unit": "queries/s", "cores": cores, "kind": "reference",
                              "march": REF_MARCH,
-                             "sample": "per fraction: " + ", ".join(f"2^{p}:{ns_p[p]}" for p in POWERS)},
+                             "sample": "per fraction: " + ", ".join(f"{frac_name(p)}:{ns_p[p]}" for p in POWERS)},
             "e2e": {"value": round(value, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "per_fraction": {f"2^{p}": {"method": ops[p][0], "beam": ops[p][1], "qps_estimate": round(est_qps[p])}
+            "per_fraction": {frac_name(p): {"method": ops[p][0], "beam": ops[p][1], "qps_estimate": round(est_qps[p])}
                              for p in POWERS}}
     emit(line)
 
@@ -987,6 +1341,17 @@ def main():
     ap.add_argument("--results-csv", default=None, help="also append the operating-point sweep to this file in the "
                     "reference driver's results format (filter_width,method,recall,average_time,qps,threads)")
     ap.add_argument("--ops-file", default=None, help="save / reuse the swept operating points (profiling runs)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = every rank answers its own batch (default); strong = ONE batch cut into N slices")
+    ap.add_argument("--mode", default="replica", choices=["replica", "label_shard", "group"],
+                    help="replica: index replicated, queries sharded over ranks (default); label_shard: every rank owns a "
+                         "contiguous label range, in-library ncclAllGather + merge (one process per GPU); group: ONE process "
+                         "drives --group-gpus GPUs through the public batch_search call (in-engine fan-out)")
+    ap.add_argument("--group-gpus", type=int, default=0, help="--mode group: number of GPUs behind one call (0 = all)")
+    ap.add_argument("--group-shard", default="replicate", choices=["replicate", "label"])
+    ap.add_argument("--group-devices", default=None, help="--mode group: explicit device list, e.g. 0,0 (two members on one GPU)")
+    ap.add_argument("--n", type=int, default=0, help="scale the configuration's row count (stated in the result line)")
+    ap.add_argument("--powers", default=None, help="comma-separated subset of the fractions, e.g. -12,-8,-4,0")
     args = ap.parse_args()
     claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
@@ -995,6 +1360,15 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.config == "auto":
         args.config = "c2"  # BASELINE.json configs[1], the configuration the metric is quoted on
+    global POWERS
+    cfg = CONFIGS[args.config]
+    if args.n and args.n != cfg["n"]:
+        cfg["n"] = args.n
+        cfg["scaled"] = True
+    if cfg.get("adversarial"):
+        POWERS = ["adv", "blowup-4", "blowup-7", "blowup-10"]
+    if args.powers:
+        POWERS = [(int(x) if x.lstrip("-").isdigit() else x) for x in args.powers.split(",")]
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -1004,7 +1378,12 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     try:
-        run_engine(args, rank, world, local_rank)
+        if args.mode == "label_shard":
+            run_label_shard(args, rank, world, local_rank)
+        elif args.mode == "group":
+            run_group(args)
+        else:
+            run_engine(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -11,15 +11,20 @@ namespace {
 #define WSK_CAT(a, b, c) WSK_CAT_(a, b, c)
 
 template <int KQ, bool EXACT>
+static WsSmemAttr& smem_attr() {
+  static WsSmemAttr a;  // shared by the launcher and the occupancy query of this instantiation
+  return a;
+}
+template <int KQ, bool EXACT>
 static cudaError_t launch_t(int grid, size_t smem, cudaStream_t s, const WsBeamArgs& a) {
-  cudaError_t e = cudaFuncSetAttribute(ws_beam_warp_kernel<KQ, WSK_METRIC, EXACT, WSK_CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = smem_attr<KQ, EXACT>().ensure(ws_beam_warp_kernel<KQ, WSK_METRIC, EXACT, WSK_CS>, smem);
   if (e != cudaSuccess) return e;
   ws_beam_warp_kernel<KQ, WSK_METRIC, EXACT, WSK_CS><<<grid, WS_WARPS_PER_CTA * 32, smem, s>>>(a);
   return cudaGetLastError();
 }
 template <int KQ, bool EXACT>
 static cudaError_t occ_t(size_t smem, int* blocks) {
-  cudaError_t e = cudaFuncSetAttribute(ws_beam_warp_kernel<KQ, WSK_METRIC, EXACT, WSK_CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = smem_attr<KQ, EXACT>().ensure(ws_beam_warp_kernel<KQ, WSK_METRIC, EXACT, WSK_CS>, smem);
   if (e != cudaSuccess) return e;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, ws_beam_warp_kernel<KQ, WSK_METRIC, EXACT, WSK_CS>, WS_WARPS_PER_CTA * 32, smem);
 }

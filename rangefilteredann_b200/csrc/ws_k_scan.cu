@@ -11,8 +11,13 @@ namespace {
 #define WSK_CAT(a, b) WSK_CAT_(a, b)
 
 template <int KQ>
+static WsSmemAttr& smem_attr() {
+  static WsSmemAttr a;  // shared by the launcher and the occupancy query of this instantiation
+  return a;
+}
+template <int KQ>
 static cudaError_t scan_t(int grid, size_t smem, cudaStream_t s, const WsScanArgs& a) {
-  cudaError_t e = cudaFuncSetAttribute(ws_scan_kernel<KQ, WSK_METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = smem_attr<KQ>().ensure(ws_scan_kernel<KQ, WSK_METRIC>, smem);
   if (e != cudaSuccess) return e;
   ws_scan_kernel<KQ, WSK_METRIC><<<grid, WS_CTA_THREADS, smem, s>>>(a);
   return cudaGetLastError();

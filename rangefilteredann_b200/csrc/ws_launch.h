@@ -2,7 +2,28 @@
 // each family is instantiated in its own translation unit (ws_k_*.cu) so that the library builds in parallel,
 // and the host orchestration (wsann.cu) only sees these plain functions.
 #pragma once
+#include <mutex>
+
 #include "ws_args.h"
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to a (function, device) pair and only ever has to grow.  One of
+// these per kernel instantiation keeps it monotone under a lock: host threads of a ws_group launch the same kernel
+// with different shared-memory sizes at the same time, possibly on the same device.
+struct WsSmemAttr {
+  std::mutex mu;
+  int cur[64] = {0};
+  template <class F>
+  cudaError_t ensure(F* fn, size_t smem) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    if ((int)smem <= cur[dev & 63]) return cudaSuccess;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) cur[dev & 63] = (int)smem;
+    return e;
+  }
+};
 
 // KQ = float4 columns per lane of a team of 8 (ws_device.cuh): the instantiated values
 #define WS_KQ_SWITCH(KQV, CALL)  \

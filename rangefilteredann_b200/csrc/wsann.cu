@@ -160,6 +160,7 @@ struct ws_index {
   int64_t opt_gemm_debug = 0;     // timing experiments (ws_gemm.h WsGemmArgs::dbg); results are invalid when set
   int64_t opt_gemm_chunk_mb = 8;  // largest slice of the label axis one work item sweeps
   bool gemm_ready = false;
+  bool gemm_attr_set = false;
   bool gemm_unfit = false;        // the arena cannot be mirrored in fp16 (non-finite or absurdly scaled components)
   int32_t g_x_exp = 0;            // the fp16 mirror holds half(x * 2^g_x_exp)
   WsDevBuf g_norms, g_ctrl, g_perm, g_row_a, g_row_b, g_items, g_group_items, g_group_cnt, g_qpack, g_rscale, g_vecs16, g_slack, g_cand,
@@ -678,10 +679,9 @@ static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw
   WS_TRY(ws_ensure(idx, idx->g_res_cnt, max_rows * sizeof(uint32_t)));
   const size_t gemm_smem = wsg_topk_smem_bytes();
   if (gemm_smem > idx->smem_optin) return ws_fail(WS_ERR_CUDA, "tensor-core prefilter needs %zu B of shared memory (> %zu)", gemm_smem, idx->smem_optin);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!idx->gemm_attr_set) {  // function attributes are per device: once per arena, not once per process
     WS_CUDA(wsg_init_attributes());
-    attr_set = true;
+    idx->gemm_attr_set = true;
   }
   unsigned long long* gctrl = (unsigned long long*)idx->g_ctrl.p;  // [0] survivors, [1] fallbacks, u32 view: [8] max |x|^2, [10] nitems
   uint32_t* gctrl32 = (uint32_t*)idx->g_ctrl.p;
