@@ -236,6 +236,16 @@ int ws_index_comm_destroy(ws_index* idx);
 int ws_allgather_merge(ws_index* idx, const uint32_t* ids, const float* dists, uint64_t nq, uint32_t k, uint32_t pad_id,
                        uint32_t* out_ids, float* out_dists);
 
+/* ---- arena snapshot ----------------------------------------------------------
+ * The reference persists only graphs (postfilter_vamana.h:54-79: one .bin per node) and re-sorts, re-derives and
+ * re-reads everything at every start.  ws_index_save writes the FINISHED arena (padded vectors, labels, id table,
+ * node table, adjacency rows, tree geometry — not scratch, options or counters) into one file; ws_index_load
+ * brings it back on any device, finalized and ready for the *_batch calls.  Layout: csrc/ws_snapshot.inl. */
+int ws_index_save(ws_index* idx, const char* path);
+int ws_index_load(const char* path, int device, ws_index** out);
+/* n, dim, metric and the number of graphs of an arena (any of the out pointers may be NULL) */
+int ws_index_shape(const ws_index* idx, uint64_t* n, uint32_t* dim, int* metric, uint64_t* nodes);
+
 /* ---- device plumbing for callers that keep batches resident in HBM (bench `value`) --- */
 int ws_index_device(const ws_index* idx, int* device);
 int ws_index_sync(ws_index* idx);

@@ -54,6 +54,9 @@ def lib() -> C.CDLL:
         L.ws_index_set_super.argtypes = [vp, u32, i32, vp, vp, vp, vp]
         L.ws_index_finalize.argtypes = [vp]
         L.ws_index_set_decode.argtypes = [vp, vp]
+        L.ws_index_save.argtypes = [vp, C.c_char_p]
+        L.ws_index_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+        L.ws_index_shape.argtypes = [vp, C.POINTER(u64), C.POINTER(u32), C.POINTER(C.c_int), C.POINTER(u64)]
         L.ws_prefilter_batch.argtypes = [vp, vp, vp, u64, u32, vp, vp, u32]
         L.ws_postfilter_batch.argtypes = [vp, i32, vp, vp, u64, C.POINTER(QueryParamsC), C.c_int, vp, vp, u32]
         L.ws_tree_batch.argtypes = [vp, C.c_int, vp, vp, u64, C.POINTER(QueryParamsC), vp, vp, u32]

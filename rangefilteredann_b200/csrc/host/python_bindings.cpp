@@ -129,7 +129,10 @@ static void add_variant(py::module_& m, const std::string& sfx) {
            },
            "queries"_a, "filters"_a, "num_queries"_a, "query_params"_a)
       .def("_arena_handle", [](Prefilter& self) { return (uintptr_t)self.arena().get(); })
-      .def("_group_handle", [](Prefilter& self) { return (uintptr_t)self.group(); });
+      .def("_group_handle", [](Prefilter& self) { return (uintptr_t)self.group(); })
+      // not in the reference (it persists graphs only): the finished arena in one file, and back
+      .def("save_snapshot", [](Prefilter& self, const std::string& path) { self.save_snapshot(path); }, "path"_a)
+      .def_static("load_snapshot", [](const std::string& path) { return new Prefilter(wsann::FromSnapshot{path}); }, "path"_a);
 
   py::class_<Postfilter>(m, ("PostfilterVamanaIndex" + sfx).c_str())
       .def(py::init([](TArray<T> points, FArray filters, BuildParams bp) {
@@ -144,7 +147,10 @@ static void add_variant(py::module_& m, const std::string& sfx) {
            },
            "queries"_a, "filters"_a, "num_queries"_a, "query_params"_a)
       .def("_arena_handle", [](Postfilter& self) { return (uintptr_t)self.arena().get(); })
-      .def("_group_handle", [](Postfilter& self) { return (uintptr_t)self.group(); });
+      .def("_group_handle", [](Postfilter& self) { return (uintptr_t)self.group(); })
+      // not in the reference (it persists graphs only): the finished arena in one file, and back
+      .def("save_snapshot", [](Postfilter& self, const std::string& path) { self.save_snapshot(path); }, "path"_a)
+      .def_static("load_snapshot", [](const std::string& path) { return new Postfilter(wsann::FromSnapshot{path}); }, "path"_a);
 
   py::class_<Tree>(m, ("VamanaRangeFilterTreeIndex" + sfx).c_str())
       .def(py::init([](TArray<T> points, FArray filter_values, int32_t cutoff, size_t split_factor, BuildParams bp) {
@@ -164,6 +170,9 @@ static void add_variant(py::module_& m, const std::string& sfx) {
            "queries"_a, "filters"_a, "num_queries"_a, "query_method"_a, "query_params"_a)
       .def("_arena_handle", [](Tree& self) { return (uintptr_t)self.arena().get(); })
       .def("_group_handle", [](Tree& self) { return (uintptr_t)self.group(); })
+      // not in the reference (it persists graphs only): the finished arena in one file, and back
+      .def("save_snapshot", [](Tree& self, const std::string& path) { self.save_snapshot(path); }, "path"_a)
+      .def_static("load_snapshot", [](const std::string& path) { return new Tree(wsann::FromSnapshot{path}); }, "path"_a)
       .def("_bucket_offsets", [](Tree& self) { return self.bucket_offsets(); });
 
   // python_bindings.cpp:119-127 — the tree over PrefilterIndex sub-indices
@@ -185,6 +194,9 @@ static void add_variant(py::module_& m, const std::string& sfx) {
            "queries"_a, "filters"_a, "num_queries"_a, "query_method"_a, "query_params"_a)
       .def("_arena_handle", [](PreTree& self) { return (uintptr_t)self.arena().get(); })
       .def("_group_handle", [](PreTree& self) { return (uintptr_t)self.group(); })
+      // not in the reference (it persists graphs only): the finished arena in one file, and back
+      .def("save_snapshot", [](PreTree& self, const std::string& path) { self.save_snapshot(path); }, "path"_a)
+      .def_static("load_snapshot", [](const std::string& path) { return new PreTree(wsann::FromSnapshot{path}); }, "path"_a)
       .def("_bucket_offsets", [](PreTree& self) { return self.bucket_offsets(); });
 
   py::class_<Super>(m, ("SuperOptimizedPostfilterTreeIndex" + sfx).c_str())
@@ -202,7 +214,10 @@ static void add_variant(py::module_& m, const std::string& sfx) {
            },
            "queries"_a, "filters"_a, "num_queries"_a, "query_params"_a)
       .def("_arena_handle", [](Super& self) { return (uintptr_t)self.arena().get(); })
-      .def("_group_handle", [](Super& self) { return (uintptr_t)self.group(); });
+      .def("_group_handle", [](Super& self) { return (uintptr_t)self.group(); })
+      // not in the reference (it persists graphs only): the finished arena in one file, and back
+      .def("save_snapshot", [](Super& self, const std::string& path) { self.save_snapshot(path); }, "path"_a)
+      .def_static("load_snapshot", [](const std::string& path) { return new Super(wsann::FromSnapshot{path}); }, "path"_a);
 
 }
 

@@ -207,6 +207,21 @@ class Arena {
   // and put the replicas behind one group: a batch is then cut into one slice per GPU.
   void finalize(const std::vector<int>& devices = {}) {
     check(ws_index_finalize(idx_), "ws_index_finalize");
+    replicate(devices);
+  }
+
+  // A finished arena read back from one file (ws_index_load): no sort, no tree derivation, no graph files.
+  void load_snapshot(const std::string& path, const std::vector<int>& devices) {
+    check(ws_index_load(path.c_str(), devices.empty() ? default_device() : devices[0], &idx_), "ws_index_load");
+    uint64_t n = 0;
+    uint32_t dim = 0;
+    check(ws_index_shape(idx_, &n, &dim, nullptr, nullptr), "ws_index_shape");
+    n_ = n; dim_ = dim;
+    replicate(devices);
+  }
+  void save_snapshot(const std::string& path) const { check(ws_index_save(idx_, path.c_str()), "ws_index_save"); }
+
+  void replicate(const std::vector<int>& devices) {
     int own = -1;
     ws_index_device(idx_, &own);
     if (own < 0 || devices.size() < 2) return;
@@ -400,6 +415,11 @@ class LabelShards {
   ws_group* group_ = nullptr;
 };
 
+// constructor tag: build the index from a file written by save_snapshot() of the same class
+struct FromSnapshot {
+  std::string path;
+};
+
 struct BatchResult {
   std::vector<uint32_t> ids;
   std::vector<float> dists;
@@ -416,6 +436,14 @@ class PrefilterIndex {
     }
     arena_.init_sorted(points, labels, n, dim, metric, plan.devices[0]);
     arena_.finalize(plan.devices);
+  }
+  PrefilterIndex(const FromSnapshot& snap, const DevicePlan& plan = device_plan()) {
+    arena_.load_snapshot(snap.path, plan.devices);
+    dim_ = arena_.dim();
+  }
+  void save_snapshot(const std::string& path) {
+    if (shards_.active()) throw std::runtime_error("a label-sharded index is saved shard by shard");
+    arena_.save_snapshot(path);
   }
   // prefiltering.h:124-146
   void batch_search(const float* queries, const float* filters, uint64_t nq, const QueryParams& qp, uint32_t* ids,
@@ -446,6 +474,11 @@ class PostfilterVamanaIndex {
     node_ = arena_.realize_graphs(bp)[0];
     arena_.finalize(plan.devices);
   }
+  PostfilterVamanaIndex(const FromSnapshot& snap, const DevicePlan& plan = device_plan()) {
+    arena_.load_snapshot(snap.path, plan.devices);
+    node_ = 0;
+  }
+  void save_snapshot(const std::string& path) { arena_.save_snapshot(path); }
   // postfilter_vamana.h:191-219 (missing slots: id 0xFFFFFFFF, FLT_MAX)
   void batch_search(const float* queries, const float* filters, uint64_t nq, const QueryParams& qp, uint32_t* ids,
                     float* dists) {
@@ -489,6 +522,11 @@ class RangeFilterTreeBase {
     arena_.init_sorted(points, labels, n, dim, metric, plan.devices[0]);
     offsets_ = stage_tree(arena_, n, cutoff, split_factor, bp, vamana_nodes);
     arena_.finalize(plan.devices);
+  }
+
+  explicit RangeFilterTreeBase(const FromSnapshot& snap, const DevicePlan& plan) {
+    arena_.load_snapshot(snap.path, plan.devices);
+    dim_ = arena_.dim();
   }
 
   // range_filter_tree.h:129-189 over the arena's n points: bucket offsets per row, one graph per bucket
@@ -549,10 +587,14 @@ class RangeFilterTreeBase {
     if (g) check(ws_group_tree_batch(g, method_from_string(query_method), queries, filters, nq, &c, ids, dists), "ws_group_tree_batch");
     else check(ws_tree_batch(arena_.get(), method_from_string(query_method), queries, filters, nq, &c, ids, dists, 0), "ws_tree_batch");
   }
+  void save_snapshot(const std::string& path) {
+    if (shards_.active()) throw std::runtime_error("a label-sharded index is saved shard by shard");
+    arena_.save_snapshot(path);
+  }
   Arena& arena() { return shards_.active() ? shards_.shard(0) : arena_; }
   ws_group* group() { return shards_.active() ? shards_.group() : arena_.group(); }
   size_t dim() const { return dim_; }
-  // bucket offsets of the tree (of shard 0's tree when label-sharded)
+  // bucket offsets of the tree (of shard 0's tree when label-sharded; empty for an index loaded from a snapshot)
   const std::vector<std::vector<uint64_t>>& bucket_offsets() const { return offsets_; }
 
  private:
@@ -569,6 +611,7 @@ class VamanaRangeFilterTreeIndex : public RangeFilterTreeBase {
                              int32_t cutoff, size_t split_factor, const BuildParams& bp,
                              const DevicePlan& plan = device_plan())
       : RangeFilterTreeBase(points, labels, n, dim, metric, cutoff, split_factor, bp, true, plan) {}
+  VamanaRangeFilterTreeIndex(const FromSnapshot& snap, const DevicePlan& plan = device_plan()) : RangeFilterTreeBase(snap, plan) {}
 };
 
 // RangeFilterTreeIndex<T, Point> = PrefilterIndex sub-indices (python_bindings.cpp:119-127)
@@ -577,6 +620,7 @@ class RangeFilterTreeIndex : public RangeFilterTreeBase {
   RangeFilterTreeIndex(const float* points, const float* labels, size_t n, size_t dim, int metric,
                        int32_t cutoff, size_t split_factor, const BuildParams& bp, const DevicePlan& plan = device_plan())
       : RangeFilterTreeBase(points, labels, n, dim, metric, cutoff, split_factor, bp, false, plan) {}
+  RangeFilterTreeIndex(const FromSnapshot& snap, const DevicePlan& plan = device_plan()) : RangeFilterTreeBase(snap, plan) {}
 };
 
 // ---- SuperOptimizedPostfilterTree (src/super_optimized_postfilter_tree.h) ------------------------
@@ -615,6 +659,10 @@ class SuperOptimizedPostfilterTree {
     arena_.finalize(plan.devices);
     sizes_ = sizes; shifts_ = shifts;
   }
+  SuperOptimizedPostfilterTree(const FromSnapshot& snap, const DevicePlan& plan = device_plan()) {
+    arena_.load_snapshot(snap.path, plan.devices);
+  }
+  void save_snapshot(const std::string& path) { arena_.save_snapshot(path); }
   // super_optimized_postfilter_tree.h:60-87
   void batch_search(const float* queries, const float* filters, uint64_t nq, const QueryParams& qp, uint32_t* ids,
                     float* dists) {

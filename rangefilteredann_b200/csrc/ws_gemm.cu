@@ -766,7 +766,12 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmB, WsGemmArgs A) {
         const int lo = max(0, min(32, wlo - cbase));
         const int hi = max(0, min(32, whi - cbase));
         if (__any_sync(0xffffffffu, hi > lo) && !(A.dbg & 1)) {
-          const bool whole = __all_sync(0xffffffffu, lo == 0 && hi == 32);
+          // Windows are contiguous and tiles walk the sorted points, so a query meets a PARTIALLY covered chunk only
+          // where its window starts and where it ends — twice per item.  Everywhere else its 32 columns are either all
+          // inside (compare as they are) or all outside (nothing may pass: threshold -inf).  The per-element masking
+          // (4 instructions per score) is therefore taken only by the few warp-tiles that hold a window edge.
+          const bool outside = hi <= lo;
+          const bool edge = __any_sync(0xffffffffu, !outside && (lo != 0 || hi != 32));
           float s[32];
           wsg_tmem_ld32(tmem_base + lane_addr + A.acc_col0 + acc * WSG_TILE_N + chunk * 32, s);
           // the scores are in registers: hand the accumulator stage back before filtering them
@@ -780,11 +785,11 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmB, WsGemmArgs A) {
             s[4 * j + 0] = fmaf(s[4 * j + 0], rs, nv.x); s[4 * j + 1] = fmaf(s[4 * j + 1], rs, nv.y);
             s[4 * j + 2] = fmaf(s[4 * j + 2], rs, nv.z); s[4 * j + 3] = fmaf(s[4 * j + 3], rs, nv.w);
           }
-          if (!whole) {
+          if (edge) {
 #pragma unroll
             for (int j = 0; j < 32; j++) s[j] = (j >= lo && j < hi) ? s[j] : INF;
           }
-          const float thr = *(volatile float*)&S->thr[lrow];
+          const float thr = outside ? -INF : *(volatile float*)&S->thr[lrow];
           float m4[8];
 #pragma unroll
           for (int g = 0; g < 8; g++) m4[g] = fminf(fminf(s[4 * g], s[4 * g + 1]), fminf(s[4 * g + 2], s[4 * g + 3]));

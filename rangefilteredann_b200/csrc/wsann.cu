@@ -1585,3 +1585,4 @@ int ws_debug_decompose_host(ws_index* idx, int method, const float* windows, uin
 }  // extern "C"
 
 #include "ws_group.inl"
+#include "ws_snapshot.inl"
