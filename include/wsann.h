@@ -294,6 +294,9 @@ int ws_debug_decompose_host(ws_index* idx, int method, const float* windows, uin
                             const ws_query_params* qp, uint32_t cap, int64_t* out_tasks,
                             uint32_t* out_counts);
 int ws_index_task_capacity(ws_index* idx, int method, uint32_t* cap);
+/* Host-only exercise of the pinned-staging helper threads (no CUDA; testing hook): `reps` copies of `bytes` bytes
+ * through the pool, each compared with its source. */
+int ws_debug_copy_pool_selftest(uint64_t bytes, uint32_t reps);
 
 #ifdef __cplusplus
 }

@@ -4,12 +4,16 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/wsann.h"
@@ -140,6 +144,10 @@ struct ws_index {
   void* comm = nullptr;
   int comm_rank = 0, comm_size = 1;
   WsDevBuf x_all_ids, x_all_dists;
+  // pinned staging of host-buffer batches (ws_stage_h2d)
+  WsDevBuf stage_in, stage_out;
+  std::vector<std::atomic<uint32_t>> stage_flags;
+  int64_t opt_stage_copies = 1;
   const float* hint_windows = nullptr;
   uint32_t query_id_base = 0;  // position of this batch's first query in the caller's batch (ws_group slices)
   unsigned long long* d_stats = nullptr;
@@ -342,6 +350,8 @@ void ws_index_destroy(ws_index* idx) {
                         &idx->g_group_items, &idx->g_group_cnt, &idx->g_qpack, &idx->g_rscale, &idx->g_vecs16, &idx->g_slack, &idx->g_cand,
                         &idx->g_cand_cnt, &idx->g_cand_thr, &idx->g_res_keys, &idx->g_res_cnt, &idx->g_thr0, &idx->g_qnorm, &idx->g_qa, &idx->g_qb};
     for (WsDevBuf* b : bufs) cudaFree(b->p);
+    if (idx->stage_in.p) cudaFreeHost(idx->stage_in.p);
+    if (idx->stage_out.p) cudaFreeHost(idx->stage_out.p);
     for (cudaEvent_t e : idx->ev_pool) cudaEventDestroy(e);
     if (idx->ev0) cudaEventDestroy(idx->ev0);
     if (idx->ev1) cudaEventDestroy(idx->ev1);
@@ -742,6 +752,208 @@ static int ws_run_prefilter_gemm(ws_index* idx, const float* dq, const float* dw
   return WS_OK;
 }
 
+// ---- host buffers -> HBM -------------------------------------------------------------------------
+// The caller's arrays are ordinary pageable memory (numpy).  cudaMemcpyAsync from pageable memory is staged by
+// the driver through one thread: 0.25 ms of a 0.43 ms call for 10 000 x 128 queries, where the DMA itself needs
+// 0.1 ms (profiles/scripts/e2e_overhead_probe.py).  Here a few helper threads copy 512 KB chunks into a pinned
+// staging buffer of the arena while the calling thread hands each finished chunk to the copy engine.
+struct WsCopyJob {
+  char* dst = nullptr;
+  const char* src = nullptr;
+  size_t bytes = 0, chunk = 0;
+  uint32_t nchunks = 0;
+  std::atomic<uint32_t> next{0};
+  std::atomic<uint32_t>* done = nullptr;  // one flag per chunk
+  std::atomic<int> active{0};             // helpers currently inside the job
+  std::atomic<uint64_t> gen{0};           // the slot is reused: which job it holds
+};
+
+// Helper threads that spin for a short while after a job (batches of a sweep follow each other within
+// microseconds) and sleep otherwise.  One job slot, owned by the pool, so that a helper that wakes up late only ever
+// touches memory that is still there; the calling thread copies chunks too, so a sleeping pool costs nothing but
+// the wake-up call.
+class WsCopyPool {
+ public:
+  static WsCopyPool& get() {
+    // leaked on purpose: helpers wait on its condition variable for the life of the process, and destroying a
+    // condition variable with waiters blocks (pthread_cond_destroy) — a static instance hangs the process at exit
+    static WsCopyPool* pool = new WsCopyPool();
+    return *pool;
+  }
+  bool enabled() const { return nthreads_ > 0; }
+  // nullptr: the pool is busy with another arena's batch (the caller copies alone)
+  WsCopyJob* begin(char* dst, const char* src, size_t bytes, size_t chunk, std::atomic<uint32_t>* done) {
+    if (nthreads_ == 0 || !busy_.try_lock()) return nullptr;
+    WsCopyJob* j = &slot_;
+    while (j->active.load(std::memory_order_acquire) != 0) cpu_relax();  // a straggler of the previous job
+    j->dst = dst; j->src = src; j->bytes = bytes; j->chunk = chunk;
+    j->nchunks = (uint32_t)((bytes + chunk - 1) / chunk);
+    j->done = done;
+    j->next.store(0, std::memory_order_relaxed);
+    j->gen.fetch_add(1, std::memory_order_relaxed);
+    cur_.store(j, std::memory_order_release);
+    if (sleepers_.load(std::memory_order_acquire) > 0) {
+      std::lock_guard<std::mutex> lk(mu_);
+      cv_.notify_all();
+    }
+    return j;
+  }
+  void end(WsCopyJob* j) {  // every chunk has been seen done by the caller
+    cur_.store(nullptr, std::memory_order_release);
+    while (j->active.load(std::memory_order_acquire) != 0) cpu_relax();
+    busy_.unlock();
+  }
+  // one chunk of the job on the calling thread; false when none is left
+  static bool help(WsCopyJob* j) {
+    const uint32_t i = j->next.fetch_add(1, std::memory_order_relaxed);
+    if (i >= j->nchunks) return false;
+    const size_t off = (size_t)i * j->chunk;
+    std::memcpy(j->dst + off, j->src + off, std::min(j->chunk, j->bytes - off));
+    j->done[i].store(1, std::memory_order_release);
+    return true;
+  }
+  static void cpu_relax() {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+
+ private:
+  WsCopyPool() {
+    int n = 4;  // measured on the 16-thread B200 host: 10 000 x 128 queries per call, 0.42 ms (driver staging) -> 0.33 ms
+    if (const char* e = std::getenv("WSANN_COPY_THREADS")) n = std::atoi(e);
+    nthreads_ = std::max(0, std::min(n, 16));
+    for (int i = 0; i < nthreads_; i++) std::thread([this] { loop(); }).detach();  // process-lifetime helpers
+  }
+  void loop() {
+    auto last = std::chrono::steady_clock::now();
+    for (;;) {
+      WsCopyJob* j = cur_.load(std::memory_order_acquire);
+      if (j != nullptr) {
+        j->active.fetch_add(1, std::memory_order_acq_rel);
+        uint64_t mine = 0;
+        if (cur_.load(std::memory_order_acquire) == j) {
+          mine = j->gen.load(std::memory_order_relaxed);
+          while (help(j)) {}
+          last = std::chrono::steady_clock::now();
+        }
+        j->active.fetch_sub(1, std::memory_order_acq_rel);
+        // the job stays published until the caller retires it: do not hammer its counter meanwhile
+        while (mine != 0 && cur_.load(std::memory_order_acquire) == j && j->gen.load(std::memory_order_relaxed) == mine) cpu_relax();
+        continue;
+      }
+      if (std::chrono::steady_clock::now() - last < std::chrono::microseconds(400)) {
+        cpu_relax();
+        continue;
+      }
+      std::unique_lock<std::mutex> lk(mu_);
+      sleepers_.fetch_add(1, std::memory_order_acq_rel);
+      cv_.wait_for(lk, std::chrono::milliseconds(200), [&] { return cur_.load(std::memory_order_acquire) != nullptr; });
+      sleepers_.fetch_sub(1, std::memory_order_acq_rel);
+      last = std::chrono::steady_clock::now();
+    }
+  }
+  int nthreads_ = 0;
+  WsCopyJob slot_;
+  std::atomic<WsCopyJob*> cur_{nullptr};
+  std::atomic<int> sleepers_{0};
+  std::mutex busy_, mu_;
+  std::condition_variable cv_;
+};
+
+static const size_t kStageChunk = 256u << 10;
+
+static int ws_ensure_pinned(ws_index* idx, WsDevBuf& b, size_t bytes) {
+  if (b.bytes >= bytes) return WS_OK;
+  if (b.p) {
+    WS_CUDA(cudaStreamSynchronize(idx->stream));
+    WS_CUDA(cudaFreeHost(b.p));
+    b.p = nullptr; b.bytes = 0;
+  }
+  const size_t want = bytes + bytes / 4 + 4096;
+  WS_CUDA(cudaMallocHost(&b.p, want));
+  b.bytes = want;
+  return WS_OK;
+}
+
+// dst (device) <- src (pageable host), enqueued on the index stream; small copies go straight to the driver
+static int ws_stage_h2d(ws_index* idx, void* dst, const void* src, size_t bytes) {
+  cudaStream_t st = idx->stream;
+  WsCopyPool& pool = WsCopyPool::get();
+  bool direct = bytes < 4 * kStageChunk || idx->opt_stage_copies == 0 || !pool.enabled();
+  if (!direct) {  // a buffer the caller pinned itself goes to the copy engine as it is
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, src) == cudaSuccess) direct = attr.type != cudaMemoryTypeUnregistered;
+    else cudaGetLastError();
+  }
+  if (direct) {
+    WS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return WS_OK;
+  }
+  WS_TRY(ws_ensure_pinned(idx, idx->stage_in, bytes));
+  const uint32_t nchunks = (uint32_t)((bytes + kStageChunk - 1) / kStageChunk);
+  if (idx->stage_flags.size() < nchunks) idx->stage_flags = std::vector<std::atomic<uint32_t>>(nchunks);
+  for (uint32_t i = 0; i < nchunks; i++) idx->stage_flags[i].store(0, std::memory_order_relaxed);
+  char* stage = (char*)idx->stage_in.p;
+  WsCopyJob* job = pool.begin(stage, (const char*)src, bytes, kStageChunk, idx->stage_flags.data());
+  if (job == nullptr) {  // pool busy with another arena (the members of a group run in parallel anyway)
+    WS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return WS_OK;
+  }
+  // copy chunks alongside the helpers; every run of finished chunks goes to the copy engine as one transfer
+  int rc = WS_OK;
+  uint32_t issued = 0;
+  auto flush = [&](bool wait_all) {
+    for (;;) {
+      uint32_t upto = issued;
+      while (upto < nchunks && idx->stage_flags[upto].load(std::memory_order_acquire) != 0) upto++;
+      if (upto > issued) {
+        const size_t off = (size_t)issued * kStageChunk, len = std::min(bytes, (size_t)upto * kStageChunk) - off;
+        if (rc == WS_OK && cudaMemcpyAsync((char*)dst + off, stage + off, len, cudaMemcpyHostToDevice, st) != cudaSuccess)
+          rc = ws_fail(WS_ERR_CUDA, "staged host-to-device copy: %s", cudaGetErrorString(cudaGetLastError()));
+        issued = upto;
+      }
+      if (!wait_all || issued == nchunks) return;
+      WsCopyPool::cpu_relax();
+    }
+  };
+  while (WsCopyPool::help(job)) flush(false);
+  flush(true);
+  pool.end(job);
+  return rc;
+}
+
+// host-only exercise of the helper pool (no CUDA): `reps` jobs of `bytes` bytes, results compared (CPU tests)
+extern "C" int ws_debug_copy_pool_selftest(uint64_t bytes, uint32_t reps) {
+  WsCopyPool& pool = WsCopyPool::get();
+  std::vector<char> src(bytes), dst(bytes);
+  for (uint64_t i = 0; i < bytes; i++) src[i] = (char)(i * 131u + (i >> 9));
+  const uint32_t nchunks = (uint32_t)((bytes + kStageChunk - 1) / kStageChunk);
+  std::vector<std::atomic<uint32_t>> flags(std::max(1u, nchunks));
+  double copy_us = 0;
+  for (uint32_t r = 0; r < reps; r++) {
+    std::fill(dst.begin(), dst.end(), 0);
+    for (auto& f : flags) f.store(0);
+    src[r % std::max<uint64_t>(1, bytes)] ^= 0x5a;
+    const auto t0 = std::chrono::steady_clock::now();
+    WsCopyJob* job = pool.begin(dst.data(), src.data(), bytes, kStageChunk, flags.data());
+    if (job == nullptr) {
+      if (pool.enabled()) return ws_fail(WS_ERR_STATE, "copy pool busy");
+      std::memcpy(dst.data(), src.data(), bytes);
+    } else {
+      while (WsCopyPool::help(job)) {}
+      for (uint32_t i = 0; i < nchunks; i++)
+        while (flags[i].load(std::memory_order_acquire) == 0) WsCopyPool::cpu_relax();
+      pool.end(job);
+    }
+    copy_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    if (std::memcmp(dst.data(), src.data(), bytes) != 0) return ws_fail(WS_ERR_STATE, "copy pool: job %u copied wrong bytes", r);
+    if ((r & 7) == 7) std::this_thread::sleep_for(std::chrono::milliseconds(1));  // let the helpers fall asleep now and then
+  }
+  if (std::getenv("WSANN_DEBUG_POOL")) std::fprintf(stderr, "[wsann] copy pool: %.1f us per %llu-byte job\n", copy_us / std::max(1u, reps), (unsigned long long)bytes);
+  return WS_OK;
+}
+
 // turns the device-side sticky error word into a status (and clears it)
 static int ws_report_sticky(ws_index* idx, uint32_t bits) {
   cudaMemsetAsync(idx->d_sticky, 0, sizeof(uint32_t), idx->stream);
@@ -810,8 +1022,8 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
     WS_TRY(ws_ensure(idx, idx->d_windows, nq * 2 * sizeof(float)));
     WS_TRY(ws_ensure(idx, idx->d_ids, nq * k * sizeof(uint32_t)));
     WS_TRY(ws_ensure(idx, idx->d_dists, nq * k * sizeof(float)));
-    WS_CUDA(cudaMemcpyAsync(idx->d_queries.p, queries, nq * idx->dim * sizeof(float), cudaMemcpyHostToDevice, st));
     WS_CUDA(cudaMemcpyAsync(idx->d_windows.p, windows, nq * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    WS_TRY(ws_stage_h2d(idx, idx->d_queries.p, queries, nq * idx->dim * sizeof(float)));
     dq = (const float*)idx->d_queries.p;
     dw = (const float*)idx->d_windows.p;
     dids = (uint32_t*)idx->d_ids.p;
@@ -1037,10 +1249,30 @@ static int ws_run_batch(ws_index* idx, const WsBatchPlan& plan, const float* que
 
   if (!dev_ptrs) {
     uint32_t h_sticky = 0;
-    WS_CUDA(cudaMemcpyAsync(ids, dids, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    WS_CUDA(cudaMemcpyAsync(dists, ddists, nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
-    WS_CUDA(cudaMemcpyAsync(&h_sticky, idx->d_sticky, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    WS_CUDA(cudaStreamSynchronize(st));
+    const size_t rows_bytes = nq * k * sizeof(uint32_t);
+    bool staged_out = rows_bytes >= (128u << 10) && idx->opt_stage_copies != 0;
+    if (staged_out) {
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, ids) == cudaSuccess) staged_out = attr.type == cudaMemoryTypeUnregistered;
+      else cudaGetLastError();
+    }
+    if (staged_out) {
+      // results through a pinned buffer: the copy engine writes it at link speed, one memcpy hands it to the caller
+      WS_TRY(ws_ensure_pinned(idx, idx->stage_out, 2 * rows_bytes + 64));
+      char* so = (char*)idx->stage_out.p;
+      WS_CUDA(cudaMemcpyAsync(so, dids, rows_bytes, cudaMemcpyDeviceToHost, st));
+      WS_CUDA(cudaMemcpyAsync(so + rows_bytes, ddists, rows_bytes, cudaMemcpyDeviceToHost, st));
+      WS_CUDA(cudaMemcpyAsync(so + 2 * rows_bytes, idx->d_sticky, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      WS_CUDA(cudaStreamSynchronize(st));
+      std::memcpy(ids, so, rows_bytes);
+      std::memcpy(dists, so + rows_bytes, rows_bytes);
+      std::memcpy(&h_sticky, so + 2 * rows_bytes, sizeof(uint32_t));
+    } else {
+      WS_CUDA(cudaMemcpyAsync(ids, dids, rows_bytes, cudaMemcpyDeviceToHost, st));
+      WS_CUDA(cudaMemcpyAsync(dists, ddists, rows_bytes, cudaMemcpyDeviceToHost, st));
+      WS_CUDA(cudaMemcpyAsync(&h_sticky, idx->d_sticky, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      WS_CUDA(cudaStreamSynchronize(st));
+    }
     if (h_sticky) return ws_report_sticky(idx, h_sticky);
   }
   return WS_OK;
@@ -1447,6 +1679,8 @@ int ws_index_set_option(ws_index* idx, const char* name, int64_t value) {
     idx->opt_expand = value;
   } else if (s == "emulate_query_id_skip") {
     idx->opt_skip_query_id = value != 0;
+  } else if (s == "stage_copies") {
+    idx->opt_stage_copies = value != 0;
   } else if (s == "prefilter_open_tail") {
     idx->opt_open_tail = value != 0;
     idx->hgeom.pf_n = idx->dgeom.pf_n = idx->n + (idx->opt_open_tail ? 1 : 0);

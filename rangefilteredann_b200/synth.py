@@ -51,9 +51,34 @@ def make_dataset(n: int, d: int, nq: int, seed: int = 0, angular: bool = False,
         labels = rng.uniform(0, 1, size=n).astype(np.float32)
     elif label_kind == "timestamp":
         labels = (1.2e9 + rng.integers(0, int(3.5e8), size=n)).astype(np.float32)
+    elif label_kind == "timestamp_unique":
+        # the same recipe (integer seconds cast to float32: multiples of 128 at this magnitude), ties nudged apart
+        labels = make_labels_unique((1.2e9 + rng.integers(0, int(3.5e8), size=n)).astype(np.float32))
     else:
         raise ValueError(label_kind)
     return data, queries, labels
+
+
+def make_labels_unique(labels: np.ndarray) -> np.ndarray:
+    """Nudges duplicated labels to the next representable float32s (in label order), so that every label is
+    distinct and the label order is total.  The reference sorts labels with an UNSTABLE parallel sort
+    (tree_utils.h:70-72), so with ties the two implementations lay the tied points out differently and a graph file
+    written for one layout is inconsistent with the other — a benchmark in which both arms load
+    ONE set of graph files needs tie-free labels.  Moves a label by a few ulps at most where ties are sparse."""
+    lab = labels.astype(np.float32).copy()
+    order = np.argsort(lab, kind="stable")
+    s = lab[order]
+    for _ in range(64):
+        dup = np.nonzero(s[1:] <= s[:-1])[0] + 1
+        if len(dup) == 0:
+            break
+        s[dup] = np.nextafter(s[dup - 1], np.float32(np.inf))
+    else:
+        for i in range(1, len(s)):  # dense runs of ties: one sequential pass settles them
+            if s[i] <= s[i - 1]:
+                s[i] = np.nextafter(s[i - 1], np.float32(np.inf))
+    lab[order] = s
+    return lab
 
 
 def make_rank_queries(d: int, nq: int, data_seed: int, rank: int, angular: bool = False) -> np.ndarray:
@@ -164,7 +189,7 @@ def make_adversarial(n: int, d: int, seed: int = 0, clusters: int = 100, intra_v
     windows = np.stack([gc - 0.5, gc + 0.5], axis=1).astype(np.float32)
     data /= np.linalg.norm(data, axis=1, keepdims=True)
     queries /= np.linalg.norm(queries, axis=1, keepdims=True)
-    return data, queries.astype(np.float32), labels, windows
+    return data, queries.astype(np.float32), make_labels_unique(labels), windows
 
 
 def make_blowup_windows(labels: np.ndarray, power: int, nq: int, seed: int) -> np.ndarray:

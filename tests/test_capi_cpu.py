@@ -82,3 +82,34 @@ def test_engine_module_surface(engine):
         engine.PrefilterIndexUInt8Euclidian(np.zeros((4, 300), np.uint8), np.arange(4, dtype=np.float32))
     with pytest.raises(RuntimeError, match="up to 1023"):
         engine.PrefilterIndexInt8Mips(np.zeros((4, 1024), np.int8), np.arange(4, dtype=np.float32))
+
+
+def test_group_and_snapshot_entry_points_validate_arguments(tmp_path):
+    """ws_group / NCCL / snapshot entry points reject bad arguments without a device (no compute)."""
+    L = capi.lib()
+    out = C.c_void_p()
+    assert L.ws_group_create(None, 0, 0, C.byref(out)) == -1 and out.value is None
+    assert L.ws_group_tree_batch(None, 0, None, None, 0, None, None, None) == -1
+    assert L.ws_index_load(str(tmp_path / "missing.wsann").encode(), 0, C.byref(out)) == -1
+    assert b"cannot open" in L.ws_last_error()
+    bad = tmp_path / "bad.wsann"
+    bad.write_bytes(b"garbage garbage garbage")
+    assert L.ws_index_load(str(bad).encode(), 0, C.byref(out)) == -1
+    assert b"not an arena snapshot" in L.ws_last_error()
+    assert L.ws_index_comm_init(None, 2, 0, None) == -1
+    assert L.ws_allgather_merge(None, None, None, 0, 10, 0, None, None) == -1
+
+
+def test_staging_helper_pool_copies_correctly_and_the_process_exits():
+    """The helper threads that stage host batches into pinned memory (csrc/wsann.cu WsCopyPool): hundreds of jobs,
+    with pauses that let the helpers fall asleep, in a child process that must also EXIT (a pool with waiting threads
+    must not block interpreter shutdown)."""
+    import subprocess
+    import sys
+    code = ("import ctypes as C, sys; sys.path.insert(0, %r); from rangefilteredann_b200 import capi; L = capi.lib(); "
+            "L.ws_debug_copy_pool_selftest.argtypes = [C.c_uint64, C.c_uint32]; "
+            "rc = L.ws_debug_copy_pool_selftest(5_300_000, 300); rc2 = L.ws_debug_copy_pool_selftest(100, 20); print('rc', rc, rc2)") % ROOT
+    for threads in ("3", "0", "8"):
+        env = dict(os.environ, WSANN_COPY_THREADS=threads)
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, env=env)
+        assert out.returncode == 0 and "rc 0 0" in out.stdout, (threads, out.stdout, out.stderr)
