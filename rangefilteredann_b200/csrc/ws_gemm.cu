@@ -778,6 +778,7 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmB, WsGemmArgs A) {
           wsg_tc_fence_before();
           __syncwarp();
           if (lane == 0) wsg_mbar_arrive(&S->acc_empty[acc]);
+          if (A.dbg & 4) { if (++acc == A.nacc) { acc = 0; acc_phase ^= 1; } continue; }  // timing: TMEM read only
           const float4* nr = reinterpret_cast<const float4*>(my_norm);
 #pragma unroll
           for (int j = 0; j < 8; j++) {
@@ -794,7 +795,7 @@ ws_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmB, WsGemmArgs A) {
 #pragma unroll
           for (int g = 0; g < 8; g++) m4[g] = fminf(fminf(s[4 * g], s[4 * g + 1]), fminf(s[4 * g + 2], s[4 * g + 3]));
           const float m = fminf(fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3])), fminf(fminf(m4[4], m4[5]), fminf(m4[6], m4[7])));
-          if (__any_sync(0xffffffffu, m < thr)) {
+          if (__any_sync(0xffffffffu, m < thr) && !(A.dbg & 8)) {  // dbg 8 (timing): filter, but keep nothing
 #pragma unroll
             for (int g = 0; g < 8; g++) {
               if (!__any_sync(0xffffffffu, m4[g] < thr)) continue;

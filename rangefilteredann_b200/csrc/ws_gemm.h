@@ -124,7 +124,8 @@ struct WsGemmArgs {
   uint32_t acc_col0;    // first accumulator column (128 or 256)
   uint32_t k;
   uint32_t dbg;         // timing experiments only (results invalid): 1 = epilogue releases stages without
-                        // reading them, 2 = producer signals point blocks without loading them
+                        // reading them, 2 = producer signals point blocks without loading them, 4 = epilogue reads
+                        // TMEM and releases, nothing else, 8 = reads, converts and filters but keeps no candidate
 };
 
 struct WsGemmRerankArgs {
