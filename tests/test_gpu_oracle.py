@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import DATA_CACHE, GOLDEN
+from conftest import DATA_CACHE, GOLDEN, REF_CACHE, ROOT
 from golden_cases import TINY, TINY_MIPS, tiny_cases, tiny_mips_cases
 from oracle_api import Oracle
 from rangefilteredann_b200 import capi, synth
@@ -219,11 +219,20 @@ def test_rejects_unsupported(tiny, engine):
         engine.PostfilterVamanaIndexFloatEuclidian(tiny.data, tiny.labels, engine.BuildParams(64, 500, 1.0, "/nonexistent/"))
 
 
-@pytest.mark.skipif(not os.path.isdir(os.path.join(DATA_CACHE, "small", "wst")), reason="data_cache/small not present")
-def test_small_config_bit_exact(engine):
-    """20 000 x 32, 6-row tree (reference-built graphs under data_cache/, git-ignored)."""
+def test_small_config_bit_exact(engine, tmp_path_factory):
+    """20 000 x 32, 6-row tree + super tree + flat index on REFERENCE-BUILT graphs (ref_cache/small, written by
+    oracle/build_ref_cache.py with the unmodified reference builder; rebuilt on the host — under a minute — when the
+    directory did not travel with the snapshot)."""
     cfg = dict(n=20000, d=32, nq=256, seed=3, cutoff=1000)
-    p = Pair(engine, cfg, os.path.join(DATA_CACHE, "small"))
+    root = os.path.join(REF_CACHE, "small")
+    if not all(os.path.isdir(os.path.join(root, kind)) and os.listdir(os.path.join(root, kind)) for kind in ("wst", "super", "flat")):
+        import subprocess
+        import sys
+        out = str(tmp_path_factory.mktemp("ref_cache_small"))
+        subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "build_ref_cache.py"), "small", "--kinds", "wst,super,flat", "--out", out],
+                       check=True, stdout=subprocess.DEVNULL)
+        root = os.path.join(out, "small")
+    p = Pair(engine, cfg, root)
     for power in (-10, -6, -3, -1, 0):
         w = synth.make_windows(p.labels, power, 128, seed=300 + power)
         q = p.queries[:128]
