@@ -4,7 +4,7 @@
  * This is the LOWER face of the drop-in boundary.  The reference
  * (JoshEngels/RangeFilteredANN) has no FFI layer of its own: its boundary is the
  * pybind11 module `window_ann` (python_bindings/python_bindings.cpp:160-238) whose
- * classes call header-only C++ (`batch_search` in src/*.h).  Every entry point below
+ * classes call header-only C++ (`batch_search` in the headers under src/).  Every entry point below
  * names the reference function(s) whose work it replaces.  The host-side C++ index
  * classes in rangefilteredann_b200/csrc/host/ (same class names / constructor /
  * batch_search signatures as the reference) are the only intended callers; the
