@@ -820,7 +820,16 @@ class WsCopyPool {
 
  private:
   WsCopyPool() {
-    int n = 4;  // measured on the 16-thread B200 host: 10 000 x 128 queries per call, 0.42 ms (driver staging) -> 0.33 ms
+    // Measured on the 16-thread B200 host: 10 000 x 128 queries per call, 0.42 ms (driver staging) -> 0.33 ms with 4
+    // helpers.  Helpers spin while batches follow each other, so a box that runs one process per GPU must not be
+    // oversubscribed: at most half of the hardware threads, shared between the visible GPUs.
+    int n = 4;
+    {
+      const unsigned hw = std::thread::hardware_concurrency();
+      int ngpu = 0;
+      if (cudaGetDeviceCount(&ngpu) != cudaSuccess) { cudaGetLastError(); ngpu = 1; }
+      if (hw > 0) n = std::max(1, std::min(4, (int)(hw / (2u * (unsigned)std::max(1, ngpu)))));
+    }
     if (const char* e = std::getenv("WSANN_COPY_THREADS")) n = std::atoi(e);
     nthreads_ = std::max(0, std::min(n, 16));
     for (int i = 0; i < nthreads_; i++) std::thread([this] { loop(); }).detach();  // process-lifetime helpers
