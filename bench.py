@@ -1,25 +1,30 @@
 #!/usr/bin/env python
-"""bench.py — BASELINE.json's metric on BASELINE.json's config, per the driver contract.
+"""bench.py — BASELINE.json's metric on BASELINE.json's configurations, per the driver contract.
 
-  python bench.py --gpus N --steps K --warmup W            this engine (one rank per GPU)
-  python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU path
+  python bench.py --gpus N --steps K --warmup W            this engine (one rank per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU path (oracle/_ref)
 
-Metric: QPS at recall@10 >= 0.95 over the 17 filter fractions 2^-16..2^0 (k = 10, 10 000
-queries per fraction).  One "step" = one pass over all 17 fractions: for each fraction the
-batch of `nq` queries is answered by the fastest (method, beam, final_multiply) operating
-point that reaches recall@10 >= 0.95 — methods: prefilter (task path, the one-launch kernel
-"prefilter_direct", or the tensor-core sweep "prefilter_tc" — same rows), range-filter tree ("fenwick"), optimized postfilter — chosen
-in an untimed sweep, exactly the pareto rule of the
-reference's plots (experiments/plot.py:14-28).  value = queries answered per second.
+Metric: QPS at recall@10 >= 0.95 over the 17 filter fractions 2^-16..2^0 (k = 10, 10 000 queries per
+fraction).  One "step" = one pass over all 17 fractions: for each fraction the batch of `nq` queries is answered
+by the fastest (method, beam, final_multiply) operating point that reaches recall@10 >= 0.95 — methods:
+prefilter (as the engine routes the batch by itself: one-launch kernel, task path or tensor-core sweep — same
+rows), range-filter tree ("fenwick"), optimized postfilter (config 3: super optimized postfilter tree) — chosen
+in an untimed sweep, exactly the pareto rule of the reference's plots (experiments/plot.py:14-28).
+value = queries answered per second.
 
-  value      inputs resident in HBM, CUDA-event timed on the engine's stream
-  e2e        same step through the public pybind `batch_search` with pinned HOST buffers
-             (H2D of queries+windows and D2H of ids+dists inside the timed region)
-  roofline   dominant kernel, algorithmic bytes / CUDA-event kernel time
+  value         inputs resident in HBM, CUDA-event timed on the engine's stream
+  e2e           same step through the pybind classes the reference driver calls, ordinary pageable numpy arrays,
+                default engine options (H2D of queries + windows and D2H of ids + dists inside the timed region)
+  roofline      dominant kernel, algorithmic bytes / flops / CUDA-event kernel time
   cpu_baseline  the unmodified reference (oracle/_ref) on the box's host cores, bounded sample
+  parity        the reference's rows against the engine's on the same queries / windows / graph files
+                (prefilter rows equal up to 1e-5 ties; recall within 0.005 at equal method, beam, multiply)
 
-Multi-GPU (torchrun): index replicated, every rank answers its own batch (weak scaling, no
-data-path collective); time = max over ranks.
+Default (what the driver runs): --config c2 (BASELINE.json configs[1]).  Other configurations: c1, c3 (GloVe shape,
+super tree), c4 (RedCaps shape; --rows scales it), c5 / c5adv (Deep shape / adversarial labels).
+Multi-GPU: default = index replicated, every rank answers its own batch (weak scaling, no data-path collective);
+--scaling strong = ONE batch cut into N slices; --mode label_shard = contiguous label ranges, in-library
+ncclAllGather + merge; --mode group = ONE process, N GPUs behind the public batch_search call.  Time = max over ranks.
 """
 from __future__ import annotations
 
